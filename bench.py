@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2] [--scaling weak|strong]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on host cores
+
+One step = one pass of the hot path over one synthetic ERP pair:
+    2-NN matching (+0.3 ratio test, ordered compaction) -> gather matched keypoints -> bearings
+    -> minimal-sample eight-point RANSAC (Philox samples, solve, score, best) -> refit.
+Workload (config.workload): BASELINE.json configs[2] "synthetic 8K ERP pair: 100k x 100k SURF-64
+2-NN + 1M-hyp RANSAC" -- the configuration north_star's target is quoted on; it fits one GPU.
+
+`value` is BASELINE.json's first metric, 2-NN dist-evals/s, over the matching stage of the step
+(device-resident inputs); the second metric, RANSAC hyps/s, is reported beside it
+(`ransac_hyps_per_s`), and `ms_per_step` is the whole step.  `e2e` is the same metric through the
+host-buffer C ABI call the reference-facing wrappers make (H2D/D2H inside the timed region).
+
+Scaling: "weak" (default, one cfg-sized ERP pair per GPU, no data-path collective -- the frame-pair
+sharding of configs[4]) or "strong" (north_star's split of ONE pair: query rows and hypothesis ids
+partitioned per rank, matches all-gathered, best model max-all-reduced).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nq, nt, dim, W, H, hypotheses)
+    "cfg2": dict(nq=20000, nt=20000, dim=64, W=4096, H=2048, hyps=10000,
+                 desc="synthetic 4K ERP pair: 20k x 20k SURF-64 2-NN + 8-pt RANSAC 10k hyps"),
+    "cfg3": dict(nq=100000, nt=100000, dim=64, W=8192, H=4096, hyps=1000000,
+                 desc="synthetic 8K ERP pair: 100k x 100k SURF-64 2-NN + 1M-hyp RANSAC"),
+}
+RATIO, TAU, METRIC, SAMPLE = 0.3, 0.002, 0, 8
+
+
+def make_pair(cfg, seed):
+    """Descriptors with 50 % planted matches, and keypoints such that planted pairs are
+    geometric correspondences of a known relative pose (30 % of them gross outliers)."""
+    from erp_match_eightpoint_test_b200 import synth
+
+    q, t, planted = synth.descriptor_pair(cfg["nq"], cfg["nt"], cfg["dim"], seed=seed)
+    n_pl = int((planted >= 0).sum())
+    kp = synth.keypoint_pair(n_pl, cfg["W"], cfg["H"], seed=seed + 100)
+    rng = np.random.Generator(np.random.Philox(seed + 200))
+    left = (rng.uniform(0, 1, (cfg["nq"], 2)) * [cfg["W"], cfg["H"] - 1]).astype(np.float32)
+    right = (rng.uniform(0, 1, (cfg["nt"], 2)) * [cfg["W"], cfg["H"] - 1]).astype(np.float32)
+    qi = np.nonzero(planted >= 0)[0]
+    left[qi] = kp["left_xy"]
+    right[planted[qi]] = kp["right_xy"]
+    return dict(q=q, t=t, planted=planted, left=left, right=right, E=kp["E"], inlier=kp["inlier"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(src="measured", hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]))
+    return dict(src="fallback", hbm=6650.0, bf16=1590.0, bf16_sus=1400.0)   # B200_PROFILING.md fallback
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port; the reference itself needs
+# OpenCV 3.4 C++ + xfeatures2d, which this image does not have -- DESIGN.md)
+# --------------------------------------------------------------------------------------------
+def cpu_sample(cfg, pair, q_rows=1024, hyps=4096):
+    """A bounded sample of the workload: q_rows queries against the full train set, and
+    `hyps` RANSAC hypotheses scored over the planted correspondences."""
+    import oracle as O
+
+    q = pair["q"][:q_rows]
+    t0 = time.perf_counter()
+    m = O.match(q, pair["t"], RATIO, False)
+    t_match = time.perf_counter() - t0
+    qi = np.nonzero(pair["planted"] >= 0)[0]
+    l = O.bearings(pair["left"][qi], cfg["W"], cfg["H"])
+    r = O.bearings(pair["right"][pair["planted"][qi]], cfg["W"], cfg["H"])
+    t0 = time.perf_counter()
+    O.ransac(l, r, seed=1, hyp0=0, H=hyps, S=SAMPLE, metric=METRIC, tau=TAU, want_counts=False)
+    t_ransac = time.perf_counter() - t0
+    return dict(evals_per_s=len(q) * cfg["nt"] / t_match, hyps_per_s=hyps / t_ransac, t_match=t_match, t_ransac=t_ransac,
+                n_matches=len(m), cores=O.num_threads(), corr=len(l),
+                sample=f"{len(q)} of {cfg['nq']} queries x {cfg['nt']} train (exact brute-force 2-NN + ratio, fp64 accumulate); "
+                       f"{hyps} of {cfg['hyps']} hypotheses x {len(l)} correspondences")
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pair = make_pair(cfg, 0xE8B0 + 3)
+    for _ in range(args.warmup):
+        cpu_sample(cfg, pair, 256, 512)
+    tm = tr = 0.0
+    s = None
+    for _ in range(args.steps):
+        s = cpu_sample(cfg, pair)
+        tm += s["t_match"]; tr += s["t_ransac"]
+    value = args.steps * 1024 * cfg["nt"] / tm
+    line = {
+        "impl": "reference", "metric": "2nn_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tm + tr) / args.steps, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 data, f64 accumulate", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "engine": "CPU oracle port of the reference path (OpenMP)", "sample": s["sample"]},
+        "ransac_hyps_per_s": args.steps * 4096 / tr,
+        "cpu_baseline": {"value": value, "unit": "dist-evals/s", "cores": s["cores"], "kind": "port", "sample": s["sample"],
+                         "ransac_hyps_per_s": args.steps * 4096 / tr},
+        "e2e": {"value": value, "unit": "dist-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    import erp_match_eightpoint_test_b200 as erp
+    from erp_match_eightpoint_test_b200 import sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = erp.Context(local)
+    if args.engine is not None:
+        ctx.set_engine(args.engine)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    strong = args.scaling == "strong" and world > 1
+
+    # ---- inputs.  weak: every rank owns a whole pair (own seed).  strong: one pair, query rows split.
+    pair = make_pair(cfg, 0xE8B0 + 3 + (0 if strong else rank))
+    nq_all, nt, dim = cfg["nq"], cfg["nt"], cfg["dim"]
+    qlo, qhi = sharding.shard_range(nq_all, rank, world) if strong else (0, nq_all)
+    nq = qhi - qlo
+    hlo, hhi = sharding.shard_range(cfg["hyps"], rank, world) if strong else (0, cfg["hyps"])
+    h_q = torch.from_numpy(pair["q"][qlo:qhi]).pin_memory()
+    h_t = torch.from_numpy(pair["t"]).pin_memory()
+    h_left = torch.from_numpy(pair["left"]).pin_memory()
+    h_right = torch.from_numpy(pair["right"]).pin_memory()
+
+    with torch.cuda.stream(stream):
+        d_q, d_t = h_q.to(dev, non_blocking=True), h_t.to(dev, non_blocking=True)
+        d_left, d_right = h_left.to(dev, non_blocking=True), h_right.to(dev, non_blocking=True)
+        d_matches = torch.empty((nq_all, 4), dtype=torch.int32, device=dev)          # erp_dmatch records
+        d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_l3 = torch.empty((nq_all, 3), dtype=torch.float64, device=dev)
+        d_r3 = torch.empty((nq_all, 3), dtype=torch.float64, device=dev)
+        d_l4 = torch.empty((nq_all, 4), dtype=torch.float32, device=dev)
+        d_r4 = torch.empty((nq_all, 4), dtype=torch.float32, device=dev)
+        d_packed = torch.zeros(1, dtype=torch.int64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                 # > 126 MB L2
+        h_n = torch.zeros(1, dtype=torch.int32).pin_memory()
+        h_packed = torch.zeros(1, dtype=torch.int64).pin_memory()
+        if strong:
+            counts = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
+            gathered = torch.empty((world, nq_all // world + 1, 4), dtype=torch.int32, device=dev)
+    stream.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(timed):
+        """One pass of the hot path with device-resident inputs.  Returns (events, result)."""
+        e0, e1, e2 = ev(), ev(), ev()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            ctx.knn2_match_dev(d_q, nq, d_t, nt, dim, RATIO, False, d_matches, d_n)
+            e1.record(stream)
+            h_n.copy_(d_n, non_blocking=True)
+            stream.synchronize()                       # the match count sizes the RANSAC launches
+            m = int(h_n.item())
+            if strong:
+                # rank-ordered all-gather of the per-rank match lists keeps ascending queryIdx;
+                # local query indices become global by adding each rank's shard offset
+                cap = gathered.shape[1]
+                dist.all_gather_into_tensor(gathered.view(world * cap, 4), d_matches[:cap].contiguous())
+                dist.all_gather(counts, d_n)
+                ns = [int(c.item()) for c in counts]
+                parts = []
+                for r in range(world):
+                    p = gathered[r, : ns[r]].clone()
+                    p[:, 0] += sharding.shard_range(nq_all, r, world)[0]
+                    parts.append(p)
+                allm = torch.cat(parts)
+                m = allm.shape[0]
+                d_matches[:m].copy_(allm)
+            ctx.gather_bearings_dev(d_matches, m, d_left, d_right, 8, 0, cfg["W"], cfg["H"], d_l3, d_r3, d_l4, d_r4)
+            ctx.ransac_local_dev(d_l3, d_r3, d_l4, d_r4, m, 1, hlo, hhi - hlo, SAMPLE, METRIC, TAU, d_packed)
+            if strong:
+                sharding.allreduce_best(d_packed, dist)        # the one 8-byte collective
+            h_packed.copy_(d_packed, non_blocking=True)
+            stream.synchronize()
+            res = ctx.ransac_finish_dev(d_l3, d_r3, d_l4, d_r4, m, 1, int(h_packed.item()), SAMPLE, METRIC, TAU)
+            e2.record(stream)
+        return (e0, e1, e2), m, res
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 0)):
+        flush_l2()
+        step(False)
+    barrier()
+
+    # ---- timed region: exactly K steps, L2 flushed between them (flush excluded from the sums)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launch_count
+    t_match = t_ransac = t_kernel = 0.0
+    m = 0
+    res = None
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        (e0, e1, e2), m, res = step(True)
+        torch.cuda.synchronize()
+        t_match += e0.elapsed_time(e1)
+        t_ransac += e1.elapsed_time(e2)
+        t_kernel += ctx.last_knn_kernel_ms()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+
+    # max over ranks of the device-timed sums
+    tt = torch.tensor([t_match, t_ransac, t_kernel], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_match, t_ransac, t_kernel = [float(x) for x in tt.tolist()]
+
+    # ---- end-to-end through the host-buffer C ABI (what the C++ class wrappers call)
+    pq, pt = h_q.numpy(), h_t.numpy()
+    qi_all = None
+    t_e2e_match = t_e2e_ransac = 0.0
+    e2e_steps = max(1, min(args.steps, 3))
+    for it in range(e2e_steps + 1):
+        torch.cuda.synchronize()
+        a = time.perf_counter()
+        mt = ctx.knn2_match(pq, pt, RATIO, False)                                     # H2D q,t; D2H matches
+        b = time.perf_counter()
+        lxy = pair["left"][mt["queryIdx"] + qlo]
+        rxy = pair["right"][mt["trainIdx"]]
+        l3 = ctx.bearings(lxy, cfg["W"], cfg["H"])
+        r3 = ctx.bearings(rxy, cfg["W"], cfg["H"])
+        r_e2e = ctx.ransac(l3, r3, 1, hlo, hhi - hlo, SAMPLE, METRIC, TAU)            # H2D bearings; D2H result + mask
+        c = time.perf_counter()
+        if it > 0:
+            t_e2e_match += b - a
+            t_e2e_ransac += c - b
+    te = torch.tensor([t_e2e_match, t_e2e_ransac], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e_match, t_e2e_ransac = [float(x) for x in te.tolist()]
+    h2d = pq.nbytes + pt.nbytes + 2 * len(mt) * 8 + 2 * len(mt) * 24
+    d2h = len(mt) * 16 + 2 * len(mt) * 24 + len(mt) + 256
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- sanity of the timed work (a number from a wrong result is not a number)
+    n_pl = int((pair["planted"] >= 0).sum())
+    if not strong:
+        assert m == n_pl, (m, n_pl)
+    En = np.asarray(res["E_refit"]).reshape(9)
+    Eg = pair["E"].reshape(9) / np.linalg.norm(pair["E"])
+    En = En / np.linalg.norm(En)
+    e_err = float(min(np.linalg.norm(En - Eg), np.linalg.norm(En + Eg)))
+    assert e_err < 2e-2, e_err
+
+    pk = peaks()
+    units = world * nq * nt if not strong else nq_all * nt
+    hyps_total = (world if not strong else 1) * cfg["hyps"]
+    value = args.steps * units / (t_match * 1e-3)
+    stats = ctx.last_knn_stats()
+    engine = {1: "exact_simt_fp64", 2: "tcgen05_3xtf32"}.get(stats["engine"], str(stats["engine"]))
+    # roofline of the dominant kernel (the distance kernel): algorithmic flops = 2*D per dist-eval
+    k_s = t_kernel * 1e-3 / args.steps
+    achieved = nq * nt * 2.0 * dim / k_s / 1e12
+    peak = pk["bf16"] / 2.0 / 3.0          # measured bf16 dense -> TF32 (1/2) -> three TF32 passes (1/3)
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(engine)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        s = cpu_sample(cfg, pair, q_rows=4096, hyps=16384)
+        cpu = {"value": s["evals_per_s"], "unit": "dist-evals/s", "cores": s["cores"], "kind": "port", "sample": s["sample"],
+               "ransac_hyps_per_s": s["hyps_per_s"], "seconds": s["t_match"] + s["t_ransac"]}
+
+    line = {
+        "metric": "2nn_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (t_match + t_ransac) / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32 data; 3xTF32 tiles + f64 refine"
+        if engine.startswith("tcgen05") else "f32 data; f64 direct-form accumulate", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "engine": engine, "nq_per_gpu": nq, "nt": nt, "dim": dim,
+                   "hyps_per_gpu": hhi - hlo, "correspondences": m, "sample_size": SAMPLE, "ratio": RATIO, "tau": TAU,
+                   "l2": "flushed between timed steps (256 MiB write); inputs 51 MB < 126 MB L2",
+                   "sharding": "query rows + hypothesis ids per rank, all-gather matches, 8-byte max all-reduce" if strong
+                   else "one ERP pair per rank, no collective"},
+        "match_ms": t_match / args.steps, "ransac_ms": t_ransac / args.steps,
+        "ransac_hyps_per_s": args.steps * hyps_total / (t_ransac * 1e-3),
+        "step_dist_evals_per_s": args.steps * units / ((t_match + t_ransac) * 1e-3),
+        "roofline": {"bound": "tensor", "kernel": "distance tiles + fused top-k (" + engine + ")", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel_ms": t_kernel / args.steps,
+                     "peak_from": f"{pk['src']} bf16 {pk['bf16']} TFLOP/s / 2 (tf32) / 3 (3xTF32); algorithmic 2*D flop per dist-eval"},
+        "e2e": {"value": world * nq * nt * e2e_steps / t_e2e_match if not strong else nq_all * nt * e2e_steps / t_e2e_match,
+                "unit": "dist-evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "match_ms": 1e3 * t_e2e_match / e2e_steps, "ransac_ms": 1e3 * t_e2e_ransac / e2e_steps,
+                "ransac_hyps_per_s": hyps_total * e2e_steps / t_e2e_ransac, "steps": e2e_steps,
+                "api": "erp_knn2_match + erp_bearings_from_pixels + erp_ransac (host buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
+        "check": {"matches": m, "planted": n_pl, "E_refit_err": e_err, "inliers": res["count"], "rescanned": stats["rescanned"]},
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--engine", type=int, default=None, help="0 auto, 1 exact SIMT, 2 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_gpu(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,624 @@
+// api.cu -- context management, error reporting, host-pointer entry points (staging + copies)
+// and the pieces of the reference's host logic that stay on the host (random_array replay).
+#include "common.cuh"
+
+#include <stdarg.h>
+
+namespace erp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int Buf::reserve(size_t bytes)
+{
+    if (bytes <= cap) return ERP_OK;
+    release();
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr; cap = 0;
+        set_error("allocation of %zu bytes (%s) failed: %s", want, host ? "pinned" : "device", cudaGetErrorString(e));
+        return ERP_E_CUDA;
+    }
+    cap = want;
+    return ERP_OK;
+}
+
+void Buf::release()
+{
+    if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
+    p = nullptr; cap = 0;
+}
+
+int gram_batch(erp_ctx*, const double*, const double*, int, const int32_t*, int, int, uint64_t, uint64_t, double*);
+int gram_masked(erp_ctx*, const double*, const double*, int, const uint8_t*, double*);
+int solve_batch(erp_ctx*, const double*, int, double*, float*);
+int consensus(erp_ctx*, const float*, int, float*, float*, int32_t*);
+int mask_launch(erp_ctx*, const double*, const float*, const float*, int, int, float, uint8_t*, int32_t*);
+
+// copy a strided host matrix (rows x row_bytes, stride) into dense device memory
+static int upload_rows(erp_ctx* ctx, void* d_dst, const void* src, int rows, size_t row_bytes, size_t stride)
+{
+    if (rows == 0) return ERP_OK;
+    if (stride == row_bytes) ERP_CUDA(cudaMemcpyAsync(d_dst, src, row_bytes * rows, cudaMemcpyHostToDevice, ctx->stream));
+    else ERP_CUDA(cudaMemcpy2DAsync(d_dst, row_bytes, src, stride, row_bytes, rows, cudaMemcpyHostToDevice, ctx->stream));
+    return ERP_OK;
+}
+
+} // namespace erp
+
+using namespace erp;
+
+// ======================================================================================
+ERP_API const char* erp_last_error(void) { return g_err; }
+ERP_API int erp_version(void) { return ERP_B200_VERSION; }
+
+ERP_API int erp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+ERP_API int erp_ctx_create(int device, erp_ctx** out)
+{
+    ERP_ARG(out, ERP_E_ARG, "erp_ctx_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return ERP_E_NO_DEVICE;
+    }
+    ERP_ARG(device >= 0 && device < n, ERP_E_ARG, "erp_ctx_create: device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    ERP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return ERP_E_ARCH;
+    }
+    DeviceGuard g(device);
+    erp_ctx* ctx = new erp_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        delete ctx;
+        return ERP_E_CUDA;
+    }
+    if (cudaEventCreate(&ctx->ev_k0) != cudaSuccess || cudaEventCreate(&ctx->ev_k1) != cudaSuccess) {
+        set_error("cudaEventCreate failed");
+        delete ctx;
+        return ERP_E_CUDA;
+    }
+    *out = ctx;
+    return ERP_OK;
+}
+
+ERP_API void erp_ctx_destroy(erp_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->dev) b.release();
+    for (auto& b : ctx->pinned) b.release();
+    if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+    if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+ERP_API void* erp_ctx_stream(erp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+ERP_API int erp_ctx_device(erp_ctx* ctx) { return ctx ? ctx->device : -1; }
+ERP_API uint64_t erp_ctx_launch_count(erp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+ERP_API int erp_ctx_synchronize(erp_ctx* ctx)
+{
+    ERP_ARG(ctx, ERP_E_ARG, "null context");
+    DeviceGuard g(ctx->device);
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+ERP_API int erp_ctx_set_engine(erp_ctx* ctx, int engine)
+{
+    ERP_ARG(ctx && engine >= ERP_ENGINE_AUTO && engine <= ERP_ENGINE_TCGEN05, ERP_E_ARG, "erp_ctx_set_engine: bad argument");
+    ctx->engine = engine;
+    return ERP_OK;
+}
+
+ERP_API int erp_ctx_last_knn_kernel_ms(erp_ctx* ctx, float* ms)
+{
+    ERP_ARG(ctx && ms, ERP_E_ARG, "erp_ctx_last_knn_kernel_ms: bad argument");
+    DeviceGuard g(ctx->device);
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ERP_CUDA(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+    return ERP_OK;
+}
+
+ERP_API int erp_ctx_last_knn_stats(erp_ctx* ctx, int64_t out[5])
+{
+    ERP_ARG(ctx && out, ERP_E_ARG, "erp_ctx_last_knn_stats: bad argument");
+    memcpy(out, ctx->knn_stats, sizeof ctx->knn_stats);
+    return ERP_OK;
+}
+
+// ======================================================================================
+// matching
+// ======================================================================================
+static int check_knn_args(const char* who, erp_ctx* ctx, int nq, int nt, int dim)
+{
+    ERP_ARG(ctx, ERP_E_ARG, "%s: null context", who);
+    ERP_ARG(nq >= 0 && nt >= 0, ERP_E_ARG, "%s: negative size", who);
+    ERP_ARG(dim > 0 && dim % 4 == 0 && dim <= 512, ERP_E_DIM, "%s: descriptor dimension %d must be a multiple of 4 in [4,512]", who, dim);
+    // knnMatch(k=2) on fewer than 2 train rows throws in the reference (FLANN: knn <= index size)
+    ERP_ARG(nq == 0 || nt >= 2, ERP_E_TOO_FEW_TRAIN, "%s: k=2 needs at least 2 train descriptors, got %d", who, nt);
+    return ERP_OK;
+}
+
+ERP_API int erp_knn2_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                         int32_t* d_idx2, float* d_dist2, double* d_d2)
+{
+    ERP_TRY(check_knn_args("erp_knn2_dev", ctx, nq, nt, dim));
+    if (nq == 0) return ERP_OK;
+    ERP_ARG(d_q && d_t, ERP_E_ARG, "erp_knn2_dev: null descriptors");
+    DeviceGuard g(ctx->device);
+    bool tc = ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_supported(nq, nt, dim));
+    if (ctx->engine == ERP_ENGINE_TCGEN05)
+        ERP_ARG(knn2_tc_supported(nq, nt, dim), ERP_E_DIM, "tcgen05 engine does not support nq=%d nt=%d dim=%d", nq, nt, dim);
+    if (tc) return knn2_tc(ctx, d_q, nq, d_t, nt, dim, d_idx2, d_dist2, d_d2);
+    ctx->knn_stats[0] = ERP_ENGINE_EXACT_SIMT; ctx->knn_stats[1] = 0; ctx->knn_stats[2] = 1; ctx->knn_stats[3] = cdiv(nq, 64);
+    ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    ERP_TRY(knn2_exact(ctx, d_q, nq, d_t, nt, dim, nullptr, 0, 0, d_idx2, d_dist2, d_d2));
+    ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+    return ERP_OK;
+}
+
+namespace erp {
+__global__ void add_offset_kernel(int32_t* v, int n, int off)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && v[i] >= 0) v[i] += off;
+}
+}
+static int add_offset(erp_ctx* ctx, int32_t* v, int n, int off)
+{
+    erp::add_offset_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(v, n, off);
+    ERP_LAUNCH(ctx, "add_offset_kernel");
+    return ERP_OK;
+}
+
+ERP_API int erp_nn1_reverse_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                                int q_offset, int32_t* d_best_q, double* d_best_d2)
+{
+    ERP_ARG(ctx && nq >= 1 && nt >= 0 && d_best_q, ERP_E_ARG, "erp_nn1_reverse_dev: bad argument");
+    ERP_ARG(dim > 0 && dim % 4 == 0 && dim <= 512, ERP_E_DIM, "erp_nn1_reverse_dev: bad dimension %d", dim);
+    if (nt == 0) return ERP_OK;
+    DeviceGuard g(ctx->device);
+    // roles swapped: every train row looks for its nearest query.  Results land interleaved
+    // (x2) in scratch and are compacted to the first neighbour.
+    int st = ERP_OK;
+    int32_t* idx2 = ctx->scratch<int32_t>(S_RS_IDX, (size_t)nt * 2, &st);
+    double* d2 = ctx->scratch<double>(S_RS_D2, (size_t)nt * 2, &st);
+    ERP_TRY(st);
+    bool tc = nq >= 2 && (ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_supported(nt, nq, dim)));
+    if (tc) {
+        ERP_TRY(knn2_tc(ctx, d_t, nt, d_q, nq, dim, idx2, nullptr, d2));
+        // tc path has no index offset: add it while compacting
+    } else {
+        ERP_TRY(knn2_exact(ctx, d_t, nt, d_q, nq, dim, nullptr, 0, 0, idx2, nullptr, d2));
+    }
+    ERP_CUDA(cudaMemcpy2DAsync(d_best_q, sizeof(int32_t), idx2, 2 * sizeof(int32_t), sizeof(int32_t), nt,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_best_d2)
+        ERP_CUDA(cudaMemcpy2DAsync(d_best_d2, sizeof(double), d2, 2 * sizeof(double), sizeof(double), nt,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    if (q_offset != 0) ERP_TRY(add_offset(ctx, d_best_q, nt, q_offset));
+    return ERP_OK;
+}
+
+ERP_API int erp_knn2_match_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                               float ratio, int cross_check, erp_dmatch* d_out, int32_t* d_n_out)
+{
+    ERP_TRY(check_knn_args("erp_knn2_match_dev", ctx, nq, nt, dim));
+    ERP_ARG(d_n_out, ERP_E_ARG, "erp_knn2_match_dev: d_n_out is null");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    int32_t* idx2 = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
+    float* dist2 = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
+    ERP_TRY(st);
+    ERP_TRY(erp_knn2_dev(ctx, d_q, nq, d_t, nt, dim, idx2, dist2, nullptr));
+    int32_t* rev = nullptr;
+    if (cross_check && nq > 0) {
+        rev = ctx->scratch<int32_t>(S_REVQ, (size_t)nt, &st);
+        ERP_TRY(st);
+        ERP_TRY(erp_nn1_reverse_dev(ctx, d_q, nq, d_t, nt, dim, 0, rev, nullptr));
+    }
+    return erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n_out);
+}
+
+static int stage_descriptors(erp_ctx* ctx, const float* q, int nq, size_t qs, const float* t, int nt, size_t ts,
+                             int dim, float** dq, float** dt)
+{
+    size_t row = (size_t)dim * sizeof(float);
+    ERP_ARG((nq == 0 || q) && (nt == 0 || t), ERP_E_ARG, "null descriptor pointer");
+    ERP_ARG(qs >= row && ts >= row, ERP_E_ARG, "row stride smaller than a descriptor row (%zu < %zu)", qs < ts ? qs : ts, row);
+    int st = ERP_OK;
+    *dq = ctx->scratch<float>(S_Q, (size_t)nq * dim + 4, &st);
+    *dt = ctx->scratch<float>(S_T, (size_t)nt * dim + 4, &st);
+    ERP_TRY(st);
+    ERP_TRY(upload_rows(ctx, *dq, q, nq, row, qs));
+    ERP_TRY(upload_rows(ctx, *dt, t, nt, row, ts));
+    return ERP_OK;
+}
+
+ERP_API int erp_knn2_match(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
+                           const float* t, int nt, size_t t_stride_bytes, int dim,
+                           float ratio, int cross_check, erp_dmatch* out, int* n_out)
+{
+    ERP_TRY(check_knn_args("erp_knn2_match", ctx, nq, nt, dim));
+    ERP_ARG(n_out, ERP_E_ARG, "erp_knn2_match: n_out is null");
+    *n_out = 0;
+    if (nq == 0) return ERP_OK;
+    ERP_ARG(out, ERP_E_ARG, "erp_knn2_match: out is null");
+    DeviceGuard g(ctx->device);
+    float *dq, *dt;
+    ERP_TRY(stage_descriptors(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, &dq, &dt));
+    int st = ERP_OK;
+    erp_dmatch* d_out = ctx->scratch<erp_dmatch>(S_OUT, (size_t)nq, &st);
+    int32_t* d_n = ctx->scratch<int32_t>(S_NOUT, 4, &st);
+    ERP_TRY(st);
+    ERP_TRY(erp_knn2_match_dev(ctx, dq, nq, dt, nt, dim, ratio, cross_check, d_out, d_n));
+    int32_t n = 0;
+    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n > 0) {
+        ERP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *n_out = n;
+    return ERP_OK;
+}
+
+ERP_API int erp_knn2_raw(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
+                         const float* t, int nt, size_t t_stride_bytes, int dim,
+                         int32_t* idx2, float* dist2)
+{
+    ERP_TRY(check_knn_args("erp_knn2_raw", ctx, nq, nt, dim));
+    if (nq == 0) return ERP_OK;
+    DeviceGuard g(ctx->device);
+    float *dq, *dt;
+    ERP_TRY(stage_descriptors(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, &dq, &dt));
+    int st = ERP_OK;
+    int32_t* d_idx = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
+    float* d_dist = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
+    ERP_TRY(st);
+    ERP_TRY(erp_knn2_dev(ctx, dq, nq, dt, nt, dim, d_idx, d_dist, nullptr));
+    if (idx2) ERP_CUDA(cudaMemcpyAsync(idx2, d_idx, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist2) ERP_CUDA(cudaMemcpyAsync(dist2, d_dist, sizeof(float) * 2 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+// ======================================================================================
+// geometry, host-pointer forms
+// ======================================================================================
+ERP_API int erp_bearings_from_pixels(erp_ctx* ctx, const void* xy, size_t stride_bytes, int n,
+                                     int width, int height, double* out3)
+{
+    ERP_ARG(ctx && n >= 0 && width > 0 && height > 0, ERP_E_ARG, "erp_bearings_from_pixels: bad argument");
+    ERP_ARG(stride_bytes >= 8 && stride_bytes % 4 == 0, ERP_E_ARG, "erp_bearings_from_pixels: bad stride %zu", stride_bytes);
+    if (n == 0) return ERP_OK;
+    ERP_ARG(xy && out3, ERP_E_ARG, "erp_bearings_from_pixels: null buffer");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    float* d_xy = ctx->scratch<float>(S_XY, (size_t)n * 2, &st);
+    double* d_o = ctx->scratch<double>(S_L3, (size_t)n * 3, &st);
+    ERP_TRY(st);
+    ERP_TRY(upload_rows(ctx, d_xy, xy, n, 8, stride_bytes));
+    ERP_TRY(erp_bearings_dev(ctx, d_xy, 8, n, width, height, d_o, nullptr));
+    ERP_CUDA(cudaMemcpyAsync(out3, d_o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+// upload m x 3 fp64 bearings for both views; optionally build the float4 copies
+static int stage_bearings(erp_ctx* ctx, const double* l3, const double* r3, int m,
+                          double** dl, double** dr, float** dl4, float** dr4)
+{
+    ERP_ARG(m == 0 || (l3 && r3), ERP_E_ARG, "null bearing pointer");
+    int st = ERP_OK;
+    *dl = ctx->scratch<double>(S_L3, (size_t)m * 3 + 4, &st);
+    *dr = ctx->scratch<double>(S_R3, (size_t)m * 3 + 4, &st);
+    ERP_TRY(st);
+    if (m) {
+        ERP_CUDA(cudaMemcpyAsync(*dl, l3, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        ERP_CUDA(cudaMemcpyAsync(*dr, r3, sizeof(double) * 3 * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (dl4) {
+        *dl4 = ctx->scratch<float>(S_L4, (size_t)m * 4 + 4, &st);
+        *dr4 = ctx->scratch<float>(S_R4, (size_t)m * 4 + 4, &st);
+        ERP_TRY(st);
+        ERP_TRY(erp_pack_float4_dev(ctx, *dl, m, *dl4));
+        ERP_TRY(erp_pack_float4_dev(ctx, *dr, m, *dr4));
+    }
+    return ERP_OK;
+}
+
+ERP_API int erp_eight_point_batch(erp_ctx* ctx, const double* l3, const double* r3, int m,
+                                  const int32_t* samples, int H, int S, uint64_t seed, uint64_t hyp_offset,
+                                  double* E_out, float* pose_out)
+{
+    ERP_ARG(ctx && E_out && H >= 0 && m >= 0, ERP_E_ARG, "erp_eight_point_batch: bad argument");
+    if (H == 0) return ERP_OK;
+    DeviceGuard g(ctx->device);
+    double *dl, *dr;
+    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, nullptr, nullptr));
+    int st = ERP_OK;
+    int32_t* d_s = nullptr;
+    if (samples) {
+        for (size_t i = 0; i < (size_t)H * S; i++)
+            ERP_ARG(samples[i] >= 0 && samples[i] < m, ERP_E_ARG, "sample index %d out of range [0,%d)", samples[i], m);
+        d_s = ctx->scratch<int32_t>(S_SAMPLES, (size_t)H * S, &st);
+        ERP_TRY(st);
+        ERP_CUDA(cudaMemcpyAsync(d_s, samples, sizeof(int32_t) * (size_t)H * S, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    double* dE = ctx->scratch<double>(S_E, (size_t)H * 9, &st);
+    float* dP = pose_out ? ctx->scratch<float>(S_POSE, (size_t)H * ERP_POSE_FLOATS, &st) : nullptr;
+    ERP_TRY(st);
+    ERP_TRY(erp_eight_point_batch_dev(ctx, dl, dr, m, d_s, H, S, seed, hyp_offset, dE, dP));
+    ERP_CUDA(cudaMemcpyAsync(E_out, dE, sizeof(double) * 9 * (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pose_out) ERP_CUDA(cudaMemcpyAsync(pose_out, dP, sizeof(float) * ERP_POSE_FLOATS * (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+ERP_API int erp_refit(erp_ctx* ctx, const double* l3, const double* r3, int m, const uint8_t* mask,
+                      double* E_out, float* pose_out)
+{
+    ERP_ARG(ctx && m >= 0 && (E_out || pose_out), ERP_E_ARG, "erp_refit: bad argument");
+    int used = m;
+    if (mask) { used = 0; for (int i = 0; i < m; i++) used += mask[i] != 0; }
+    ERP_ARG(used >= 8, ERP_E_TOO_FEW_POINTS, "erp_refit: %d correspondences selected, need >= 8", used);
+    DeviceGuard g(ctx->device);
+    double *dl, *dr;
+    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, nullptr, nullptr));
+    int st = ERP_OK;
+    uint8_t* d_mask = nullptr;
+    if (mask) {
+        d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m, &st);
+        ERP_TRY(st);
+        ERP_CUDA(cudaMemcpyAsync(d_mask, mask, (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    double* misc = ctx->scratch<double>(S_MISC, 128, &st);
+    ERP_TRY(st);
+    double *G = misc, *E = misc + 45;
+    float* pose = reinterpret_cast<float*>(misc + 54);
+    ERP_TRY(gram_masked(ctx, dl, dr, m, d_mask, G));
+    ERP_TRY(solve_batch(ctx, G, 1, E, pose));
+    if (E_out) ERP_CUDA(cudaMemcpyAsync(E_out, E, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pose_out) ERP_CUDA(cudaMemcpyAsync(pose_out, pose, sizeof(float) * ERP_POSE_FLOATS, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+// eight_point::eight_point_estimation(w, h, left, right, R1, R2, T, v1, v2, n)
+ERP_API int erp_eight_point_estimation(erp_ctx* ctx, const double* l3, const double* r3, int n,
+                                       double* E_out, float* R1_vec, float* R2_vec, float* T_vec,
+                                       int* R1_valid, int* R2_valid)
+{
+    ERP_ARG(n >= 8, ERP_E_TOO_FEW_POINTS, "eight_point_estimation needs >= 8 correspondences, got %d", n);
+    double E[9];
+    float pose[ERP_POSE_FLOATS];
+    ERP_TRY(erp_refit(ctx, l3, r3, n, nullptr, E, pose));
+    if (E_out) memcpy(E_out, E, sizeof E);
+    if (R1_vec) memcpy(R1_vec, pose, 12);
+    if (R2_vec) memcpy(R2_vec, pose + 3, 12);
+    if (T_vec) memcpy(T_vec, pose + 6, 12);
+    if (R1_valid) *R1_valid = pose[9] != 0.f;
+    if (R2_valid) *R2_valid = pose[10] != 0.f;
+    return ERP_OK;
+}
+
+ERP_API int erp_score(erp_ctx* ctx, const double* E, int H, const double* l3, const double* r3, int m,
+                      int metric, float tau, int32_t* counts)
+{
+    ERP_ARG(ctx && H >= 0 && m >= 0, ERP_E_ARG, "erp_score: bad argument");
+    if (H == 0) return ERP_OK;
+    ERP_ARG(E && counts, ERP_E_ARG, "erp_score: null buffer");
+    DeviceGuard g(ctx->device);
+    double *dl, *dr;
+    float *dl4, *dr4;
+    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, &dl4, &dr4));
+    int st = ERP_OK;
+    double* dE = ctx->scratch<double>(S_E, (size_t)H * 9, &st);
+    int32_t* dc = ctx->scratch<int32_t>(S_COUNTS, (size_t)H, &st);
+    ERP_TRY(st);
+    ERP_CUDA(cudaMemcpyAsync(dE, E, sizeof(double) * 9 * (size_t)H, cudaMemcpyHostToDevice, ctx->stream));
+    ERP_TRY(erp_score_dev(ctx, dE, H, dl4, dr4, m, metric, tau, 0, dc, nullptr));
+    ERP_CUDA(cudaMemcpyAsync(counts, dc, sizeof(int32_t) * (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+ERP_API int erp_inlier_mask(erp_ctx* ctx, const double* E9, const double* l3, const double* r3, int m,
+                            int metric, float tau, uint8_t* mask, int* n_inliers)
+{
+    ERP_ARG(ctx && E9 && m >= 0, ERP_E_ARG, "erp_inlier_mask: bad argument");
+    ERP_ARG(metric >= 0 && metric <= 2, ERP_E_ARG, "erp_inlier_mask: unknown metric %d", metric);
+    DeviceGuard g(ctx->device);
+    double *dl, *dr;
+    float *dl4, *dr4;
+    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, &dl4, &dr4));
+    int st = ERP_OK;
+    double* misc = ctx->scratch<double>(S_MISC, 128, &st);
+    uint8_t* d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m + 4, &st);
+    ERP_TRY(st);
+    int32_t* d_n = reinterpret_cast<int32_t*>(misc + 16);
+    ERP_CUDA(cudaMemcpyAsync(misc, E9, sizeof(double) * 9, cudaMemcpyHostToDevice, ctx->stream));
+    ERP_TRY(mask_launch(ctx, misc, dl4, dr4, m, metric, tau, d_mask, d_n));
+    int32_t n = 0;
+    if (mask && m) ERP_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_inliers) *n_inliers = n;
+    return ERP_OK;
+}
+
+ERP_API int erp_ransac(erp_ctx* ctx, const double* l3, const double* r3, int m, uint64_t seed,
+                       uint64_t hyp_offset, int H, int S, int metric, float tau,
+                       erp_ransac_result* result, uint8_t* mask)
+{
+    ERP_ARG(ctx && result && H >= 1, ERP_E_ARG, "erp_ransac: bad argument");
+    ERP_ARG(m >= S && S >= 8, ERP_E_TOO_FEW_POINTS, "erp_ransac: %d correspondences for sample size %d", m, S);
+    DeviceGuard g(ctx->device);
+    double *dl, *dr;
+    float *dl4, *dr4;
+    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, &dl4, &dr4));
+    int st = ERP_OK;
+    uint64_t* d_packed = ctx->scratch<uint64_t>(S_PACKED, 2, &st);
+    uint8_t* d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m + 4, &st);
+    ERP_TRY(st);
+    ERP_TRY(erp_ransac_local_dev(ctx, dl, dr, dl4, dr4, m, seed, hyp_offset, H, S, metric, tau, d_packed));
+    uint64_t packed = 0;
+    ERP_CUDA(cudaMemcpyAsync(&packed, d_packed, sizeof packed, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ERP_TRY(erp_ransac_finish_dev(ctx, dl, dr, dl4, dr4, m, seed, packed, S, metric, tau, d_mask, result));
+    if (mask) {
+        ERP_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return ERP_OK;
+}
+
+// ======================================================================================
+// reference mode: initial_guess / find
+// ======================================================================================
+// glibc rand() (TYPE_3 additive feedback, r[i] = r[i-3] + r[i-31]) restated so the library
+// neither reads nor disturbs the process-wide rand() state the way the reference does.
+namespace {
+struct GlibcRand {
+    uint32_t r[34];
+    int k = 0;
+    explicit GlibcRand(unsigned seed)
+    {
+        int32_t w = (int32_t)(seed ? seed : 1);
+        int32_t s[34];
+        s[0] = w;
+        for (int i = 1; i < 31; i++) {
+            long hi = s[i - 1] / 127773, lo = s[i - 1] % 127773;
+            long word = 16807 * lo - 2836 * hi;
+            if (word < 0) word += 2147483647;
+            s[i] = (int32_t)word;
+        }
+        for (int i = 31; i < 34; i++) s[i] = s[i - 31];
+        for (int i = 0; i < 34; i++) r[i] = (uint32_t)s[i];
+        for (int i = 0; i < 310; i++) next_raw();
+    }
+    uint32_t next_raw()
+    {
+        // ring of 34: new = r[k-31] + r[k-3]
+        uint32_t v = r[(k + 34 - 31) % 34] + r[(k + 34 - 3) % 34];
+        r[k % 34] = v;
+        k = (k + 1) % 34;
+        return v;
+    }
+    int next() { return (int)(next_raw() >> 1); }
+};
+} // namespace
+
+ERP_API int erp_libstdcxx_sample_table(int m, int H, int S, unsigned seed, int32_t* table)
+{
+    ERP_ARG(m >= 1 && H >= 0 && S >= 0 && S <= m && table, ERP_E_ARG, "erp_libstdcxx_sample_table: bad argument");
+    GlibcRand rng(seed);
+    std::vector<int32_t> perm(m);
+    for (int h = 0; h < H; h++) {
+        // random_array::rand_idx_generate (src/eight_point.hpp:54-58): iota + random_shuffle;
+        // libstdc++: for i in 1..n-1: swap(a[i], a[rand() % (i+1)])
+        for (int i = 0; i < m; i++) perm[i] = i;
+        for (int i = 1; i < m; i++) {
+            int j = rng.next() % (i + 1);
+            if (i != j) { int32_t t = perm[i]; perm[i] = perm[j]; perm[j] = t; }
+        }
+        memcpy(table + (size_t)h * S, perm.data(), sizeof(int32_t) * S);
+    }
+    return ERP_OK;
+}
+
+ERP_API int erp_initial_guess(erp_ctx* ctx, const double* l3, const double* r3, int m,
+                              const int32_t* samples, int H, int S,
+                              float* R_vec_out, float* T_vec_out,
+                              float* cand_R, float* cand_T, int* n_cand, int* chosen)
+{
+    ERP_ARG(ctx && R_vec_out && T_vec_out && H >= 1 && H <= 4096, ERP_E_ARG, "erp_initial_guess: bad argument");
+    ERP_ARG(S >= 8 && m >= S, ERP_E_TOO_FEW_POINTS,
+            "erp_initial_guess: sample size %d of %d correspondences (the reference needs match_size >= 32)", S, m);
+    std::vector<int32_t> replay;
+    if (!samples) {
+        replay.resize((size_t)H * S);
+        ERP_TRY(erp_libstdcxx_sample_table(m, H, S, 1, replay.data()));
+        samples = replay.data();
+    }
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    float* dP = ctx->scratch<float>(S_POSE, (size_t)H * ERP_POSE_FLOATS + (size_t)H * 12 + 16, &st);
+    ERP_TRY(st);
+    // hypotheses solved exactly as erp_eight_point_batch does (pose included)
+    double *dl, *dr;
+    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, nullptr, nullptr));
+    for (size_t i = 0; i < (size_t)H * S; i++)
+        ERP_ARG(samples[i] >= 0 && samples[i] < m, ERP_E_ARG, "sample index %d out of range [0,%d)", samples[i], m);
+    int32_t* d_s = ctx->scratch<int32_t>(S_SAMPLES, (size_t)H * S, &st);
+    double* dE = ctx->scratch<double>(S_E, (size_t)H * 9, &st);
+    ERP_TRY(st);
+    ERP_CUDA(cudaMemcpyAsync(d_s, samples, sizeof(int32_t) * (size_t)H * S, cudaMemcpyHostToDevice, ctx->stream));
+    ERP_TRY(erp_eight_point_batch_dev(ctx, dl, dr, m, d_s, H, S, 0, 0, dE, dP));
+    float* d_candR = dP + (size_t)H * ERP_POSE_FLOATS;
+    float* d_candT = d_candR + (size_t)H * 6;
+    int32_t* d_out = ctx->scratch<int32_t>(S_NOUT, 4, &st);
+    ERP_TRY(st);
+    ERP_TRY(consensus(ctx, dP, H, d_candR, d_candT, d_out));
+    int32_t res[2] = {0, -1};
+    ERP_CUDA(cudaMemcpyAsync(res, d_out, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_cand) *n_cand = res[0];
+    if (chosen) *chosen = res[1];
+    std::vector<float> hR((size_t)res[0] * 3 + 3), hT((size_t)res[0] * 3 + 3);
+    if (res[0] > 0) {
+        ERP_CUDA(cudaMemcpyAsync(hR.data(), d_candR, sizeof(float) * 3 * res[0], cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaMemcpyAsync(hT.data(), d_candT, sizeof(float) * 3 * res[0], cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (cand_R) memcpy(cand_R, hR.data(), sizeof(float) * 3 * res[0]);
+    if (cand_T) memcpy(cand_T, hT.data(), sizeof(float) * 3 * res[0]);
+    // the reference dereferences an empty vector here (src/eight_point.cpp:147-149): report it
+    ERP_ARG(res[0] > 0 && res[1] >= 0, ERP_E_NO_CANDIDATE, "initial_guess: none of the %d hypotheses passed the <1.57 rad test", H);
+    memcpy(R_vec_out, hR.data() + 3 * res[1], 12);
+    memcpy(T_vec_out, hT.data() + 3 * res[1], 12);
+    return ERP_OK;
+}
+
+ERP_API int erp_find(erp_ctx* ctx, int width, int height, const void* left_xy, const void* right_xy,
+                     size_t stride_bytes, int match_size, const int32_t* samples, int H, int S,
+                     float* R_vec_out, float* T_vec_out)
+{
+    ERP_ARG(ctx && left_xy && right_xy && match_size >= 0, ERP_E_ARG, "erp_find: bad argument");
+    if (H <= 0) H = 80;                               // src/eight_point.cpp:99
+    if (S <= 0) S = (int)(match_size * 0.25);         // src/eight_point.cpp:102
+    ERP_ARG(S >= 8, ERP_E_TOO_FEW_POINTS, "erp_find: match_size %d gives sample size %d < 8", match_size, S);
+    std::vector<double> l((size_t)match_size * 3), r((size_t)match_size * 3);
+    ERP_TRY(erp_bearings_from_pixels(ctx, left_xy, stride_bytes, match_size, width, height, l.data()));
+    ERP_TRY(erp_bearings_from_pixels(ctx, right_xy, stride_bytes, match_size, width, height, r.data()));
+    return erp_initial_guess(ctx, l.data(), r.data(), match_size, samples, H, S, R_vec_out, T_vec_out,
+                             nullptr, nullptr, nullptr, nullptr);
+}

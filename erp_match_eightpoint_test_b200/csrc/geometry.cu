@@ -1,0 +1,628 @@
+// geometry.cu -- pixel->bearing, Philox minimal samples, batched eight-point solve,
+// consensus pick.  Replaces /root/reference/src/eight_point.cpp:16-192 on the device.
+//
+// The solve is the Gram form of OpenCV's one-sided Jacobi SVD: cv::SVDecomp(A) rotates the
+// columns of the S x 9 matrix A (modules/core/src/lapack.cpp, JacobiSVDImpl_); the rotation of
+// columns (i,j) depends only on a = |a_i|^2, b = |a_j|^2, p = a_i.a_j, i.e. on the 9 x 9 Gram
+// matrix G = A^T A.  Applying the same cyclic pivot order and the same (c,s) formulas to G
+// (G <- J^T G J, V <- V J) reproduces the same right singular vectors, including their sign,
+// without ever materialising A: S x 9 collapses to 45 doubles per hypothesis, which is what
+// lets a million hypotheses run concurrently.  The 3 x 3 SVDs (rank-2 projection and
+// cv::decomposeEssentialMat) are run one-sided exactly as OpenCV does.
+#include "common.cuh"
+
+#include <float.h>
+
+namespace erp {
+
+// ------------------------------------------------------------------ bearings (eight_point.cpp:163-186)
+__global__ void bearings_kernel(const char* __restrict__ xy, size_t stride, int n, int W, int H,
+                                double* __restrict__ out3, float4* __restrict__ out4)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(xy + (size_t)i * stride);
+    float fx = __fdiv_rn(p[0], (float)W);      // float quotient, then promoted (pt.x / im_width)
+    float fy = __fdiv_rn(p[1], (float)H);
+    double lon = 2 * 3.14159265358979323846 * (double)fx;
+    double lat = 3.14159265358979323846 * (double)fy;
+    double sl, cl, so, co;
+    sincos(lat, &sl, &cl);
+    sincos(lon, &so, &co);
+    double x = -sl * co, y = sl * so, z = cl;   // MPEG OMAF axes
+    if (out3) { out3[3 * (size_t)i] = x; out3[3 * (size_t)i + 1] = y; out3[3 * (size_t)i + 2] = z; }
+    if (out4) out4[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+}
+
+__device__ __forceinline__ void pixel_to_bearing(const float* p, int W, int H, double& x, double& y, double& z)
+{
+    float fx = __fdiv_rn(p[0], (float)W), fy = __fdiv_rn(p[1], (float)H);
+    double lon = 2 * 3.14159265358979323846 * (double)fx, lat = 3.14159265358979323846 * (double)fy;
+    double sl, cl, so, co;
+    sincos(lat, &sl, &cl);
+    sincos(lon, &so, &co);
+    x = -sl * co; y = sl * so; z = cl;
+}
+
+// spherical_surf.cpp:155-162 (gather the matched keypoints) fused with eight_point.cpp:163-186
+__global__ void gather_bearings_kernel(const erp_dmatch* __restrict__ mt, int n, const char* __restrict__ lxy,
+                                       const char* __restrict__ rxy, size_t stride, int q_offset, int W, int H,
+                                       double* __restrict__ l3, double* __restrict__ r3,
+                                       float4* __restrict__ l4, float4* __restrict__ r4)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    erp_dmatch m = mt[i];
+    double x, y, z;
+    pixel_to_bearing(reinterpret_cast<const float*>(lxy + (size_t)(m.queryIdx - q_offset) * stride), W, H, x, y, z);
+    if (l3) { l3[3 * (size_t)i] = x; l3[3 * (size_t)i + 1] = y; l3[3 * (size_t)i + 2] = z; }
+    if (l4) l4[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+    pixel_to_bearing(reinterpret_cast<const float*>(rxy + (size_t)m.trainIdx * stride), W, H, x, y, z);
+    if (r3) { r3[3 * (size_t)i] = x; r3[3 * (size_t)i + 1] = y; r3[3 * (size_t)i + 2] = z; }
+    if (r4) r4[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+}
+
+__global__ void pack4_kernel(const double* __restrict__ v3, int n, float4* __restrict__ v4)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v4[i] = make_float4((float)v3[3 * (size_t)i], (float)v3[3 * (size_t)i + 1], (float)v3[3 * (size_t)i + 2], 0.f);
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 sampler
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// S distinct indices in [0,m): counter (hyp_lo, hyp_hi, block, 'ERP8'), key = seed; same spec as
+// oracle/erp_oracle.c: orc_philox_samples.  out may be shared or global memory.
+__device__ void philox_sample(uint64_t seed, uint64_t hyp, int m, int S, int32_t* out)
+{
+    int count = 0;
+    uint32_t block = 0;
+    while (count < S) {
+        uint32_t c[4] = {(uint32_t)hyp, (uint32_t)(hyp >> 32), block++, 0x45525038u};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        for (int w = 0; w < 4 && count < S; w++) {
+            int32_t idx = (int32_t)__umulhi(c[w], (uint32_t)m);
+            bool dup = false;
+            for (int j = 0; j < count; j++) dup |= out[j] == idx;
+            if (!dup) out[count++] = idx;
+        }
+    }
+}
+
+__global__ void philox_table_kernel(uint64_t seed, uint64_t hyp0, int H, int S, int m, int32_t* table)
+{
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < H) philox_sample(seed, hyp0 + h, m, S, table + (size_t)h * S);
+}
+
+// ------------------------------------------------------------------ Gram matrices G = A^T A
+// upper-triangle index e -> (i,j), i <= j, row-major order
+__constant__ uint8_t kTriI[45] = {0,0,0,0,0,0,0,0,0, 1,1,1,1,1,1,1,1, 2,2,2,2,2,2,2, 3,3,3,3,3,3, 4,4,4,4,4, 5,5,5,5, 6,6,6, 7,7, 8};
+__constant__ uint8_t kTriJ[45] = {0,1,2,3,4,5,6,7,8, 1,2,3,4,5,6,7,8, 2,3,4,5,6,7,8, 3,4,5,6,7,8, 4,5,6,7,8, 5,6,7,8, 6,7,8, 7,8, 8};
+
+constexpr int GW = 4;          // warps (hypotheses) per block in the small-sample kernel
+constexpr int SMALL_S = 32;
+
+// One warp per hypothesis, S <= 32 (the minimal-sample RANSAC case, S = 8).
+// lane s builds row a_s = kron(l_s, r_s) (eight_point.cpp:28-36); lanes then own Gram entries.
+__global__ void __launch_bounds__(GW * 32)
+gram_small_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m,
+                  const int32_t* __restrict__ samples, int H, int S, uint64_t seed, uint64_t hyp0,
+                  double* __restrict__ G /* H x 45 */)
+{
+    __shared__ double a[GW][SMALL_S][9];
+    __shared__ int32_t smp[GW][SMALL_S];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x * GW + w;
+    if (h >= H) return;
+    if (samples) { if (lane < S) smp[w][lane] = samples[(size_t)h * S + lane]; }
+    else if (lane == 0) philox_sample(seed, hyp0 + h, m, S, smp[w]);
+    __syncwarp();
+    if (lane < S) {
+        int idx = smp[w][lane];
+        double lx = l3[3 * (size_t)idx], ly = l3[3 * (size_t)idx + 1], lz = l3[3 * (size_t)idx + 2];
+        double rx = r3[3 * (size_t)idx], ry = r3[3 * (size_t)idx + 1], rz = r3[3 * (size_t)idx + 2];
+        double* o = a[w][lane];
+        o[0] = lx * rx; o[1] = lx * ry; o[2] = lx * rz;
+        o[3] = ly * rx; o[4] = ly * ry; o[5] = ly * rz;
+        o[6] = lz * rx; o[7] = lz * ry; o[8] = lz * rz;
+    }
+    __syncwarp();
+    for (int e = lane; e < 45; e += 32) {
+        int i = kTriI[e], j = kTriJ[e];
+        double acc = 0.0;
+        for (int s = 0; s < S; s++) acc = __fma_rn(a[w][s][i], a[w][s][j], acc);
+        G[(size_t)h * 45 + e] = acc;
+    }
+}
+
+// One block per hypothesis for large samples (reference mode S = int(0.25 m), and the refit):
+// every thread accumulates all 45 entries over a strided subset of rows, then a fixed-order
+// tree reduction (deterministic).  index source: samples table, mask (compact on the fly), or all.
+constexpr int GL_THREADS = 256;
+__global__ void __launch_bounds__(GL_THREADS)
+gram_large_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m,
+                  const int32_t* __restrict__ samples, int S, const uint8_t* __restrict__ mask,
+                  double* __restrict__ G /* gridDim.y x gridDim.x x 45 partials */)
+{
+    // blockIdx.y = hypothesis, blockIdx.x = slice of its rows
+    const int h = blockIdx.y;
+    double acc[45];
+#pragma unroll
+    for (int e = 0; e < 45; e++) acc[e] = 0.0;
+    const int stride = gridDim.x * GL_THREADS;
+    for (int s = blockIdx.x * GL_THREADS + threadIdx.x; s < S; s += stride) {
+        int idx = samples ? samples[(size_t)h * S + s] : s;
+        if (mask && !mask[idx]) continue;
+        double v[9];
+        {
+            double lx = l3[3 * (size_t)idx], ly = l3[3 * (size_t)idx + 1], lz = l3[3 * (size_t)idx + 2];
+            double rx = r3[3 * (size_t)idx], ry = r3[3 * (size_t)idx + 1], rz = r3[3 * (size_t)idx + 2];
+            v[0] = lx * rx; v[1] = lx * ry; v[2] = lx * rz;
+            v[3] = ly * rx; v[4] = ly * ry; v[5] = ly * rz;
+            v[6] = lz * rx; v[7] = lz * ry; v[8] = lz * rz;
+        }
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+#pragma unroll
+            for (int j = i; j < 9; j++) { acc[e] = __fma_rn(v[i], v[j], acc[e]); e++; }
+    }
+    __shared__ double red[GL_THREADS / 32][45];
+#pragma unroll
+    for (int e = 0; e < 45; e++) {
+        double x = acc[e];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][e] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 45) {
+        double x = 0.0;
+        for (int w = 0; w < GL_THREADS / 32; w++) x += red[w][threadIdx.x];
+        G[((size_t)h * gridDim.x + blockIdx.x) * 45 + threadIdx.x] = x;
+    }
+}
+
+// sum the per-slice partials in slice order: G[h] = sum_b P[h][b]
+__global__ void gram_finish_kernel(const double* __restrict__ P, int H, int slices, double* __restrict__ G)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * 45) return;
+    int h = i / 45, e = i % 45;
+    double x = 0.0;
+    for (int b = 0; b < slices; b++) x += P[((size_t)h * slices + b) * 45 + e];
+    G[i] = x;
+}
+
+// ------------------------------------------------------------------ 3x3 helpers
+struct M3 { double v[9]; };
+
+__device__ __forceinline__ M3 mul3(const M3& A, const M3& B)
+{
+    M3 C;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            C.v[3 * i + j] = A.v[3 * i] * B.v[j] + A.v[3 * i + 1] * B.v[3 + j] + A.v[3 * i + 2] * B.v[6 + j];
+    return C;
+}
+
+__device__ __forceinline__ double det3(const M3& M)
+{
+    return M.v[0] * (M.v[4] * M.v[8] - M.v[5] * M.v[7]) - M.v[1] * (M.v[3] * M.v[8] - M.v[5] * M.v[6]) +
+           M.v[2] * (M.v[3] * M.v[7] - M.v[4] * M.v[6]);
+}
+
+// OpenCV's Jacobi rotation coefficients for the pair with squared norms a, b and dot p
+__device__ __forceinline__ void cv_rotation(double a, double b, double p, double& c, double& s)
+{
+    p *= 2;
+    double beta = a - b, gamma = hypot(p, beta);
+    if (beta < 0) {
+        double delta = (gamma - beta) * 0.5;
+        s = sqrt(delta / gamma);
+        c = p / (gamma * s * 2);
+    } else {
+        c = sqrt((gamma + beta) / (gamma * 2));
+        s = p / (gamma * c * 2);
+    }
+}
+
+// cv::SVD::compute on a 3x3 (m == n): one-sided Jacobi on the columns of E.
+// U = normalised rotated columns, Vt rows = right singular vectors, w descending.
+__device__ void svd3(const M3& E, double w[3], M3& U, M3& Vt)
+{
+    const double eps = DBL_EPSILON * 10;
+    double At[3][3], V[3][3], W[3];   // At rows = columns of E
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { At[i][k] = E.v[3 * k + i]; V[i][k] = (i == k) ? 1.0 : 0.0; }
+        W[i] = At[i][0] * At[i][0] + At[i][1] * At[i][1] + At[i][2] * At[i][2];
+    }
+    for (int iter = 0; iter < 30; iter++) {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = i + 1; j < 3; j++) {
+                double a = W[i], b = W[j];
+                double p = At[i][0] * At[j][0] + At[i][1] * At[j][1] + At[i][2] * At[j][2];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                double c, s;
+                cv_rotation(a, b, p, c, s);
+                a = b = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    double t0 = c * At[i][k] + s * At[j][k], t1 = -s * At[i][k] + c * At[j][k];
+                    At[i][k] = t0; At[j][k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                    double v0 = c * V[i][k] + s * V[j][k], v1 = -s * V[i][k] + c * V[j][k];
+                    V[i][k] = v0; V[j][k] = v1;
+                }
+                W[i] = a; W[j] = b;
+                changed = true;
+            }
+        if (!changed) break;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) W[i] = sqrt(At[i][0] * At[i][0] + At[i][1] * At[i][1] + At[i][2] * At[i][2]);
+    // selection sort, descending, strict < as OpenCV
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int j = i;
+#pragma unroll
+        for (int k = i + 1; k < 3; k++) if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double t = W[i]; W[i] = W[j]; W[j] = t;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                t = At[i][k]; At[i][k] = At[j][k]; At[j][k] = t;
+                t = V[i][k]; V[i][k] = V[j][k]; V[j][k] = t;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        w[i] = W[i];
+        // OpenCV substitutes a pseudo-random orthogonal vector when W <= DBL_MIN; an exactly
+        // singular E has no usable third column, so the device leaves it zero and lets
+        // decompose() rebuild it from the other two.
+        double s = W[i] > DBL_MIN ? 1.0 / W[i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { U.v[3 * k + i] = At[i][k] * s; Vt.v[3 * i + k] = V[i][k]; }
+    }
+}
+
+// erp_rotation.cpp:43-63
+__device__ __forceinline__ void rot2eular(const M3& R, double e[3])
+{
+    double sy = sqrt(R.v[8] * R.v[8] + R.v[5] * R.v[5]);
+    e[0] = sy < 1e-6 ? 0.0 : atan2(-R.v[5], R.v[8]);
+    e[1] = atan2(R.v[2], sy);
+    e[2] = atan2(-R.v[1], R.v[0]);
+}
+
+__device__ __forceinline__ float max_vec3(float a, float b, float c)   // eight_point.cpp:6-14
+{
+    if ((a > b) && (a > c)) return a;
+    else if (b > c) return b;
+    else return c;
+}
+
+// cv::decomposeEssentialMat + rot2eular + validity (eight_point.cpp:53-84)
+__device__ void decompose_pose(const M3& Ec, float* pose)
+{
+    double D[3];
+    M3 U, Vt;
+    svd3(Ec, D, U, Vt);
+    if (!(D[2] > DBL_MIN)) {   // exactly rank-2 input: third left vector = u1 x u2
+        U.v[2] = U.v[3] * U.v[7] - U.v[6] * U.v[4];
+        U.v[5] = U.v[6] * U.v[1] - U.v[0] * U.v[7];
+        U.v[8] = U.v[0] * U.v[4] - U.v[3] * U.v[1];
+    }
+    if (det3(U) < 0) for (int i = 0; i < 9; i++) U.v[i] = -U.v[i];
+    if (det3(Vt) < 0) for (int i = 0; i < 9; i++) Vt.v[i] = -Vt.v[i];
+    M3 Wm = {{0, 1, 0, -1, 0, 0, 0, 0, 1}}, Wt = {{0, -1, 0, 1, 0, 0, 0, 0, 1}};
+    M3 R1 = mul3(mul3(U, Wm), Vt), R2 = mul3(mul3(U, Wt), Vt);
+    double e1[3], e2[3];
+    rot2eular(R1, e1);
+    rot2eular(R2, e2);
+    float f1[3] = {(float)e1[0], (float)e1[1], (float)e1[2]};
+    float f2[3] = {(float)e2[0], (float)e2[1], (float)e2[2]};
+    pose[0] = f1[0]; pose[1] = f1[1]; pose[2] = f1[2];
+    pose[3] = f2[0]; pose[4] = f2[1]; pose[5] = f2[2];
+    pose[6] = (float)U.v[2]; pose[7] = (float)U.v[5]; pose[8] = (float)U.v[8];
+    pose[9] = ((double)max_vec3(fabsf(f1[0]), fabsf(f1[1]), fabsf(f1[2])) < 1.57) ? 1.f : 0.f;
+    pose[10] = ((double)max_vec3(fabsf(f2[0]), fabsf(f2[1]), fabsf(f2[2])) < 1.57) ? 1.f : 0.f;
+    pose[11] = 0.f;
+}
+
+// ------------------------------------------------------------------ 9x9 Jacobi, thread per hypothesis
+constexpr int SOLVE_THREADS = 64;
+// symmetric index into the packed upper triangle
+__host__ __device__ constexpr int tri(int i, int j) { return i <= j ? i * 9 - i * (i - 1) / 2 + (j - i) : j * 9 - j * (j - 1) / 2 + (i - j); }
+
+template <bool WANT_POSE>
+__global__ void __launch_bounds__(SOLVE_THREADS)
+solve_kernel(const double* __restrict__ Gin, int H, int max_sweeps,
+             double* __restrict__ Eout /* H x 9 */, float* __restrict__ pose /* H x 12 */)
+{
+    // V (rows = right singular vectors, OpenCV's Vt) lives in shared memory, element-major so
+    // that the 64 threads of a block hit 64 consecutive doubles; G (45 doubles) in registers.
+    __shared__ double Vs[81][SOLVE_THREADS];
+    const int tid = threadIdx.x;
+    const int h = blockIdx.x * SOLVE_THREADS + tid;
+    if (h >= H) return;
+    double G[45];
+#pragma unroll
+    for (int e = 0; e < 45; e++) G[e] = Gin[(size_t)h * 45 + e];
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+#pragma unroll
+        for (int k = 0; k < 9; k++) Vs[i * 9 + k][tid] = (i == k) ? 1.0 : 0.0;
+
+    const double eps = DBL_EPSILON * 10;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int j = i + 1; j < 9; j++) {
+                double a = G[tri(i, i)], b = G[tri(j, j)], p = G[tri(i, j)];
+                double ab = fmax(a, 0.0) * fmax(b, 0.0);
+                // OpenCV's relative test, plus the floor a Gram matrix can resolve
+                if (fabs(p) <= eps * sqrt(ab) || fabs(p) <= DBL_EPSILON * fmax(fabs(a), fabs(b))) continue;
+                double c, s;
+                cv_rotation(a, b, p, c, s);
+                // G <- J^T G J  with  col_i' = c col_i + s col_j,  col_j' = -s col_i + c col_j
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    if (k == i || k == j) continue;
+                    double gi = G[tri(k, i)], gj = G[tri(k, j)];
+                    G[tri(k, i)] = c * gi + s * gj;
+                    G[tri(k, j)] = -s * gi + c * gj;
+                }
+                double cc = c * c, ss = s * s, cs = c * s;
+                G[tri(i, i)] = cc * a + 2 * cs * p + ss * b;
+                G[tri(j, j)] = ss * a - 2 * cs * p + cc * b;
+                G[tri(i, j)] = (cc - ss) * p + cs * (b - a);
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    double vi = Vs[i * 9 + k][tid], vj = Vs[j * 9 + k][tid];
+                    Vs[i * 9 + k][tid] = c * vi + s * vj;
+                    Vs[j * 9 + k][tid] = -s * vi + c * vj;
+                }
+                changed = true;
+            }
+        }
+        if (!changed) break;
+    }
+    // singular values = sqrt of the diagonal; OpenCV's descending selection sort decides which
+    // row ends up last (vt.row(vt.rows-1), eight_point.cpp:42)
+    double W[9];
+    int perm[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { W[i] = sqrt(fmax(G[tri(i, i)], 0.0)); perm[i] = i; }
+    for (int i = 0; i < 8; i++) {
+        int j = i;
+        for (int k = i + 1; k < 9; k++) if (W[j] < W[k]) j = k;
+        if (i != j) { double t = W[i]; W[i] = W[j]; W[j] = t; int q = perm[i]; perm[i] = perm[j]; perm[j] = q; }
+    }
+    const int last = perm[8];
+    M3 E;
+#pragma unroll
+    for (int k = 0; k < 9; k++) E.v[k] = Vs[last * 9 + k][tid];
+
+    // rank-2 projection (eight_point.cpp:45-50): SVD, sigma3 <- 0, recompose
+    double w[3];
+    M3 U, Vt;
+    svd3(E, w, U, Vt);
+    M3 UD;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { UD.v[3 * i] = U.v[3 * i] * w[0]; UD.v[3 * i + 1] = U.v[3 * i + 1] * w[1]; UD.v[3 * i + 2] = 0.0; }
+    M3 Ec = mul3(UD, Vt);
+#pragma unroll
+    for (int k = 0; k < 9; k++) Eout[(size_t)h * 9 + k] = Ec.v[k];
+    if (WANT_POSE) decompose_pose(Ec, pose + (size_t)h * ERP_POSE_FLOATS);
+}
+
+// ------------------------------------------------------------------ consensus pick (eight_point.cpp:117-149)
+// single block.  pose: H x 12.  Builds the candidate list in hypothesis order (R1 then R2),
+// then each thread owns one candidate: distances to all, sort, trimmed mean; arg-min.
+__global__ void consensus_kernel(const float* __restrict__ pose, int H, float* __restrict__ candR,
+                                 float* __restrict__ candT, double* __restrict__ scratch /* C x C */,
+                                 double* __restrict__ dist, int32_t* __restrict__ out /* [0]=C, [1]=chosen */)
+{
+    __shared__ int C_sh;
+    if (threadIdx.x == 0) {
+        int C = 0;
+        for (int h = 0; h < H; h++) {
+            const float* p = pose + (size_t)h * ERP_POSE_FLOATS;
+            if (p[9] != 0.f) { for (int k = 0; k < 3; k++) { candR[3 * C + k] = p[k]; candT[3 * C + k] = p[6 + k]; } C++; }
+            if (p[10] != 0.f) { for (int k = 0; k < 3; k++) { candR[3 * C + k] = p[3 + k]; candT[3 * C + k] = p[6 + k]; } C++; }
+        }
+        C_sh = C;
+        out[0] = C;
+    }
+    __syncthreads();
+    const int C = C_sh;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        double* row = scratch + (size_t)i * C;
+        for (int j = 0; j < C; j++) {
+            float d0 = __fsub_rn(candR[3 * i], candR[3 * j]), d1 = __fsub_rn(candR[3 * i + 1], candR[3 * j + 1]);
+            float d2 = __fsub_rn(candR[3 * i + 2], candR[3 * j + 2]);
+            float ss = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+            row[j] = (double)__fsqrt_rn(ss);
+        }
+        // shell sort ascending
+        for (int gap = C / 2; gap > 0; gap /= 2)
+            for (int a = gap; a < C; a++) {
+                double x = row[a];
+                int b = a;
+                for (; b >= gap && row[b - gap] > x; b -= gap) row[b] = row[b - gap];
+                row[b] = x;
+            }
+        int lo = (int)(C * 0.2), hi = (int)(C * 0.8);
+        double acc = 0.0;
+        for (int j = lo; j < hi; j++) acc += row[j];
+        dist[i] = acc / ((hi - lo) * 1.0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = C > 0 ? 0 : -1;
+        for (int i = 1; i < C; i++) if (dist[i] < dist[best]) best = i;
+        out[1] = best;
+    }
+}
+
+} // namespace erp
+
+using namespace erp;
+
+// ======================================================================================
+// device-level API
+// ======================================================================================
+ERP_API int erp_bearings_dev(erp_ctx* ctx, const void* d_xy, size_t stride_bytes, int n,
+                             int width, int height, double* d_out3, float* d_out4)
+{
+    ERP_ARG(ctx && n >= 0 && width > 0 && height > 0 && stride_bytes >= 8 && stride_bytes % 4 == 0, ERP_E_ARG,
+            "erp_bearings_dev: bad argument");
+    if (n == 0) return ERP_OK;
+    ERP_ARG(d_xy && (d_out3 || d_out4), ERP_E_ARG, "erp_bearings_dev: null buffer");
+    DeviceGuard g(ctx->device);
+    bearings_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const char*)d_xy, stride_bytes, n, width, height,
+                                                          d_out3, (float4*)d_out4);
+    ERP_LAUNCH(ctx, "bearings_kernel");
+    return ERP_OK;
+}
+
+ERP_API int erp_gather_bearings_dev(erp_ctx* ctx, const erp_dmatch* d_matches, int n,
+                                    const void* d_left_xy, const void* d_right_xy, size_t stride_bytes,
+                                    int q_offset, int width, int height,
+                                    double* d_l3, double* d_r3, float* d_l4, float* d_r4)
+{
+    ERP_ARG(ctx && n >= 0 && width > 0 && height > 0 && stride_bytes >= 8 && stride_bytes % 4 == 0, ERP_E_ARG,
+            "erp_gather_bearings_dev: bad argument");
+    if (n == 0) return ERP_OK;
+    ERP_ARG(d_matches && d_left_xy && d_right_xy, ERP_E_ARG, "erp_gather_bearings_dev: null buffer");
+    DeviceGuard g(ctx->device);
+    gather_bearings_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_matches, n, (const char*)d_left_xy, (const char*)d_right_xy,
+                                                                 stride_bytes, q_offset, width, height, d_l3, d_r3,
+                                                                 (float4*)d_l4, (float4*)d_r4);
+    ERP_LAUNCH(ctx, "gather_bearings_kernel");
+    return ERP_OK;
+}
+
+ERP_API int erp_pack_float4_dev(erp_ctx* ctx, const double* d_v3, int n, float* d_v4)
+{
+    ERP_ARG(ctx && n >= 0, ERP_E_ARG, "erp_pack_float4_dev: bad argument");
+    if (n == 0) return ERP_OK;
+    DeviceGuard g(ctx->device);
+    pack4_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_v3, n, (float4*)d_v4);
+    ERP_LAUNCH(ctx, "pack4_kernel");
+    return ERP_OK;
+}
+
+namespace erp {
+
+// G for H hypotheses into d_G (H x 45)
+int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples,
+               int H, int S, uint64_t seed, uint64_t hyp0, double* d_G)
+{
+    if (S <= SMALL_S) {
+        gram_small_kernel<<<cdiv(H, GW), GW * 32, 0, ctx->stream>>>(d_l3, d_r3, m, d_samples, H, S, seed, hyp0, d_G);
+        ERP_LAUNCH(ctx, "gram_small_kernel");
+        return ERP_OK;
+    }
+    // large samples need an explicit table
+    int slices = max(1, min(cdiv(S, GL_THREADS * 4), max(1, (ctx->sm_count * 4) / max(H, 1))));
+    int st = ERP_OK;
+    double* P = ctx->scratch<double>(S_PARTIAL, (size_t)H * slices * 45, &st);
+    ERP_TRY(st);
+    gram_large_kernel<<<dim3(slices, H), GL_THREADS, 0, ctx->stream>>>(d_l3, d_r3, m, d_samples, S, nullptr, P);
+    ERP_LAUNCH(ctx, "gram_large_kernel");
+    gram_finish_kernel<<<cdiv(H * 45, 256), 256, 0, ctx->stream>>>(P, H, slices, d_G);
+    ERP_LAUNCH(ctx, "gram_finish_kernel");
+    return ERP_OK;
+}
+
+int gram_masked(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const uint8_t* d_mask, double* d_G)
+{
+    int slices = max(1, min(cdiv(m, GL_THREADS * 2), ctx->sm_count * 2));
+    int st = ERP_OK;
+    double* P = ctx->scratch<double>(S_PARTIAL, (size_t)slices * 45, &st);
+    ERP_TRY(st);
+    gram_large_kernel<<<dim3(slices, 1), GL_THREADS, 0, ctx->stream>>>(d_l3, d_r3, m, nullptr, m, d_mask, P);
+    ERP_LAUNCH(ctx, "gram_large_kernel");
+    gram_finish_kernel<<<1, 64, 0, ctx->stream>>>(P, 1, slices, d_G);
+    ERP_LAUNCH(ctx, "gram_finish_kernel");
+    return ERP_OK;
+}
+
+int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose)
+{
+    const int max_sweeps = 30;
+    if (d_pose) solve_kernel<true><<<cdiv(H, SOLVE_THREADS), SOLVE_THREADS, 0, ctx->stream>>>(d_G, H, max_sweeps, d_E, d_pose);
+    else solve_kernel<false><<<cdiv(H, SOLVE_THREADS), SOLVE_THREADS, 0, ctx->stream>>>(d_G, H, max_sweeps, d_E, nullptr);
+    ERP_LAUNCH(ctx, "solve_kernel");
+    return ERP_OK;
+}
+
+int consensus(erp_ctx* ctx, const float* d_pose, int H, float* d_candR, float* d_candT, int32_t* d_out)
+{
+    int st = ERP_OK;
+    size_t C = (size_t)2 * H;
+    double* scr = ctx->scratch<double>(S_CONS, C * C + C, &st);
+    ERP_TRY(st);
+    consensus_kernel<<<1, 256, 0, ctx->stream>>>(d_pose, H, d_candR, d_candT, scr, scr + C * C, d_out);
+    ERP_LAUNCH(ctx, "consensus_kernel");
+    return ERP_OK;
+}
+
+} // namespace erp
+
+ERP_API int erp_eight_point_batch_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m,
+                                      const int32_t* d_samples, int H, int S, uint64_t seed,
+                                      uint64_t hyp_offset, double* d_E, float* d_pose)
+{
+    ERP_ARG(ctx && d_l3 && d_r3 && d_E && H >= 0 && m >= 0, ERP_E_ARG, "erp_eight_point_batch_dev: bad argument");
+    ERP_ARG(S >= 8, ERP_E_TOO_FEW_POINTS, "erp_eight_point_batch_dev: sample size %d < 8", S);
+    ERP_ARG(m >= S, ERP_E_TOO_FEW_POINTS, "erp_eight_point_batch_dev: %d correspondences < sample size %d", m, S);
+    ERP_ARG(d_samples || S <= SMALL_S, ERP_E_ARG, "erp_eight_point_batch_dev: samples table required for S > %d", SMALL_S);
+    if (H == 0) return ERP_OK;
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    double* G = ctx->scratch<double>(S_GRAM, (size_t)H * 45, &st);
+    ERP_TRY(st);
+    ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, d_samples, H, S, seed, hyp_offset, G));
+    ERP_TRY(solve_batch(ctx, G, H, d_E, d_pose));
+    return ERP_OK;
+}
+
+ERP_API int erp_philox_samples(erp_ctx* ctx, uint64_t seed, uint64_t hyp_offset, int H, int S, int m, int32_t* out)
+{
+    ERP_ARG(ctx && out && H >= 0 && S >= 1 && S <= SMALL_S, ERP_E_ARG, "erp_philox_samples: bad argument");
+    ERP_ARG(m >= S, ERP_E_TOO_FEW_POINTS, "erp_philox_samples: m %d < S %d", m, S);
+    if (H == 0) return ERP_OK;
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    int32_t* d = ctx->scratch<int32_t>(S_SAMPLES, (size_t)H * S, &st);
+    ERP_TRY(st);
+    philox_table_kernel<<<cdiv(H, 128), 128, 0, ctx->stream>>>(seed, hyp_offset, H, S, m, d);
+    ERP_LAUNCH(ctx, "philox_table_kernel");
+    ERP_CUDA(cudaMemcpyAsync(out, d, sizeof(int32_t) * (size_t)H * S, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}

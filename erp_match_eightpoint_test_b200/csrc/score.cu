@@ -1,0 +1,300 @@
+// score.cu -- hypothesis scoring, inlier mask, best-model selection and the RANSAC glue.
+//
+// The residual is the one /root/reference/src/epipolar_tool.cpp:100-107 evaluates
+// (result = l . (E^T p), |result| < 0.002), written for eight_point's convention l^T E r.
+// The arithmetic is fp32 with an explicit fma chain and is spelled identically in the oracle
+// (oracle/erp_oracle.c: is_inlier), so inlier COUNTS are bit-exact, not approximately equal:
+//     Eh   = (float)(E * sqrt(2)/|E|_F)
+//     k_ab = l_a * r_b
+//     res  = fma(Eh8,k8, ... fma(Eh1,k1, Eh0*k0))
+#include "common.cuh"
+
+namespace erp {
+
+constexpr int TH = 128;         // hypotheses per block: their scaled E stay in shared memory
+constexpr int SC_THREADS = 256;
+
+template <int METRIC>
+__device__ __forceinline__ bool inlier(const float* __restrict__ E, const float k[9], float4 l, float4 r,
+                                       float tau, float tau2, float sin2)
+{
+    float res = __fmul_rn(E[0], k[0]);
+#pragma unroll
+    for (int i = 1; i < 9; i++) res = __fmaf_rn(E[i], k[i], res);
+    if (METRIC == ERP_METRIC_ALGEBRAIC) return fabsf(res) < tau;
+    float n0 = __fmaf_rn(E[2], r.z, __fmaf_rn(E[1], r.y, __fmul_rn(E[0], r.x)));
+    float n1 = __fmaf_rn(E[5], r.z, __fmaf_rn(E[4], r.y, __fmul_rn(E[3], r.x)));
+    float n2 = __fmaf_rn(E[8], r.z, __fmaf_rn(E[7], r.y, __fmul_rn(E[6], r.x)));
+    float nn = __fmaf_rn(n2, n2, __fmaf_rn(n1, n1, __fmul_rn(n0, n0)));
+    float rr = __fmul_rn(res, res);
+    if (METRIC == ERP_METRIC_ANGULAR) return rr < __fmul_rn(sin2, nn);
+    float m0 = __fmaf_rn(E[6], l.z, __fmaf_rn(E[3], l.y, __fmul_rn(E[0], l.x)));
+    float m1 = __fmaf_rn(E[7], l.z, __fmaf_rn(E[4], l.y, __fmul_rn(E[1], l.x)));
+    float m2 = __fmaf_rn(E[8], l.z, __fmaf_rn(E[5], l.y, __fmul_rn(E[2], l.x)));
+    float mm = __fmaf_rn(m2, m2, __fmaf_rn(m1, m1, __fmul_rn(m0, m0)));
+    return rr < __fmul_rn(tau2, __fadd_rn(nn, mm));
+}
+
+__device__ __forceinline__ void kron9(float4 l, float4 r, float k[9])
+{
+    k[0] = __fmul_rn(l.x, r.x); k[1] = __fmul_rn(l.x, r.y); k[2] = __fmul_rn(l.x, r.z);
+    k[3] = __fmul_rn(l.y, r.x); k[4] = __fmul_rn(l.y, r.y); k[5] = __fmul_rn(l.y, r.z);
+    k[6] = __fmul_rn(l.z, r.x); k[7] = __fmul_rn(l.z, r.y); k[8] = __fmul_rn(l.z, r.z);
+}
+
+__device__ __forceinline__ void scale_E(const double* __restrict__ E, float* __restrict__ Eh)
+{
+    double n = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) n += E[i] * E[i];
+    double s = n > 0 ? sqrt(2.0) / sqrt(n) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) Eh[i] = (float)(E[i] * s);
+}
+
+// grid (ceil(H/TH), msplit).  Each thread keeps C correspondences (their 9 products k_ab) in
+// registers and walks the block's hypothesis tile, whose 9 coefficients arrive as shared-memory
+// broadcasts: 9 FMA-pipe instructions per (hypothesis, correspondence) and nothing else in the
+// inner loop.  The correspondence slice is read once per hypothesis tile (32 B each, coalesced
+// float4 pairs); counts are reduced in-warp (REDUX) and merged in shared memory.
+template <int METRIC, int C>
+__global__ void __launch_bounds__(SC_THREADS)
+score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
+             const float4* __restrict__ r4, int m, float tau, float tau2, float sin2,
+             int32_t* __restrict__ counts)
+{
+    __shared__ __align__(16) float Es[TH][12];
+    __shared__ int cs[TH];
+    const int h0 = blockIdx.x * TH;
+    for (int t = threadIdx.x; t < TH; t += SC_THREADS) {
+        int h = h0 + t;
+        float e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (h < H) scale_E(E + (size_t)h * 9, e);
+#pragma unroll
+        for (int i = 0; i < 9; i++) Es[t][i] = e[i];
+        cs[t] = 0;
+    }
+    __syncthreads();
+    const int nh = min(TH, H - h0);
+    const int per = (m + gridDim.y - 1) / gridDim.y;
+    const int c0 = blockIdx.y * per, c1 = min(m, c0 + per);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int base = c0; base < c1; base += SC_THREADS * C) {
+        float k[C][9];
+        float4 lv[C], rv[C];
+        bool live[C];
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            int c = base + j * SC_THREADS + threadIdx.x;
+            live[j] = c < c1;
+            lv[j] = live[j] ? l4[c] : zero;
+            rv[j] = live[j] ? r4[c] : zero;
+            kron9(lv[j], rv[j], k[j]);
+        }
+#pragma unroll 2
+        for (int h = 0; h < nh; h++) {
+            float4 e0 = *reinterpret_cast<const float4*>(&Es[h][0]);
+            float4 e1 = *reinterpret_cast<const float4*>(&Es[h][4]);
+            float e8 = Es[h][8];
+            float e[9] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e8};
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < C; j++) c += (int)(inlier<METRIC>(e, k[j], lv[j], rv[j], tau, tau2, sin2) & live[j]);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cs[h], c);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nh; t += SC_THREADS) {
+        if (gridDim.y == 1) counts[h0 + t] = cs[t];
+        else if (cs[t]) atomicAdd(&counts[h0 + t], cs[t]);
+    }
+}
+
+// packed best over a count array: (count << 32) | (0xFFFFFFFF - global id)
+__global__ void best_kernel(const int32_t* __restrict__ counts, int H, uint64_t hyp0,
+                            unsigned long long* __restrict__ best)
+{
+    unsigned long long b = 0;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+        unsigned long long id = hyp0 + (unsigned long long)h;
+        unsigned long long p = ((unsigned long long)(uint32_t)counts[h] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)id);
+        b = p > b ? p : b;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long y = __shfl_down_sync(0xffffffffu, b, o);
+        b = y > b ? y : b;
+    }
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(best, b);
+}
+
+template <int METRIC>
+__global__ void mask_kernel(const double* __restrict__ E9, const float4* __restrict__ l4,
+                            const float4* __restrict__ r4, int m, float tau, float tau2, float sin2,
+                            uint8_t* __restrict__ mask, int32_t* __restrict__ n_in)
+{
+    __shared__ float Es[9];
+    if (threadIdx.x == 0) scale_E(E9, Es);
+    __syncthreads();
+    float e[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) e[i] = Es[i];
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    if (c < m) {
+        float4 l = l4[c], r = r4[c];
+        float k[9];
+        kron9(l, r, k);
+        in = inlier<METRIC>(e, k, l, r, tau, tau2, sin2);
+        if (mask) mask[c] = in ? 1 : 0;
+    }
+    int s = __reduce_add_sync(0xffffffffu, in ? 1 : 0);
+    if ((threadIdx.x & 31) == 0 && s && n_in) atomicAdd(n_in, s);
+}
+
+int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples,
+               int H, int S, uint64_t seed, uint64_t hyp0, double* d_G);
+int gram_masked(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const uint8_t* d_mask, double* d_G);
+int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose);
+
+static inline void thresholds(float tau, float& tau2, float& sin2)
+{
+    tau2 = tau * tau;
+    double sd = sin((double)tau);
+    sin2 = (float)(sd * sd);
+}
+
+int score_launch(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m,
+                 int metric, float tau, int32_t* d_counts)
+{
+    float tau2, sin2;
+    thresholds(tau, tau2, sin2);
+    int gx = cdiv(H, TH);
+    // split the correspondences when there are too few hypothesis tiles to fill the machine
+    int msplit = 1;
+    if (gx < ctx->sm_count * 4) msplit = max(1, min(cdiv(m, SC_THREADS * 8), (ctx->sm_count * 4) / gx));
+    // (a zero-padded lane contributes res = 0 < tau, hence the live[] predicate in the kernel)
+    if (msplit > 1) ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H, ctx->stream));
+    dim3 grid(gx, msplit);
+    const float4* l4 = (const float4*)d_l4;
+    const float4* r4 = (const float4*)d_r4;
+    switch (metric) {
+    case ERP_METRIC_ALGEBRAIC: score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts); break;
+    case ERP_METRIC_SAMPSON: score_kernel<ERP_METRIC_SAMPSON, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts); break;
+    case ERP_METRIC_ANGULAR: score_kernel<ERP_METRIC_ANGULAR, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts); break;
+    default: set_error("unknown metric %d", metric); return ERP_E_ARG;
+    }
+    ERP_LAUNCH(ctx, "score_kernel");
+    return ERP_OK;
+}
+
+int mask_launch(erp_ctx* ctx, const double* d_E9, const float* d_l4, const float* d_r4, int m, int metric,
+                float tau, uint8_t* d_mask, int32_t* d_n)
+{
+    float tau2, sin2;
+    thresholds(tau, tau2, sin2);
+    if (d_n) ERP_CUDA(cudaMemsetAsync(d_n, 0, sizeof(int32_t), ctx->stream));
+    if (m == 0) return ERP_OK;
+    const float4* l4 = (const float4*)d_l4;
+    const float4* r4 = (const float4*)d_r4;
+    int grid = cdiv(m, 256);
+    switch (metric) {
+    case ERP_METRIC_ALGEBRAIC: mask_kernel<ERP_METRIC_ALGEBRAIC><<<grid, 256, 0, ctx->stream>>>(d_E9, l4, r4, m, tau, tau2, sin2, d_mask, d_n); break;
+    case ERP_METRIC_SAMPSON: mask_kernel<ERP_METRIC_SAMPSON><<<grid, 256, 0, ctx->stream>>>(d_E9, l4, r4, m, tau, tau2, sin2, d_mask, d_n); break;
+    case ERP_METRIC_ANGULAR: mask_kernel<ERP_METRIC_ANGULAR><<<grid, 256, 0, ctx->stream>>>(d_E9, l4, r4, m, tau, tau2, sin2, d_mask, d_n); break;
+    default: set_error("unknown metric %d", metric); return ERP_E_ARG;
+    }
+    ERP_LAUNCH(ctx, "mask_kernel");
+    return ERP_OK;
+}
+
+} // namespace erp
+
+using namespace erp;
+
+ERP_API int erp_score_dev(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4,
+                          int m, int metric, float tau, uint64_t hyp_offset,
+                          int32_t* d_counts, uint64_t* d_best_packed)
+{
+    ERP_ARG(ctx && H >= 0 && m >= 0, ERP_E_ARG, "erp_score_dev: bad argument");
+    if (H == 0) return ERP_OK;
+    ERP_ARG(d_E && (m == 0 || (d_l4 && d_r4)), ERP_E_ARG, "erp_score_dev: null buffer");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    if (!d_counts) { d_counts = ctx->scratch<int32_t>(S_COUNTS, H, &st); ERP_TRY(st); }
+    if (m == 0) ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H, ctx->stream));
+    else ERP_TRY(score_launch(ctx, d_E, H, d_l4, d_r4, m, metric, tau, d_counts));
+    if (d_best_packed) {
+        best_kernel<<<min(cdiv(H, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(d_counts, H, hyp_offset,
+                                                                                (unsigned long long*)d_best_packed);
+        ERP_LAUNCH(ctx, "best_kernel");
+    }
+    return ERP_OK;
+}
+
+ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3,
+                                 const float* d_l4, const float* d_r4, int m, uint64_t seed,
+                                 uint64_t hyp_offset, int H, int S, int metric, float tau,
+                                 uint64_t* d_packed)
+{
+    ERP_ARG(ctx && d_l3 && d_r3 && d_l4 && d_r4 && d_packed && H >= 0, ERP_E_ARG, "erp_ransac_local_dev: bad argument");
+    ERP_ARG(S >= 8 && S <= 32, ERP_E_ARG, "erp_ransac_local_dev: sample size must be in [8,32], got %d", S);
+    ERP_ARG(m >= S, ERP_E_TOO_FEW_POINTS, "erp_ransac_local_dev: %d correspondences < sample size %d", m, S);
+    ERP_ARG(hyp_offset + (uint64_t)H <= 0xFFFFFFFFull, ERP_E_LIMIT, "hypothesis ids must fit 32 bits");
+    DeviceGuard g(ctx->device);
+    ERP_CUDA(cudaMemsetAsync(d_packed, 0, sizeof(uint64_t), ctx->stream));
+    const int CH = 1 << 18;   // hypotheses per pass: 9.4 MB of Gram + 18.9 MB of E scratch
+    int st = ERP_OK;
+    int chunk = H < CH ? H : CH;
+    double* G = ctx->scratch<double>(S_GRAM, (size_t)chunk * 45, &st);
+    double* E = ctx->scratch<double>(S_E, (size_t)chunk * 9, &st);
+    int32_t* counts = ctx->scratch<int32_t>(S_COUNTS, chunk, &st);
+    ERP_TRY(st);
+    for (int h0 = 0; h0 < H; h0 += CH) {
+        int n = H - h0 < CH ? H - h0 : CH;
+        ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, n, S, seed, hyp_offset + h0, G));
+        ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
+        ERP_TRY(erp_score_dev(ctx, E, n, d_l4, d_r4, m, metric, tau, hyp_offset + h0, counts, d_packed));
+    }
+    return ERP_OK;
+}
+
+ERP_API int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3,
+                                  const float* d_l4, const float* d_r4, int m, uint64_t seed,
+                                  uint64_t packed, int S, int metric, float tau,
+                                  uint8_t* d_mask, erp_ransac_result* result)
+{
+    ERP_ARG(ctx && d_l3 && d_r3 && d_l4 && d_r4 && result, ERP_E_ARG, "erp_ransac_finish_dev: bad argument");
+    ERP_ARG(S >= 8 && S <= 32 && m >= S, ERP_E_TOO_FEW_POINTS, "erp_ransac_finish_dev: bad sample size / too few points");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    uint64_t hyp = 0xFFFFFFFFull - (packed & 0xFFFFFFFFull);
+    // layout of the small result scratch: G(45) | E_best(9) | G_refit(45) | E_refit(9) | pose(12 floats) | n(int)
+    double* misc = ctx->scratch<double>(S_MISC, 128, &st);
+    if (!d_mask) d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m, &st);
+    ERP_TRY(st);
+    double *G = misc, *Eb = misc + 45, *Gr = misc + 54, *Er = misc + 99;
+    float* pose = reinterpret_cast<float*>(misc + 108);
+    int32_t* n_in = reinterpret_cast<int32_t*>(misc + 116);
+    ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, 1, S, seed, hyp, G));   // replay the winning sample
+    ERP_TRY(solve_batch(ctx, G, 1, Eb, nullptr));
+    ERP_TRY(mask_launch(ctx, Eb, d_l4, d_r4, m, metric, tau, d_mask, n_in));
+    ERP_TRY(gram_masked(ctx, d_l3, d_r3, m, d_mask, Gr));                   // refit on the inliers
+    ERP_TRY(solve_batch(ctx, Gr, 1, Er, pose));
+    struct { double Eb[9]; } hb;
+    struct { double Er[9]; float pose[12]; int32_t n; } hr;
+    ERP_CUDA(cudaMemcpyAsync(&hb, Eb, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaMemcpyAsync(hr.Er, Er, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaMemcpyAsync(hr.pose, pose, sizeof(float) * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaMemcpyAsync(&hr.n, n_in, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    result->packed = packed;
+    result->hyp_id = hyp;
+    result->count = (int32_t)(packed >> 32);
+    result->n_refit = hr.n;
+    memcpy(result->E_best, hb.Eb, sizeof hb.Eb);
+    memcpy(result->E_refit, hr.Er, sizeof hr.Er);
+    memcpy(result->pose, hr.pose, sizeof hr.pose);
+    return ERP_OK;
+}

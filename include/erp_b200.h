@@ -1,0 +1,216 @@
+/*
+ * erp_b200.h -- C ABI of the B200-native ERP match + eight-point hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its callers
+ * include plain C++ classes (src/feature_matcher.hpp, src/eight_point.hpp,
+ * src/epipolar_tool.hpp).  The class wrappers under host/ keep those signatures
+ * verbatim and call the functions below; each entry point cites the reference
+ * interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - every function returns an erp_status: 0 ok, > 0 argument/domain error,
+ *    < 0 CUDA failure.  erp_last_error() gives the message (thread local).
+ *  - there is NO CPU fallback: without a CUDA device erp_ctx_create fails.
+ *  - "host" entry points take borrowed host pointers and copy through
+ *    context-owned staging buffers; "_dev" entry points take device pointers,
+ *    enqueue on the context stream and do not synchronise unless stated.
+ *  - row-major, little endian.  fp32 descriptors, fp64 bearings (cv::Point3d),
+ *    erp_dmatch has the layout of cv::DMatch (16 bytes).
+ *  - one context per host thread and device; a context is not thread safe.
+ */
+#ifndef ERP_B200_H
+#define ERP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERP_B200_VERSION 100
+
+typedef struct erp_ctx erp_ctx;
+
+typedef struct {          /* == cv::DMatch */
+    int32_t queryIdx;
+    int32_t trainIdx;
+    int32_t imgIdx;
+    float distance;
+} erp_dmatch;
+
+typedef enum {
+    ERP_OK = 0,
+    ERP_E_ARG = 1,             /* null pointer, negative size, bad stride ...                  */
+    ERP_E_DIM = 2,             /* descriptor dimension not a positive multiple of 4, > 512      */
+    ERP_E_TOO_FEW_TRAIN = 3,   /* k=2 needs >= 2 train rows (the reference throws / is UB)      */
+    ERP_E_TOO_FEW_POINTS = 4,  /* fewer correspondences than the sample size                    */
+    ERP_E_NO_CANDIDATE = 5,    /* initial_guess: no hypothesis passed the <1.57 rad test (UB in ref) */
+    ERP_E_LIMIT = 6,           /* a size exceeds an implementation limit                        */
+    ERP_E_CUDA = -1,
+    ERP_E_NO_DEVICE = -2,
+    ERP_E_ARCH = -3            /* device is not sm_100                                          */
+} erp_status;
+
+typedef enum {
+    ERP_METRIC_ALGEBRAIC = 0,  /* |l^T E r| < tau          (src/epipolar_tool.cpp:100-107, tau 0.002) */
+    ERP_METRIC_SAMPSON = 1,    /* res^2 < tau^2 (|E r|^2 + |E^T l|^2)                             */
+    ERP_METRIC_ANGULAR = 2     /* angle(l, epipolar plane of r) < tau   (one_image_test/main.cpp:27-50) */
+} erp_metric;
+
+/* which distance engine erp_knn2* uses */
+typedef enum {
+    ERP_ENGINE_AUTO = 0,       /* tcgen05 when the shape allows, else exact SIMT */
+    ERP_ENGINE_EXACT_SIMT = 1, /* fp64 direct-form brute force (also the rescan path)            */
+    ERP_ENGINE_TCGEN05 = 2     /* 3xTF32 GEMM-form tiles + fused top-k, exact fp64 refine         */
+} erp_engine;
+
+/* pose record per hypothesis: XYZ-euler of R1, of R2 (rad), t, validity flags (1.0/0.0), 1 pad */
+#define ERP_POSE_FLOATS 12
+
+typedef struct {
+    uint64_t packed;        /* (count << 32) | (0xFFFFFFFF - hyp_id): max == best, ties -> lowest id */
+    uint64_t hyp_id;
+    int32_t  count;         /* inliers of the winning hypothesis (fp32 scoring)                */
+    int32_t  n_refit;       /* correspondences used by the refit (== count)                    */
+    double   E_best[9];     /* rank-2 corrected E of the winning minimal sample                */
+    double   E_refit[9];    /* least-squares eight-point on its inliers (eight_point.cpp:16-50) */
+    float    pose[ERP_POSE_FLOATS]; /* decomposition of E_refit                                */
+} erp_ransac_result;
+
+/* ---------------------------------------------------------------- context */
+const char* erp_last_error(void);
+int  erp_version(void);
+int  erp_device_count(void);
+int  erp_ctx_create(int device, erp_ctx** out);
+void erp_ctx_destroy(erp_ctx* ctx);
+void* erp_ctx_stream(erp_ctx* ctx);                 /* cudaStream_t the context enqueues on */
+int  erp_ctx_synchronize(erp_ctx* ctx);
+int  erp_ctx_set_engine(erp_ctx* ctx, int engine);  /* erp_engine */
+int  erp_ctx_device(erp_ctx* ctx);
+/* number of kernels this context has launched since creation (bench "gpu_launches") */
+uint64_t erp_ctx_launch_count(erp_ctx* ctx);
+/* diagnostics of the last erp_knn2* call: [0] engine used, [1] queries re-scanned exactly,
+ * [2] train chunks, [3] work items, [4] reserved */
+int  erp_ctx_last_knn_stats(erp_ctx* ctx, int64_t out[5]);
+/* device time of the dominant distance kernel of the last erp_knn2* call, from CUDA events the
+ * library records on its own stream around that launch (synchronises the stream) */
+int  erp_ctx_last_knn_kernel_ms(erp_ctx* ctx, float* ms);
+
+/* ---------------------------------------------------------------- matching
+ * replaces feature_matcher::match_two_image      src/feature_matcher.hpp:36, .cpp:42-59
+ *          cv::DescriptorMatcher::knnMatch(k=2)  src/feature_matcher.cpp:45
+ * ratio < 0 disables the ratio test; the reference uses 0.3f (.cpp:47).
+ * cross_check != 0 additionally keeps (q,t) only if q is t's nearest query
+ * (cv::BFMatcher(crossCheck=true) semantics; an extension).
+ * Strides are in bytes between rows (cv::Mat::step).  out needs room for nq records. */
+int erp_knn2_match(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
+                   const float* t, int nt, size_t t_stride_bytes, int dim,
+                   float ratio, int cross_check, erp_dmatch* out, int* n_out);
+/* raw 2-NN: idx2 / dist2 are nq x 2 (nearest first); either may be NULL */
+int erp_knn2_raw(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
+                 const float* t, int nt, size_t t_stride_bytes, int dim,
+                 int32_t* idx2, float* dist2);
+
+/* device-resident forms (dense rows: stride == dim * 4) */
+int erp_knn2_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                 int32_t* d_idx2, float* d_dist2, double* d_d2 /* nq x 2 or NULL */);
+/* nearest query per train row over this rank's queries; indices offset by q_offset.
+ * d_best_d2 (nt doubles) and d_best_q (nt int32) feed the multi-GPU min-reduction. */
+int erp_nn1_reverse_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                        int q_offset, int32_t* d_best_q, double* d_best_d2);
+/* ratio + (optional) cross-check filter with ordered compaction (feature_matcher.cpp:50-56).
+ * d_rev_best_q: nt global query ids or NULL.  d_n_out: one int32 on the device. */
+int erp_match_filter_dev(erp_ctx* ctx, const int32_t* d_idx2, const float* d_dist2, int nq,
+                         float ratio, const int32_t* d_rev_best_q, int q_offset,
+                         erp_dmatch* d_out, int32_t* d_n_out);
+/* the three above chained on one device */
+int erp_knn2_match_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                       float ratio, int cross_check, erp_dmatch* d_out, int32_t* d_n_out);
+
+/* ---------------------------------------------------------------- geometry
+ * pixel -> unit-sphere bearing, replaces src/eight_point.cpp:157-186.
+ * xy points at the first (x,y) float pair; stride 28 == sizeof(cv::KeyPoint). */
+int erp_bearings_from_pixels(erp_ctx* ctx, const void* xy, size_t stride_bytes, int n,
+                             int width, int height, double* out3);
+int erp_bearings_dev(erp_ctx* ctx, const void* d_xy, size_t stride_bytes, int n,
+                     int width, int height, double* d_out3, float* d_out4 /* n x 4 or NULL */);
+/* gather + convert: for match i, left bearing of keypoint queryIdx and right bearing of keypoint
+ * trainIdx (src/spherical_surf.cpp:155-162 followed by src/eight_point.cpp:163-186), fused.
+ * q_offset is subtracted from queryIdx when left_xy holds only this rank's shard. */
+int erp_gather_bearings_dev(erp_ctx* ctx, const erp_dmatch* d_matches, int n,
+                            const void* d_left_xy, const void* d_right_xy, size_t stride_bytes,
+                            int q_offset, int width, int height,
+                            double* d_l3, double* d_r3, float* d_l4, float* d_r4);
+/* fp64 n x 3 -> fp32 n x 4 copies used by scoring */
+int erp_pack_float4_dev(erp_ctx* ctx, const double* d_v3, int n, float* d_v4);
+
+/* batched hypothesis solve, replaces eight_point::eight_point_estimation per hypothesis
+ * (src/eight_point.cpp:16-85).  samples: H x S indices into the m correspondences, or NULL
+ * to draw S distinct indices per hypothesis with Philox4x32-10 keyed by (seed, hyp_offset+h).
+ * E_out: H x 9 rank-2 corrected E (l^T E r = 0, row major).  pose_out: H x 12 or NULL. */
+int erp_eight_point_batch(erp_ctx* ctx, const double* l3, const double* r3, int m,
+                          const int32_t* samples, int H, int S, uint64_t seed, uint64_t hyp_offset,
+                          double* E_out, float* pose_out);
+int erp_eight_point_batch_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m,
+                              const int32_t* d_samples, int H, int S, uint64_t seed,
+                              uint64_t hyp_offset, double* d_E, float* d_pose);
+/* the Philox sample table alone (for replay by the oracle): out H x S */
+int erp_philox_samples(erp_ctx* ctx, uint64_t seed, uint64_t hyp_offset, int H, int S, int m,
+                       int32_t* out);
+
+/* eight_point::eight_point_estimation called directly on n >= 8 correspondences
+ * (src/manual.cpp:152): the N-point least-squares solve, also used as the refit. */
+int erp_eight_point_estimation(erp_ctx* ctx, const double* l3, const double* r3, int n,
+                               double* E_out /* 9 or NULL */, float* R1_vec, float* R2_vec,
+                               float* T_vec, int* R1_valid, int* R2_valid);
+
+/* ---------------------------------------------------------------- scoring / RANSAC
+ * residual of src/epipolar_tool.cpp:100-107 over all correspondences per hypothesis */
+int erp_score(erp_ctx* ctx, const double* E, int H, const double* l3, const double* r3, int m,
+              int metric, float tau, int32_t* counts);
+int erp_score_dev(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4,
+                  int m, int metric, float tau, uint64_t hyp_offset,
+                  int32_t* d_counts /* H or NULL */, uint64_t* d_best_packed /* 1, max-merged, or NULL */);
+int erp_inlier_mask(erp_ctx* ctx, const double* E9, const double* l3, const double* r3, int m,
+                    int metric, float tau, uint8_t* mask, int* n_inliers);
+/* least-squares refit on mask != 0 (mask NULL = all points) */
+int erp_refit(erp_ctx* ctx, const double* l3, const double* r3, int m, const uint8_t* mask,
+              double* E_out, float* pose_out);
+
+/* whole minimal-sample RANSAC on one device: hypotheses [hyp_offset, hyp_offset+H) */
+int erp_ransac(erp_ctx* ctx, const double* l3, const double* r3, int m, uint64_t seed,
+               uint64_t hyp_offset, int H, int S, int metric, float tau,
+               erp_ransac_result* result, uint8_t* mask /* m or NULL */);
+/* sharded form: every rank scores its hypothesis range and leaves its packed best in
+ * d_packed (one uint64 on the device); the caller max-reduces it across ranks (one 8-byte
+ * NCCL allreduce) and calls erp_ransac_finish_dev with the winning packed value. */
+int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3,
+                         const float* d_l4, const float* d_r4, int m, uint64_t seed,
+                         uint64_t hyp_offset, int H, int S, int metric, float tau,
+                         uint64_t* d_packed);
+int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3,
+                          const float* d_l4, const float* d_r4, int m, uint64_t seed,
+                          uint64_t packed, int S, int metric, float tau,
+                          uint8_t* d_mask /* m or NULL */, erp_ransac_result* result /* host */);
+
+/* ---------------------------------------------------------------- reference mode
+ * eight_point::initial_guess  src/eight_point.hpp:20-23, .cpp:87-150
+ * samples: H x S table (H = 80, S = int(m*0.25) in the reference) or NULL to replay
+ * libstdc++ random_shuffle over never-seeded glibc rand() (src/eight_point.hpp:54-58).
+ * cand_R / cand_T: room for 2H x 3 floats, or NULL. */
+int erp_initial_guess(erp_ctx* ctx, const double* l3, const double* r3, int m,
+                      const int32_t* samples, int H, int S,
+                      float* R_vec_out, float* T_vec_out,
+                      float* cand_R, float* cand_T, int* n_cand, int* chosen);
+/* eight_point::find  src/eight_point.hpp:11-14, .cpp:152-192 */
+int erp_find(erp_ctx* ctx, int width, int height, const void* left_xy, const void* right_xy,
+             size_t stride_bytes, int match_size, const int32_t* samples, int H, int S,
+             float* R_vec_out, float* T_vec_out);
+/* host-side replay of random_array (glibc TYPE_3 rand + libstdc++ shuffle): H x S */
+int erp_libstdcxx_sample_table(int m, int H, int S, unsigned seed, int32_t* table);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERP_B200_H */

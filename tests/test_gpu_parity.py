@@ -1,0 +1,277 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs, against the committed cv2 golden vectors, and -- at
+BASELINE.json's full sizes -- through size-independent properties.
+
+Bars (north_star): match indices and distances bit-exact (the oracle and the device spell
+the same fp64 chain); inlier counts and masks bit-exact (same fp32 fma chain); E within 1e-5
+Frobenius after sign/scale normalisation given the same samples; poses within 1e-5.
+"""
+import numpy as np
+import pytest
+
+import erp_match_eightpoint_test_b200 as erp
+import oracle as O
+from conftest import e_dist
+from erp_match_eightpoint_test_b200 import binding, synth
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-5        # north_star: ||E_dev - E_ref||_F after sign and scale normalisation
+POSE_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = erp.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def scene():
+    kp = synth.keypoint_pair(3000, 4096, 2048, seed=9)
+    l, r = O.bearings(kp["left_xy"], 4096, 2048), O.bearings(kp["right_xy"], 4096, 2048)
+    return kp, l, r
+
+
+def engines():
+    return [binding.ENGINE_EXACT_SIMT, binding.ENGINE_AUTO]
+
+
+# ------------------------------------------------------------------ matching
+@pytest.mark.parametrize("engine", engines())
+@pytest.mark.parametrize("nq,nt,dim", [(1000, 1500, 64), (517, 733, 128), (64, 2, 64), (1, 300, 64),
+                                        (333, 4097, 64), (200, 300, 4), (130, 140, 100)])
+def test_knn2_bit_exact_vs_oracle(ctx, engine, nq, nt, dim):
+    ctx.set_engine(engine)
+    q, t, _ = synth.descriptor_pair(nq, nt, dim, seed=nq + nt)
+    if nt > 40:
+        t[37] = t[12]; t[5] = t[12]; q[0] = t[12]            # exact ties -> lowest trainIdx first
+    idx, dist = ctx.knn2_raw(q, t)
+    oidx, odist, _ = O.knn2(q, t)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(dist.view(np.uint32), odist.view(np.uint32))   # bit-exact distances
+    ctx.set_engine(binding.ENGINE_AUTO)
+
+
+@pytest.mark.parametrize("engine", engines())
+@pytest.mark.parametrize("name", ["m64", "m128"])
+def test_knn2_matches_cv2_golden(ctx, golden, engine, name):
+    ctx.set_engine(engine)
+    g = golden["matching"]
+    idx, dist = ctx.knn2_raw(g[name + "_q"], g[name + "_t"])
+    assert np.array_equal(idx, g[name + "_idx"])
+    assert np.allclose(dist, g[name + "_dist"], rtol=2e-6, atol=1e-7)     # cv2 sums in fp32 lanes
+    m = ctx.knn2_match(g[name + "_q"], g[name + "_t"], ratio=-1.0, cross_check=True)
+    assert np.array_equal(np.stack([m["queryIdx"], m["trainIdx"]], 1), g[name + "_cross"])
+    ctx.set_engine(binding.ENGINE_AUTO)
+
+
+@pytest.mark.parametrize("engine", engines())
+@pytest.mark.parametrize("ratio,cross", [(0.3, False), (-1.0, False), (0.3, True), (0.8, True)])
+def test_match_two_image_records(ctx, engine, ratio, cross):
+    ctx.set_engine(engine)
+    q, t, planted = synth.descriptor_pair(2500, 2200, 64, seed=5)
+    got = ctx.knn2_match(q, t, ratio=ratio, cross_check=cross)
+    want = O.match(q, t, ratio=ratio, cross_check=cross)
+    assert got.dtype == binding.DMATCH and len(got) == len(want)
+    assert got.tobytes() == want.tobytes()                                 # every field, bit for bit
+    assert (np.diff(got["queryIdx"]) > 0).all()                            # ascending queryIdx
+    if ratio == 0.3 and not cross:
+        assert (planted[got["queryIdx"]] == got["trainIdx"]).all()
+    ctx.set_engine(binding.ENGINE_AUTO)
+
+
+def test_match_edge_cases(ctx):
+    q, t, _ = synth.descriptor_pair(10, 5, 64, seed=1)
+    assert len(ctx.knn2_match(q[:0], t)) == 0                              # empty query set
+    with pytest.raises(erp.ErpError) as ei:                                # knnMatch(k=2) on one row
+        ctx.knn2_match(q, t[:1])
+    assert ei.value.status == binding.E_TOO_FEW_TRAIN
+    with pytest.raises(erp.ErpError) as ei:
+        ctx.knn2_match(q[:, :63], t[:, :63])
+    assert ei.value.status == binding.E_DIM
+    # cv::Mat with a row step larger than the row (a column range of a wider matrix)
+    wide = np.zeros((10, 96), np.float32)
+    wide[:, :64] = q
+    sub = wide[:, :64]
+    lib = erp.lib()
+    out = np.empty(10, binding.DMATCH)
+    n = np.zeros(1, np.int32)
+    import ctypes
+    st = lib.erp_knn2_match(ctx._h, sub.ctypes.data, 10, sub.strides[0], t.ctypes.data, 5, t.strides[0], 64,
+                            -1.0, 0, out.ctypes.data, n.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert st == 0 and out[: n[0]].tobytes() == O.match(q, t, ratio=-1.0).tobytes()
+
+
+# ------------------------------------------------------------------ geometry
+def test_bearings(ctx):
+    kp = synth.keypoint_pair(5000, 8192, 4096, seed=2)
+    for xy in (kp["left_xy"], kp["right_xy"]):
+        got, want = ctx.bearings(xy, 8192, 4096), O.bearings(xy, 8192, 4096)
+        assert np.abs(got - want).max() < 1e-14           # CUDA sincos vs glibc: a few ulp
+        assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 1e-14
+    assert ctx.bearings(kp["left_xy"][:0], 8192, 4096).shape == (0, 3)
+
+
+def test_philox_table_matches_oracle(ctx):
+    for (seed, off, H, S, m) in [(7, 0, 500, 8, 3000), (2**40 + 3, 10**6, 64, 8, 9), (1, 5, 33, 12, 40), (9, 0, 10, 8, 8)]:
+        got = ctx.philox_samples(seed, off, H, S, m)
+        want = np.stack([O.philox_samples(seed, off + h, m, S) for h in range(H)])
+        assert np.array_equal(got, want)
+
+
+def _pose_close(pose, ref):
+    """pose: 12 floats (R1e, R2e, T, v1, v2).  {R1,R2} compared as a set: which rotation is
+    called R1 depends on the sign of a numerically-zero singular vector."""
+    a = np.abs(pose[0:3] - ref["R1"]).max() + np.abs(pose[3:6] - ref["R2"]).max()
+    b = np.abs(pose[0:3] - ref["R2"]).max() + np.abs(pose[3:6] - ref["R1"]).max()
+    swapped = b < a
+    v = (bool(pose[9]), bool(pose[10]))
+    vref = (ref["R1_valid"], ref["R2_valid"])
+    if swapped:
+        vref = vref[::-1]
+    return min(a, b), np.abs(pose[6:9] - ref["T"]).max(), v == vref
+
+
+@pytest.mark.parametrize("S", [8, 9, 16, 32])
+def test_eight_point_batch_minimal_samples(ctx, scene, S):
+    kp, l, r = scene
+    H = 400
+    samples = ctx.philox_samples(11, 0, H, S, len(l))
+    E, pose = ctx.eight_point_batch(l, r, samples=samples)
+    Ephi, _ = ctx.eight_point_batch(l, r, H=H, S=S, seed=11, hyp_offset=0, want_pose=False)
+    assert np.array_equal(E, Ephi)                         # device-drawn samples == replayed table
+    worst, n_bad = 0.0, 0
+    for h in range(H):
+        ref = O.eight_point(l[samples[h]], r[samples[h]], null_mode=1)
+        d = e_dist(E[h], ref["E"])
+        s = np.linalg.svd(np.einsum("na,nb->nab", l[samples[h]], r[samples[h]]).reshape(S, 9), compute_uv=False)
+        well = s[7] / s[0] > 1e-5                          # sample not (numerically) degenerate
+        if well:
+            worst = max(worst, d)
+            dr, dt, vok = _pose_close(pose[h], ref)
+            assert dr < POSE_TOL * 10 and dt < POSE_TOL and vok, (h, dr, dt)
+        n_bad += d > E_TOL
+    assert worst < E_TOL, worst
+    assert n_bad <= H // 100
+
+
+def test_eight_point_estimation_and_golden(ctx, golden, scene):
+    g = golden["eight_point"]
+    for k in range(3):
+        l, r = g[f"l{k}"], g[f"r{k}"]
+        res = ctx.eight_point_estimation(l, r)
+        assert e_dist(res["E"], g[f"Ec{k}"]) < E_TOL       # cv2.SVDecomp pipeline (eight_point.cpp:22-50)
+        ref = O.eight_point(l, r, null_mode=0)
+        assert e_dist(res["E"], ref["E"]) < 1e-8
+    kp, l, r = scene
+    inl = kp["inlier"]
+    res = ctx.eight_point_estimation(l[inl], r[inl])
+    ref = O.eight_point(l[inl], r[inl])
+    assert e_dist(res["E"], ref["E"]) < 1e-8 and e_dist(res["E"], kp["E"]) < 5e-3
+    pose = np.concatenate([res["R1"], res["R2"], res["T"], [res["R1_valid"], res["R2_valid"], 0]]).astype(np.float32)
+    dr, dt, vok = _pose_close(pose, ref)
+    assert dr < POSE_TOL and dt < POSE_TOL and vok
+    with pytest.raises(erp.ErpError) as ei:
+        ctx.eight_point_estimation(l[:7], r[:7])
+    assert ei.value.status == binding.E_TOO_FEW_POINTS
+
+
+# ------------------------------------------------------------------ scoring / RANSAC
+@pytest.mark.parametrize("metric,tau", [(0, 0.002), (1, 0.002), (2, 0.002), (0, 0.01)])
+@pytest.mark.parametrize("m", [3000, 777, 1])
+def test_score_counts_bit_exact(ctx, scene, metric, tau, m):
+    kp, l, r = scene
+    E, _ = ctx.eight_point_batch(l, r, H=300, S=8, seed=5, want_pose=False)
+    E = np.concatenate([E, kp["E"][None], -2.5 * kp["E"][None], np.zeros((1, 3, 3))])
+    got = ctx.score(E, l[:m], r[:m], metric, tau)
+    want = O.score(E, l[:m], r[:m], metric, tau)
+    assert np.array_equal(got, want)
+    mask, n = ctx.inlier_mask(kp["E"], l[:m], r[:m], metric, tau)
+    assert np.array_equal(mask, O.inlier_mask(kp["E"], l[:m], r[:m], metric, tau)) and n == mask.sum() == got[300]
+
+
+def test_refit_on_inliers(ctx, scene):
+    kp, l, r = scene
+    mask = O.inlier_mask(kp["E"], l, r)
+    E, pose = ctx.refit(l, r, mask)
+    ref = O.eight_point(l[mask > 0], r[mask > 0])
+    assert e_dist(E, ref["E"]) < 1e-8
+    dr, dt, vok = _pose_close(pose, ref)
+    assert dr < POSE_TOL and dt < POSE_TOL and vok
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2])
+def test_ransac_same_winner_same_inliers(ctx, scene, metric):
+    kp, l, r = scene
+    H = 1500
+    got = ctx.ransac(l, r, seed=42, hyp_offset=0, H=H, S=8, metric=metric, tau=0.002)
+    want = O.ransac(l, r, seed=42, hyp0=0, H=H, S=8, metric=metric, tau=0.002)
+    assert got["packed"] == want["packed"]                 # same hypothesis, same inlier count
+    assert e_dist(got["E"], want["E"]) < E_TOL
+    omask = O.inlier_mask(want["E"], l, r, metric, 0.002)
+    assert np.array_equal(got["mask"], omask) and got["n_refit"] == got["count"] == omask.sum()
+    ref = O.eight_point(l[omask > 0], r[omask > 0])
+    assert e_dist(got["E_refit"], ref["E"]) < 1e-8
+    assert e_dist(got["E_refit"], kp["E"]) < 5e-3          # and it is the right answer
+    # sharded hypothesis ranges: max of the packed words == the single-range result
+    a = ctx.ransac(l, r, seed=42, hyp_offset=0, H=700, S=8, metric=metric)
+    b = ctx.ransac(l, r, seed=42, hyp_offset=700, H=800, S=8, metric=metric)
+    assert max(a["packed"], b["packed"]) == got["packed"]
+
+
+# ------------------------------------------------------------------ reference mode
+@pytest.mark.parametrize("m", [2000, 400, 100, 50, 40])
+def test_initial_guess_reference_mode(ctx, m):
+    """eight_point::initial_guess with the libstdc++/glibc sample replay (H=80, S=m/4)."""
+    kp = synth.keypoint_pair(m, 4096, 2048, noise_px=0.3, outlier_frac=0.0, seed=60 + m)
+    l, r = O.bearings(kp["left_xy"], 4096, 2048), O.bearings(kp["right_xy"], 4096, 2048)
+    table = O.ref_sample_table(m)
+    got = ctx.initial_guess(l, r)                          # samples=None -> in-library replay
+    want = O.initial_guess(l, r, table, null_mode=1)
+    assert len(got["cand_R"]) == len(want["cand_R"])
+    # candidate lists agree as multisets of (R, T) (R1/R2 order inside one hypothesis may swap)
+    key = lambda R, T: np.lexsort(np.round(np.concatenate([R, T], 1), 4).T[::-1])
+    gi, wi = key(got["cand_R"], got["cand_T"]), key(want["cand_R"], want["cand_T"])
+    assert np.abs(got["cand_R"][gi] - want["cand_R"][wi]).max() < 1e-4
+    assert np.abs(got["R"] - want["R"]).max() < POSE_TOL and np.abs(got["T"] - want["T"]).max() < POSE_TOL
+    assert np.rad2deg(np.abs(got["R"] - O.rot2eular(kp["R"].T))).mean() < 1.0   # two_synthesis_image_test bar
+
+
+def test_find_end_to_end(ctx):
+    kp = synth.keypoint_pair(1200, 4096, 2048, euler_deg=(10, 5, 20), noise_px=0.3, outlier_frac=0.0, seed=77)
+    R, T = ctx.find(4096, 2048, kp["left_xy"], kp["right_xy"])
+    l, r = O.bearings(kp["left_xy"], 4096, 2048), O.bearings(kp["right_xy"], 4096, 2048)
+    want = O.initial_guess(l, r, O.ref_sample_table(1200))
+    assert np.abs(R - want["R"]).max() < POSE_TOL and np.abs(T - want["T"]).max() < POSE_TOL
+    # match_size smaller than the keypoint vectors (two_real_image_test/main.cpp:278-286)
+    R2, T2 = ctx.find(4096, 2048, kp["left_xy"], kp["right_xy"], match_size=100)
+    w2 = O.initial_guess(l[:100], r[:100], O.ref_sample_table(100))
+    assert np.abs(R2 - w2["R"]).max() < POSE_TOL
+    with pytest.raises(erp.ErpError) as ei:                # S = int(20*0.25) = 5 < 8
+        ctx.find(4096, 2048, kp["left_xy"], kp["right_xy"], match_size=20)
+    assert ei.value.status == binding.E_TOO_FEW_POINTS
+
+
+# ------------------------------------------------------------------ BASELINE sizes, properties
+def test_cfg2_full_size_properties(ctx):
+    """configs[1]: 20k x 20k SURF-64 + 10k hypotheses on one GPU."""
+    q, t, planted = synth.descriptor_pair(20000, 20000, 64, seed=synth.SEED_BASE + 1)
+    m = ctx.knn2_match(q, t, ratio=0.3)
+    assert len(m) == (planted >= 0).sum() and (planted[m["queryIdx"]] == m["trainIdx"]).all()
+    # a 1/16 sub-sample of the queries checked exactly against the oracle
+    sub = np.arange(0, 20000, 16)
+    idx, dist = ctx.knn2_raw(q, t)
+    oidx, odist, _ = O.knn2(q[sub], t)
+    assert np.array_equal(idx[sub], oidx) and np.array_equal(dist[sub], odist)
+    # cross-check is idempotent and symmetric: matching t->q gives the mirrored pairs
+    a = ctx.knn2_match(q, t, ratio=-1.0, cross_check=True)
+    b = ctx.knn2_match(t, q, ratio=-1.0, cross_check=True)
+    assert set(zip(a["queryIdx"].tolist(), a["trainIdx"].tolist())) == set(zip(b["trainIdx"].tolist(), b["queryIdx"].tolist()))
+    kp = synth.keypoint_pair(len(m), 4096, 2048, seed=synth.SEED_BASE + 2)
+    l, r = ctx.bearings(kp["left_xy"], 4096, 2048), ctx.bearings(kp["right_xy"], 4096, 2048)
+    res = ctx.ransac(l, r, seed=1, hyp_offset=0, H=10000)
+    assert e_dist(res["E_refit"], kp["E"]) < 5e-3 and res["count"] > 0.55 * len(m)
+    assert res["mask"].sum() == res["count"]
+    assert (res["mask"][kp["inlier"]].mean() > 0.8) and (res["mask"][~kp["inlier"]].mean() < 0.1)
