@@ -319,6 +319,8 @@ def run_gpu(args, cfg):
     h2d = pq.nbytes + pt.nbytes + 2 * len(mt) * 8 + 2 * len(mt) * 24
     d2h = len(mt) * 16 + 2 * len(mt) * 24 + len(mt) + 256
 
+    stats = ctx.last_knn_stats()
+    ctx.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -338,7 +340,6 @@ def run_gpu(args, cfg):
     units = world * nq * nt if not strong else nq_all * nt
     hyps_total = (world if not strong else 1) * cfg["hyps"]
     value = args.steps * units / (t_match * 1e-3)
-    stats = ctx.last_knn_stats()
     engine = {1: "exact_simt_fp64", 2: "tcgen05_3xtf32"}.get(stats["engine"], str(stats["engine"]))
     # roofline of the dominant kernel (the distance kernel): algorithmic flops = 2*D per dist-eval
     k_s = t_kernel * 1e-3 / args.steps

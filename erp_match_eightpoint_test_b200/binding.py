@@ -6,8 +6,10 @@ import of ``oracle``: if the library is missing or no B200 is visible the call r
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -139,6 +141,16 @@ def libstdcxx_sample_table(m: int, H: int = 80, S: int | None = None, seed: int 
     return t
 
 
+_live = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all():
+    # destroy contexts while the CUDA runtime is still alive (not from __del__ at interpreter teardown)
+    for c in list(_live):
+        c.close()
+
+
 class Context:
     """One CUDA stream + scratch on one device (include/erp_b200.h: erp_ctx)."""
 
@@ -146,6 +158,7 @@ class Context:
         self._h = C.c_void_p()
         _check(lib().erp_ctx_create(device, C.byref(self._h)))
         self.device = device
+        _live.add(self)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
