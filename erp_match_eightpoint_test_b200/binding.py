@@ -195,7 +195,7 @@ class Context:
     def last_knn_stats(self):
         out = (C.c_int64 * 5)()
         _check(lib().erp_ctx_last_knn_stats(self._h, out))
-        return dict(engine=out[0], rescanned=out[1], chunks=out[2], items=out[3])
+        return dict(engine=out[0], rescanned=out[1], chunks=out[2], items=out[3], deviation=out[4] * 1e-12)
 
     def last_knn_kernel_ms(self) -> float:
         ms = C.c_float(0)

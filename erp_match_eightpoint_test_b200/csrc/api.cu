@@ -150,6 +150,17 @@ ERP_API int erp_ctx_last_knn_stats(erp_ctx* ctx, int64_t out[5])
 {
     ERP_ARG(ctx && out, ERP_E_ARG, "erp_ctx_last_knn_stats: bad argument");
     memcpy(out, ctx->knn_stats, sizeof ctx->knn_stats);
+    if (ctx->knn_stats[0] == ERP_ENGINE_TCGEN05 && ctx->tc_misc_dev) {
+        // the re-scan count and the observed deviation live on the device
+        DeviceGuard g(ctx->device);
+        int32_t w[4] = {0, 0, 0, 0};
+        ERP_CUDA(cudaMemcpyAsync(w, ctx->tc_misc_dev, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        out[1] = w[0];
+        float dev;
+        memcpy(&dev, &w[2], 4);
+        out[4] = (int64_t)((double)dev * 1e12);     // max |s_tc - s_exact| / (|q|^2 + max|t|^2), in 1e-12 units
+    }
     return ERP_OK;
 }
 
@@ -173,11 +184,12 @@ ERP_API int erp_knn2_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_
     if (nq == 0) return ERP_OK;
     ERP_ARG(d_q && d_t, ERP_E_ARG, "erp_knn2_dev: null descriptors");
     DeviceGuard g(ctx->device);
-    bool tc = ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_supported(nq, nt, dim));
+    bool tc = ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_preferred(nq, nt, dim));
     if (ctx->engine == ERP_ENGINE_TCGEN05)
         ERP_ARG(knn2_tc_supported(nq, nt, dim), ERP_E_DIM, "tcgen05 engine does not support nq=%d nt=%d dim=%d", nq, nt, dim);
     if (tc) return knn2_tc(ctx, d_q, nq, d_t, nt, dim, d_idx2, d_dist2, d_d2);
     ctx->knn_stats[0] = ERP_ENGINE_EXACT_SIMT; ctx->knn_stats[1] = 0; ctx->knn_stats[2] = 1; ctx->knn_stats[3] = cdiv(nq, 64);
+    ctx->knn_stats[4] = 0;
     ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
     ERP_TRY(knn2_exact(ctx, d_q, nq, d_t, nt, dim, nullptr, 0, 0, d_idx2, d_dist2, d_d2));
     ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
@@ -211,7 +223,7 @@ ERP_API int erp_nn1_reverse_dev(erp_ctx* ctx, const float* d_q, int nq, const fl
     int32_t* idx2 = ctx->scratch<int32_t>(S_RS_IDX, (size_t)nt * 2, &st);
     double* d2 = ctx->scratch<double>(S_RS_D2, (size_t)nt * 2, &st);
     ERP_TRY(st);
-    bool tc = nq >= 2 && (ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_supported(nt, nq, dim)));
+    bool tc = nq >= 2 && (ctx->engine == ERP_ENGINE_TCGEN05 ? knn2_tc_supported(nt, nq, dim) : (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_preferred(nt, nq, dim)));
     if (tc) {
         ERP_TRY(knn2_tc(ctx, d_t, nt, d_q, nq, dim, idx2, nullptr, d2));
         // tc path has no index offset: add it while compacting

@@ -55,7 +55,7 @@ enum ScratchId {
     S_L3, S_R3, S_L4, S_R4, S_XY, S_SAMPLES, S_GRAM, S_E, S_EF, S_POSE, S_COUNTS, S_PACKED,
     S_MASK, S_PARTIAL, S_CONS, S_MISC,
     S_TC_Q, S_TC_T, S_TC_QN, S_TC_TN, S_TC_CAND, S_TC_LIST, S_TC_MISC,
-    S_RS_IDX, S_RS_DIST, S_RS_D2,
+    S_RS_IDX, S_RS_DIST, S_RS_D2, S_RS_PARTIAL,
     S_COUNT_
 };
 
@@ -68,6 +68,7 @@ struct erp_ctx {
     int engine = ERP_ENGINE_AUTO;
     uint64_t launches = 0;
     int64_t knn_stats[5] = {0, 0, 0, 0, 0};
+    int32_t* tc_misc_dev = nullptr;                 // device words of the last tcgen05 call: re-scan count, ., deviation
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around the dominant distance kernel
     erp::Buf dev[erp::S_COUNT_];
     erp::Buf pinned[8];
@@ -115,5 +116,6 @@ int knn2_exact(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt,
 int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
             int32_t* d_idx2, float* d_dist2, double* d_d2);
 bool knn2_tc_supported(int nq, int nt, int dim);
+bool knn2_tc_preferred(int nq, int nt, int dim);
 
 } // namespace erp

@@ -30,30 +30,43 @@ __device__ __forceinline__ void top2_insert(double d, int i, double& b0, int& i0
     }
 }
 
-// grid.x = ceil(n_rows / QT).  n_rows = nlist when qlist != nullptr else nq.
+// grid.x = ceil(n_rows / QT) row groups, grid.y = T slices.
+// Rows: r in [row_base, row_base + n_rows), further limited by *n_rows_dev when given (a list whose
+// length only the device knows: blocks past the end exit).  Row r is query qlist[r] (or r).
+// With one T slice the block writes final results; with several it writes its partial top-2 to
+// partial[r * gridDim.y + slice] for knn2_merge_kernel.
+struct Top2 { double d0, d1; int i0, i1; };
+
 __global__ void __launch_bounds__(256)
 knn2_exact_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim,
-                  const int32_t* __restrict__ qlist, int n_rows, int idx_offset,
-                  int32_t* __restrict__ idx2, float* __restrict__ dist2, double* __restrict__ d2out)
+                  const int32_t* __restrict__ qlist, int row_base, int n_rows, const int32_t* __restrict__ n_rows_dev,
+                  int idx_offset, int32_t* __restrict__ idx2, float* __restrict__ dist2, double* __restrict__ d2out,
+                  Top2* __restrict__ partial)
 {
     __shared__ __align__(16) double Qs[KC][PITCH];
     __shared__ __align__(16) double Ts[KC][PITCH];
     __shared__ int qrow[QT];
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int q0 = blockIdx.x * QT;
+    int row_end = row_base + n_rows;
+    if (n_rows_dev) row_end = min(row_end, *n_rows_dev);
+    const int q0 = row_base + blockIdx.x * QT;
+    if (q0 >= row_end) return;
     if (tid < QT) {
         int r = q0 + tid;
-        qrow[tid] = r < n_rows ? (qlist ? qlist[r] : r) : -1;
+        qrow[tid] = r < row_end ? (qlist ? qlist[r] : r) : -1;
     }
     __syncthreads();
+    // T slice of this block (multiples of TT so that tiles never straddle slices)
+    const int per = ((nt + (int)gridDim.y - 1) / (int)gridDim.y + TT - 1) / TT * TT;
+    const int t_begin = min(nt, (int)blockIdx.y * per), t_end = min(nt, t_begin + per);
 
     double b0[4], b1[4];
     int i0[4], i1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) { b0[i] = b1[i] = INFINITY; i0[i] = i1[i] = 0x7fffffff; }
 
-    for (int t0 = 0; t0 < nt; t0 += TT) {
+    for (int t0 = t_begin; t0 < t_end; t0 += TT) {
         double acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -69,7 +82,7 @@ knn2_exact_kernel(const float* __restrict__ q, int nq, const float* __restrict__
                 int qr = qrow[row];
                 if (qr >= 0 && k < dim) a = *reinterpret_cast<const float4*>(q + (size_t)qr * dim + k);
                 int tr = t0 + row;
-                if (tr < nt && k < dim) b = *reinterpret_cast<const float4*>(t + (size_t)tr * dim + k);
+                if (tr < t_end && k < dim) b = *reinterpret_cast<const float4*>(t + (size_t)tr * dim + k);
                 Qs[c4 * 4 + 0][row] = (double)a.x; Qs[c4 * 4 + 1][row] = (double)a.y;
                 Qs[c4 * 4 + 2][row] = (double)a.z; Qs[c4 * 4 + 3][row] = (double)a.w;
                 Ts[c4 * 4 + 0][row] = (double)b.x; Ts[c4 * 4 + 1][row] = (double)b.y;
@@ -97,7 +110,7 @@ knn2_exact_kernel(const float* __restrict__ q, int nq, const float* __restrict__
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int tr = t0 + tx * 4 + j;
-            if (tr < nt) {
+            if (tr < t_end) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) top2_insert(acc[i][j], tr, b0[i], i0[i], b1[i], i1[i]);
             }
@@ -119,6 +132,11 @@ knn2_exact_kernel(const float* __restrict__ q, int nq, const float* __restrict__
         double B0 = INFINITY, B1 = INFINITY;
         int I0 = 0x7fffffff, I1 = 0x7fffffff;
         for (int c = 0; c < 32; c++) top2_insert(md[tid * 32 + c], mi[tid * 32 + c], B0, I0, B1, I1);
+        if (gridDim.y > 1) {
+            Top2 r; r.d0 = B0; r.d1 = B1; r.i0 = I0; r.i1 = I1;
+            partial[(size_t)(q0 + tid) * gridDim.y + blockIdx.y] = r;
+            return;
+        }
         int o = qrow[tid];
         if (idx2) {
             idx2[2 * o] = I0 == 0x7fffffff ? -1 : I0 + idx_offset;
@@ -129,15 +147,77 @@ knn2_exact_kernel(const float* __restrict__ q, int nq, const float* __restrict__
     }
 }
 
+// merges the T-slice partials of listed row r (one thread per row)
+__global__ void knn2_merge_kernel(const Top2* __restrict__ partial, int slices, const int32_t* __restrict__ qlist,
+                                  int n_rows, const int32_t* __restrict__ n_rows_dev, int idx_offset,
+                                  int32_t* __restrict__ idx2, float* __restrict__ dist2, double* __restrict__ d2out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int row_end = n_rows_dev ? min(n_rows, *n_rows_dev) : n_rows;
+    if (r >= row_end) return;
+    double B0 = INFINITY, B1 = INFINITY;
+    int I0 = 0x7fffffff, I1 = 0x7fffffff;
+    for (int s = 0; s < slices; s++) {
+        Top2 p = partial[(size_t)r * slices + s];
+        top2_insert(p.d0, p.i0, B0, I0, B1, I1);
+        top2_insert(p.d1, p.i1, B0, I0, B1, I1);
+    }
+    int o = qlist ? qlist[r] : r;
+    if (idx2) {
+        idx2[2 * o] = I0 == 0x7fffffff ? -1 : I0 + idx_offset;
+        idx2[2 * o + 1] = I1 == 0x7fffffff ? -1 : I1 + idx_offset;
+    }
+    if (dist2) { dist2[2 * o] = (float)sqrt(B0); dist2[2 * o + 1] = (float)sqrt(B1); }
+    if (d2out) { d2out[2 * o] = B0; d2out[2 * o + 1] = B1; }
+}
+
 int knn2_exact(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
                const int32_t* d_qlist, int nlist, int idx_offset,
                int32_t* d_idx2, float* d_dist2, double* d_d2)
 {
     int rows = d_qlist ? nlist : nq;
     if (rows <= 0) return ERP_OK;
-    knn2_exact_kernel<<<cdiv(rows, QT), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, d_qlist, rows,
-                                                              idx_offset, d_idx2, d_dist2, d_d2);
+    knn2_exact_kernel<<<cdiv(rows, QT), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, d_qlist, 0, rows, nullptr,
+                                                              idx_offset, d_idx2, d_dist2, d_d2, nullptr);
     ERP_LAUNCH(ctx, "knn2_exact_kernel");
+    return ERP_OK;
+}
+
+// Re-scan of a device-resident query list whose length (*d_count <= max_rows) the host does not
+// know: the first RESCAN_SMALL entries run T-split (short lists are the normal case and must not
+// serialise on one SM), the rest one block per 64 queries.  Blocks past the count exit at once,
+// so the launch sequence is fixed and nothing synchronises with the host.
+constexpr int RS_SMALL = 1024, RS_SLICES = 128;
+
+int knn2_exact_rescan(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                      const int32_t* d_list, const int32_t* d_count, int max_rows,
+                      int32_t* d_idx2, float* d_dist2, double* d_d2)
+{
+    if (max_rows <= 0) return ERP_OK;
+    int st = ERP_OK;
+    int small = max_rows < RS_SMALL ? max_rows : RS_SMALL;
+    int slices = cdiv(nt, TT) < RS_SLICES ? cdiv(nt, TT) : RS_SLICES;
+    if (slices > 1) {
+        Top2* partial = ctx->scratch<Top2>(S_RS_PARTIAL, (size_t)cdiv(small, QT) * QT * slices, &st);
+        ERP_TRY(st);
+        dim3 grid(cdiv(small, QT), slices);
+        knn2_exact_kernel<<<grid, 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, d_list, 0, small, d_count, 0,
+                                                         nullptr, nullptr, nullptr, partial);
+        ERP_LAUNCH(ctx, "knn2_exact_kernel(split)");
+        knn2_merge_kernel<<<cdiv(small, 256), 256, 0, ctx->stream>>>(partial, slices, d_list, small, d_count, 0,
+                                                                     d_idx2, d_dist2, d_d2);
+        ERP_LAUNCH(ctx, "knn2_merge_kernel");
+    } else {
+        knn2_exact_kernel<<<cdiv(small, QT), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, d_list, 0, small, d_count, 0,
+                                                                   d_idx2, d_dist2, d_d2, nullptr);
+        ERP_LAUNCH(ctx, "knn2_exact_kernel(list)");
+    }
+    if (max_rows > RS_SMALL) {
+        knn2_exact_kernel<<<cdiv(max_rows - RS_SMALL, QT), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, d_list, RS_SMALL,
+                                                                                 max_rows - RS_SMALL, d_count, 0,
+                                                                                 d_idx2, d_dist2, d_d2, nullptr);
+        ERP_LAUNCH(ctx, "knn2_exact_kernel(overflow)");
+    }
     return ERP_OK;
 }
 

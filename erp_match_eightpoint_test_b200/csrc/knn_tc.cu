@@ -1,14 +1,645 @@
-// knn_tc.cu -- tcgen05 3xTF32 distance engine (placeholder until the kernel lands).
+// knn_tc.cu -- the tcgen05 distance engine: 3xTF32 GEMM-form tiles with a fused top-4 epilogue,
+// followed by an exact fp64 refine that CERTIFIES each query or sends it to the exact re-scan.
+//
+// Replaces cv::DescriptorMatcher::knnMatch(k=2) of /root/reference/src/feature_matcher.cpp:45 in its
+// exact-L2 limit.  Pipeline, all on ctx->stream, no host synchronisation:
+//
+//   split_kernel (x2)   fp32 rows -> [hi | lo] TF32 pairs (hi = rna_tf32(v), lo = rna_tf32(v - hi)),
+//                       query rows pre-scaled by -2 (exact), train norms |t|^2, max norm
+//   knn2_tc_kernel      persistent, warp specialised: TMA (128B-swizzled K-major boxes) -> smem ring
+//                       -> tcgen05.mma kind::tf32, three products per 32-wide k chunk
+//                       (lo*hi + hi*hi + hi*lo) accumulated in a TMEM tile of 128 queries x 256 train
+//                       rows, double buffered (2 x 256 columns) so the epilogue of tile i overlaps
+//                       the MMAs of tile i+1.  Epilogue: tcgen05.ld 32x32b (one query row per
+//                       thread), s = acc + |t|^2, running top-4 per row in registers.  The distance
+//                       matrix never leaves the SM.
+//   refine_kernel       exact fp64 direct-form distance (the oracle's fma chain) of the candidates,
+//                       lexicographic (d2, index) top-2, and the certificate
+//                           d2_exact(second) < min_split(s_4th) + |q|^2 - eps
+//                       (every non-candidate has approximate score >= s_4th, so its exact distance
+//                       is >= s_4th + |q|^2 - eps).  Uncertified queries go to a list.
+//   re-scan             the listed queries through the exact fp64 kernel (knn_exact.cu), T-split for
+//                       short lists.  Results are therefore identical to ERP_ENGINE_EXACT_SIMT.
 #include "common.cuh"
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through the runtime)
 
 namespace erp {
 
-bool knn2_tc_supported(int, int, int) { return false; }
+// ------------------------------------------------------------------------------------------
+// tile configuration
+// ------------------------------------------------------------------------------------------
+constexpr int BM = 128;                 // queries per tile  (UMMA M, TMEM lanes)
+constexpr int BN = 256;                 // train rows per tile (UMMA N, TMEM columns per accumulator)
+constexpr int KC = 32;                  // floats per k chunk: one 128-byte swizzle atom
+constexpr int UK = 8;                   // UMMA K for kind::tf32
+constexpr int Q_CHUNK_BYTES = BM * KC * 4;   // 16 KB
+constexpr int T_CHUNK_BYTES = BN * KC * 4;   // 32 KB
+constexpr int TC_THREADS = 256;         // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
+constexpr int TOPK = 4;
+constexpr int MAX_SPLIT = 16;
+constexpr int SMEM_LIMIT = 232448;      // 227 KB
+// certificate slack: |s_tc - s_exact| <= KAPPA * (|q|^2 + max|t|^2).  3xTF32 drops lo*lo (2^-22),
+// rounds lo to tf32 (2^-23) and accumulates 3*D/8 partial sums in fp32 (<= 2^-18 for D = 128);
+// 2^-14 leaves a factor > 8.  refine_kernel reports the largest deviation it observes.
+constexpr double KAPPA = 1.0 / 16384.0;
 
-int knn2_tc(erp_ctx*, const float*, int, const float*, int, int, int32_t*, float*, double*)
+__host__ __device__ constexpr int n_slots(int kch) { return (SMEM_LIMIT - 1024 - 2 * kch * Q_CHUNK_BYTES - 1024) / T_CHUNK_BYTES; }
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    set_error("tcgen05 engine not built");
-    return ERP_E_DIM;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 256 x 8, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread i of the warp receives lane (base + i)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, rows of 128 bytes, 8-row groups of
+// 1024 bytes (SBO), descriptor version 1 (sm_100).  addr may point inside the first swizzle row
+// (k advance of 32 bytes per UMMA K step).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                          // version
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, N = 256, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------
+// prep: fp32 rows -> [hi | lo] (dpad each), norms
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// one warp per row.  out: n x (2*dpad).  norm (optional): n_pad floats, rows >= n get +inf.
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
+             float* __restrict__ out, float* __restrict__ norm, int n_pad, unsigned* __restrict__ max_bits)
+{
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    if (row >= n) {
+        if (norm && lane == 0) norm[row] = INFINITY;
+        return;
+    }
+    double acc = 0.0;
+    for (int k = lane * 4; k < dpad; k += 128) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < dim) v = *reinterpret_cast<const float4*>(x + (size_t)row * dim + k);
+        acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        float4 s = make_float4(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale));
+        float4 hi = make_float4(tf32_rna(s.x), tf32_rna(s.y), tf32_rna(s.z), tf32_rna(s.w));
+        float4 lo = make_float4(tf32_rna(__fsub_rn(s.x, hi.x)), tf32_rna(__fsub_rn(s.y, hi.y)),
+                                tf32_rna(__fsub_rn(s.z, hi.z)), tf32_rna(__fsub_rn(s.w, hi.w)));
+        float* o = out + (size_t)row * 2 * dpad + k;
+        *reinterpret_cast<float4*>(o) = hi;
+        *reinterpret_cast<float4*>(o + dpad) = lo;
+    }
+    if (norm) {
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            float f = (float)acc;
+            norm[row] = f;
+            // non-negative floats (and +inf, NaN) order like their bit patterns
+            atomicMax(max_bits, __float_as_uint(f));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the distance kernel
+// ------------------------------------------------------------------------------------------
+struct TcParams {
+    int nq, nt;
+    int n_qtiles, n_ttiles;
+    int n_split, tiles_per_split;
+    const float* tn;          // n_ttiles * BN norms (+inf padded)
+    int32_t* cand_idx;        // nq x n_split x TOPK
+    float* cand_s;            // nq x n_split x TOPK approximate scores, ascending (inf when missing)
+};
+
+__device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[TOPK], int (&bi)[TOPK])
+{
+    // strict <: equal scores keep the earlier (lower) train index
+    if (s < bs[2]) {
+        bs[3] = bs[2]; bi[3] = bi[2];
+        if (s < bs[1]) {
+            bs[2] = bs[1]; bi[2] = bi[1];
+            if (s < bs[0]) { bs[1] = bs[0]; bi[1] = bi[0]; bs[0] = s; bi[0] = idx; }
+            else { bs[1] = s; bi[1] = idx; }
+        } else { bs[2] = s; bi[2] = idx; }
+    } else { bs[3] = s; bi[3] = idx; }
+}
+
+template <int KCH>   // k chunks of 32 floats per half (hi or lo): dpad = 32 * KCH
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const TcParams p)
+{
+    constexpr int NS = n_slots(KCH);
+    static_assert(NS >= 2, "T ring too small");
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* q_smem = smem;                                   // 2*KCH chunks: hi 0..KCH-1, lo KCH..2KCH-1
+    uint8_t* t_smem = smem + 2 * KCH * Q_CHUNK_BYTES;         // NS slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(t_smem + NS * T_CHUNK_BYTES);
+    uint64_t* full = bars;              // [NS]  TMA -> MMA
+    uint64_t* empty = bars + NS;        // [NS]  MMA -> TMA
+    uint64_t* qfull = bars + 2 * NS;    // Q tile landed
+    uint64_t* qempty = qfull + 1;       // Q tile no longer read
+    uint64_t* tfull = qfull + 2;        // [2] accumulator ready
+    uint64_t* tempty = qfull + 4;       // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.n_qtiles * p.n_split;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_t);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(qfull, 1); mbar_init(qempty, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, item_n = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, item_n++) {
+                const int qtile = item / p.n_split, split = item - qtile * p.n_split;
+                const int t_begin = split * p.tiles_per_split;
+                const int t_end = min(p.n_ttiles, t_begin + p.tiles_per_split);
+                mbar_wait(qempty, (item_n & 1) ^ 1);
+                mbar_expect_tx(qfull, 2 * KCH * Q_CHUNK_BYTES);
+#pragma unroll
+                for (int c = 0; c < 2 * KCH; c++)
+                    tma_load_2d(&map_q, qfull, q_smem + c * Q_CHUNK_BYTES, c * KC, qtile * BM);
+                for (int tt = t_begin; tt < t_end; tt++) {
+#pragma unroll
+                    for (int c = 0; c < KCH; c++) {
+#pragma unroll
+                        for (int half = 0; half < 2; half++) {      // hi chunk c, then lo chunk c
+                            mbar_wait(&empty[slot], ph ^ 1);
+                            mbar_expect_tx(&full[slot], T_CHUNK_BYTES);
+                            tma_load_2d(&map_t, &full[slot], t_smem + slot * T_CHUNK_BYTES, (half * KCH + c) * KC, tt * BN);
+                            if (++slot == NS) { slot = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, item_n = 0, tile_n = 0;
+            const uint32_t q_base = smem_u32(q_smem), t_base = smem_u32(t_smem);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, item_n++) {
+                const int qtile = item / p.n_split, split = item - qtile * p.n_split;
+                const int t_begin = split * p.tiles_per_split;
+                const int t_end = min(p.n_ttiles, t_begin + p.tiles_per_split);
+                mbar_wait(qfull, item_n & 1);
+                for (int tt = t_begin; tt < t_end; tt++, tile_n++) {
+                    const uint32_t acc = tile_n & 1;
+                    mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll
+                    for (int c = 0; c < KCH; c++) {
+                        const uint32_t a_hi = q_base + c * Q_CHUNK_BYTES, a_lo = q_base + (KCH + c) * Q_CHUNK_BYTES;
+                        // ---- T hi chunk c: lo*hi then hi*hi
+                        mbar_wait(&full[slot], ph);
+                        tc_fence_after();
+                        uint32_t b = t_base + slot * T_CHUNK_BYTES;
+#pragma unroll
+                        for (int k = 0; k < KC / UK; k++)
+                            tc_mma_tf32(d_tmem, smem_desc_sw128(a_lo + k * UK * 4), smem_desc_sw128(b + k * UK * 4), IDESC, (c | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < KC / UK; k++)
+                            tc_mma_tf32(d_tmem, smem_desc_sw128(a_hi + k * UK * 4), smem_desc_sw128(b + k * UK * 4), IDESC, 1);
+                        tc_commit(&empty[slot]);
+                        if (++slot == NS) { slot = 0; ph ^= 1; }
+                        // ---- T lo chunk c: hi*lo
+                        mbar_wait(&full[slot], ph);
+                        tc_fence_after();
+                        b = t_base + slot * T_CHUNK_BYTES;
+#pragma unroll
+                        for (int k = 0; k < KC / UK; k++)
+                            tc_mma_tf32(d_tmem, smem_desc_sw128(a_hi + k * UK * 4), smem_desc_sw128(b + k * UK * 4), IDESC, 1);
+                        tc_commit(&empty[slot]);
+                        if (++slot == NS) { slot = 0; ph ^= 1; }
+                    }
+                    tc_commit(&tfull[acc]);
+                }
+                tc_commit(qempty);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================ epilogue (4 warps)
+        const int ew = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row = ew * 32 + lane;          // query row inside the tile
+        uint32_t tile_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int qtile = item / p.n_split, split = item - qtile * p.n_split;
+            const int t_begin = split * p.tiles_per_split;
+            const int t_end = min(p.n_ttiles, t_begin + p.tiles_per_split);
+            float bs[TOPK];
+            int bi[TOPK];
+#pragma unroll
+            for (int j = 0; j < TOPK; j++) { bs[j] = INFINITY; bi[j] = -1; }
+            for (int tt = t_begin; tt < t_end; tt++, tile_n++) {
+                const uint32_t acc = tile_n & 1;
+                mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+                const float4* tn4 = reinterpret_cast<const float4*>(p.tn + (size_t)tt * BN);
+#pragma unroll 1
+                for (int cc = 0; cc < BN / 64; cc++) {
+                    uint32_t v0[32], v1[32];
+                    __syncwarp();
+                    tc_ld32(taddr + cc * 64, v0);
+                    tc_ld32(taddr + cc * 64 + 32, v1);
+                    tc_wait_ld();
+                    const int col0 = tt * BN + cc * 64;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        float4 n = __ldg(tn4 + cc * 16 + j4);
+                        float s0 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 0]), n.x);
+                        float s1 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 1]), n.y);
+                        float s2 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 2]), n.z);
+                        float s3 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 3]), n.w);
+                        if (s0 < bs[3]) top4_insert(s0, col0 + j4 * 4 + 0, bs, bi);
+                        if (s1 < bs[3]) top4_insert(s1, col0 + j4 * 4 + 1, bs, bi);
+                        if (s2 < bs[3]) top4_insert(s2, col0 + j4 * 4 + 2, bs, bi);
+                        if (s3 < bs[3]) top4_insert(s3, col0 + j4 * 4 + 3, bs, bi);
+                    }
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        float4 n = __ldg(tn4 + cc * 16 + 8 + j4);
+                        float s0 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 0]), n.x);
+                        float s1 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 1]), n.y);
+                        float s2 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 2]), n.z);
+                        float s3 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 3]), n.w);
+                        if (s0 < bs[3]) top4_insert(s0, col0 + 32 + j4 * 4 + 0, bs, bi);
+                        if (s1 < bs[3]) top4_insert(s1, col0 + 32 + j4 * 4 + 1, bs, bi);
+                        if (s2 < bs[3]) top4_insert(s2, col0 + 32 + j4 * 4 + 2, bs, bi);
+                        if (s3 < bs[3]) top4_insert(s3, col0 + 32 + j4 * 4 + 3, bs, bi);
+                    }
+                }
+                // accumulator drained: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            const int qg = qtile * BM + row;
+            if (qg < p.nq) {
+                const size_t o = (size_t)qg * p.n_split + split;
+                *reinterpret_cast<int4*>(p.cand_idx + o * TOPK) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+                *reinterpret_cast<float4*>(p.cand_s + o * TOPK) = make_float4(bs[0], bs[1], bs[2], bs[3]);
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// refine: exact distances of the candidates, top-2, certificate
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lex_less(double d, int i, double bd, int bi) { return d < bd || (d == bd && i < bi); }
+
+// one warp per query; lane j owns candidates j and j + 32 (n_split * TOPK <= 64)
+__global__ void __launch_bounds__(256)
+refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim, int n_split,
+              const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_s,
+              unsigned* __restrict__ misc /* [0] re-scan count, [1] max |t|^2 bits, [2] max deviation bits */,
+              int32_t* __restrict__ idx2, float* __restrict__ dist2, double* __restrict__ d2out,
+              int32_t* __restrict__ rescan_list)
+{
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const int ncand = n_split * TOPK;
+    const float* qr = q + (size_t)qi * dim;
+
+    double d[2];
+    int id[2];
+    float sc[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        int c = lane + 32 * s;
+        int ti = c < ncand ? cand_idx[(size_t)qi * ncand + c] : -1;
+        sc[s] = c < ncand ? cand_s[(size_t)qi * ncand + c] : INFINITY;
+        d[s] = INFINITY; id[s] = 0x7fffffff;
+        if (ti >= 0 && ti < nt) {
+            const float* tr = t + (size_t)ti * dim;
+            double a = 0.0;
+            for (int k = 0; k < dim; k += 4) {
+                float4 x = *reinterpret_cast<const float4*>(qr + k);
+                float4 y = *reinterpret_cast<const float4*>(tr + k);
+                double e;
+                e = __dsub_rn((double)x.x, (double)y.x); a = __fma_rn(e, e, a);
+                e = __dsub_rn((double)x.y, (double)y.y); a = __fma_rn(e, e, a);
+                e = __dsub_rn((double)x.z, (double)y.z); a = __fma_rn(e, e, a);
+                e = __dsub_rn((double)x.w, (double)y.w); a = __fma_rn(e, e, a);
+            }
+            d[s] = a; id[s] = ti;
+        }
+    }
+    // certificate inputs: the smallest 4th-best approximate score over the splits, |q|^2, max |t|^2
+    float thr = INFINITY;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        int c = lane + 32 * s;
+        if (c < ncand && (c & (TOPK - 1)) == TOPK - 1) thr = fminf(thr, sc[s]);
+    }
+    for (int o = 16; o > 0; o >>= 1) thr = fminf(thr, __shfl_xor_sync(0xffffffffu, thr, o));
+    double qn = 0.0;
+    for (int k = lane; k < dim; k += 32) { double x = (double)qr[k]; qn += x * x; }
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+    const double tn_max = (double)__uint_as_float(misc[1]);
+    const double scale = qn + tn_max;
+    // observed |approximate - exact| over the candidates, in units of (|q|^2 + max|t|^2)
+    float dev = 0.f;
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+        if (id[s] != 0x7fffffff && scale > 0.0) dev = fmaxf(dev, (float)(fabs((double)sc[s] + qn - d[s]) / scale));
+    for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+
+    // lane-local order, then two warp-wide lexicographic minima
+    if (lex_less(d[1], id[1], d[0], id[0])) { double x = d[0]; d[0] = d[1]; d[1] = x; int y = id[0]; id[0] = id[1]; id[1] = y; }
+    double B0 = d[0]; int I0 = id[0];
+    for (int o = 16; o > 0; o >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, B0, o); int oi = __shfl_xor_sync(0xffffffffu, I0, o);
+        if (lex_less(od, oi, B0, I0)) { B0 = od; I0 = oi; }
+    }
+    // the lane holding the winner promotes its second entry (candidate indices are distinct)
+    double m = d[0]; int mi = id[0];
+    if (mi == I0) { m = d[1]; mi = id[1]; }
+    double B1 = m; int I1 = mi;
+    for (int o = 16; o > 0; o >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, B1, o); int oi = __shfl_xor_sync(0xffffffffu, I1, o);
+        if (lex_less(od, oi, B1, I1)) { B1 = od; I1 = oi; }
+    }
+
+    if (lane == 0) {
+        if (dev > 0.f) atomicMax(misc + 2, __float_as_uint(dev));
+        const double eps = KAPPA * scale;
+        // non-finite input anywhere (NaN compares false, inf norms) -> exact re-scan
+        bool finite_in = scale < (double)INFINITY && scale == scale;
+        bool certified = finite_in && I1 != 0x7fffffff &&
+                         (!(thr < INFINITY) /* every train row was a candidate */ || B1 < (double)thr + qn - eps);
+        if (certified) {
+            if (idx2) { idx2[2 * qi] = I0; idx2[2 * qi + 1] = I1; }
+            if (dist2) { dist2[2 * qi] = (float)sqrt(B0); dist2[2 * qi + 1] = (float)sqrt(B1); }
+            if (d2out) { d2out[2 * qi] = B0; d2out[2 * qi + 1] = B1; }
+        } else {
+            int pos = (int)atomicAdd(misc, 1u);
+            rescan_list[pos] = qi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// rows x (2*dpad) fp32, row major; box = 32 floats x box_rows, 128B swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const float* base, int rows, int dpad, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ERP_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)(2 * dpad), (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(2 * dpad) * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ERP_E_CUDA; }
+    return ERP_OK;
+}
+
+bool knn2_tc_supported(int nq, int nt, int dim) { return nq >= 1 && nt >= 2 && dim >= 4 && dim % 4 == 0 && dim <= 128; }
+
+// AUTO policy: tensor cores once the problem is large enough to amortise the extra passes
+bool knn2_tc_preferred(int nq, int nt, int dim)
+{
+    return knn2_tc_supported(nq, nt, dim) && (double)nq * (double)nt >= 4.0e6;
+}
+
+// choose how many T splits per query tile: minimise the makespan (in T tiles) over the grid
+static void plan(int n_qtiles, int n_ttiles, int sms, int* n_split, int* tps)
+{
+    long best = -1;
+    int bs = 1;
+    for (int s = 1; s <= MAX_SPLIT && s <= n_ttiles; s++) {
+        int per = (n_ttiles + s - 1) / s;
+        int real = (n_ttiles + per - 1) / per;        // splits that are not empty
+        if (real != s) continue;
+        long items = (long)n_qtiles * s;
+        long waves = (items + sms - 1) / sms;
+        long cost = waves * (per + 1);                // +1: the Q tile load / pipeline refill per item
+        if (best < 0 || cost < best) { best = cost; bs = s; }
+    }
+    *n_split = bs;
+    *tps = (n_ttiles + bs - 1) / bs;
+}
+
+template <int KCH>
+static int launch_tc(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt, const TcParams& p, int grid)
+{
+    constexpr int NS = n_slots(KCH);
+    constexpr int smem = 1024 + 2 * KCH * Q_CHUNK_BYTES + NS * T_CHUNK_BYTES + 1024;
+    static_assert(smem <= SMEM_LIMIT, "shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        ERP_CUDA(cudaFuncSetAttribute(knn2_tc_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    knn2_tc_kernel<KCH><<<grid, TC_THREADS, smem, ctx->stream>>>(mq, mt, p);
+    ERP_LAUNCH(ctx, "knn2_tc_kernel");
+    return ERP_OK;
+}
+
+int knn2_exact_rescan(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                      const int32_t* d_list, const int32_t* d_count, int max_rows,
+                      int32_t* d_idx2, float* d_dist2, double* d_d2);
+
+int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+            int32_t* d_idx2, float* d_dist2, double* d_d2)
+{
+    if (!knn2_tc_supported(nq, nt, dim)) { set_error("tcgen05 engine: unsupported shape nq=%d nt=%d dim=%d", nq, nt, dim); return ERP_E_DIM; }
+    const int kch = (dim + KC - 1) / KC, dpad = kch * KC;
+    const int n_qtiles = cdiv(nq, BM), n_ttiles = cdiv(nt, BN);
+    int n_split, tps;
+    plan(n_qtiles, n_ttiles, ctx->sm_count, &n_split, &tps);
+
+    int st = ERP_OK;
+    float* qs = ctx->scratch<float>(S_TC_Q, (size_t)nq * 2 * dpad, &st);
+    float* ts = ctx->scratch<float>(S_TC_T, (size_t)nt * 2 * dpad, &st);
+    float* tn = ctx->scratch<float>(S_TC_TN, (size_t)n_ttiles * BN, &st);
+    int32_t* cand = ctx->scratch<int32_t>(S_TC_CAND, (size_t)nq * n_split * TOPK * 2, &st);
+    int32_t* list = ctx->scratch<int32_t>(S_TC_LIST, (size_t)nq + 8, &st);
+    int32_t* misc = ctx->scratch<int32_t>(S_TC_MISC, 8, &st);     // [0] re-scan count, [1] max |t|^2 bits, [2] max deviation bits
+    ERP_TRY(st);
+    float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_split * TOPK);
+    ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
+
+    split_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, dim, dpad, -2.0f, qs, nullptr, nq, nullptr);
+    ERP_LAUNCH(ctx, "split_kernel(q)");
+    split_kernel<<<cdiv(n_ttiles * BN, 8), 256, 0, ctx->stream>>>(d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * BN,
+                                                                 reinterpret_cast<unsigned*>(misc + 1));
+    ERP_LAUNCH(ctx, "split_kernel(t)");
+
+    CUtensorMap mq, mt;
+    ERP_TRY(make_map(&mq, qs, nq, dpad, BM));
+    ERP_TRY(make_map(&mt, ts, nt, dpad, BN));
+    TcParams p;
+    p.nq = nq; p.nt = nt; p.n_qtiles = n_qtiles; p.n_ttiles = n_ttiles; p.n_split = n_split; p.tiles_per_split = tps;
+    p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s;
+    const int n_items = n_qtiles * n_split;
+    const int grid = n_items < ctx->sm_count ? n_items : ctx->sm_count;
+
+    ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    switch (kch) {
+    case 1: ERP_TRY(launch_tc<1>(ctx, mq, mt, p, grid)); break;
+    case 2: ERP_TRY(launch_tc<2>(ctx, mq, mt, p, grid)); break;
+    case 3: ERP_TRY(launch_tc<3>(ctx, mq, mt, p, grid)); break;
+    default: ERP_TRY(launch_tc<4>(ctx, mq, mt, p, grid)); break;
+    }
+    ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+
+    refine_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_split, cand, cand_s,
+                                                        reinterpret_cast<unsigned*>(misc), d_idx2, d_dist2, d_d2, list);
+    ERP_LAUNCH(ctx, "refine_kernel");
+    ERP_TRY(knn2_exact_rescan(ctx, d_q, nq, d_t, nt, dim, list, misc, nq, d_idx2, d_dist2, d_d2));
+
+    ctx->knn_stats[0] = ERP_ENGINE_TCGEN05;
+    ctx->knn_stats[1] = -1;                       // re-scan count lives on the device: see erp_ctx_last_knn_stats
+    ctx->knn_stats[2] = n_split;
+    ctx->knn_stats[3] = n_items;
+    ctx->knn_stats[4] = grid;
+    ctx->tc_misc_dev = misc;
+    return ERP_OK;
 }
 
 } // namespace erp

@@ -35,7 +35,7 @@ def scene():
 
 
 def engines():
-    return [binding.ENGINE_EXACT_SIMT, binding.ENGINE_AUTO]
+    return [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_AUTO]
 
 
 # ------------------------------------------------------------------ matching
@@ -80,6 +80,48 @@ def test_match_two_image_records(ctx, engine, ratio, cross):
     if ratio == 0.3 and not cross:
         assert (planted[got["queryIdx"]] == got["trainIdx"]).all()
     ctx.set_engine(binding.ENGINE_AUTO)
+
+
+@pytest.mark.parametrize("nq,nt,dim", [(5000, 7000, 64), (3000, 4000, 128), (2000, 2500, 32), (1500, 1500, 96),
+                                        (700, 900, 100), (129, 257, 64), (128, 256, 64), (4000, 300, 64)])
+def test_tcgen05_engine_certifies_and_matches_exact(ctx, nq, nt, dim):
+    """The tensor-core engine must (1) return exactly what the fp64 SIMT engine returns, (2) certify
+    nearly every query itself (a broken tile layout would push everything through the re-scan and
+    still pass (1)), (3) stay far inside the certificate's error budget KAPPA = 2^-14."""
+    q, t, _ = synth.descriptor_pair(nq, nt, dim, seed=3 * nq + nt)
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    eidx, edist = ctx.knn2_raw(q, t)
+    ctx.set_engine(binding.ENGINE_TCGEN05)
+    idx, dist = ctx.knn2_raw(q, t)
+    st = ctx.last_knn_stats()
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert st["engine"] == binding.ENGINE_TCGEN05
+    assert np.array_equal(idx, eidx)
+    assert np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
+    assert st["rescanned"] <= max(2, nq // 100), st
+    assert 0 < st["deviation"] < 2.0 ** -14 / 4, st
+
+
+def test_tcgen05_engine_adversarial_inputs(ctx):
+    """Duplicated rows (more duplicates than the candidate list holds), un-normalised and widely
+    scaled descriptors, zero rows: everything the certificate cannot prove must be re-scanned."""
+    rng = np.random.default_rng(5)
+    q = rng.normal(size=(600, 64)).astype(np.float32) * rng.uniform(0.01, 50.0, (600, 1)).astype(np.float32)
+    t = rng.normal(size=(900, 64)).astype(np.float32) * rng.uniform(0.01, 50.0, (900, 1)).astype(np.float32)
+    t[100:110] = t[7]            # 11 identical train rows
+    q[3] = t[7]
+    q[4] = 0
+    t[50] = 0
+    t[51] = 0
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    eidx, edist = ctx.knn2_raw(q, t)
+    ctx.set_engine(binding.ENGINE_TCGEN05)
+    idx, dist = ctx.knn2_raw(q, t)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert np.array_equal(idx, eidx)
+    assert np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
+    oidx, odist, _ = O.knn2(q, t)
+    assert np.array_equal(idx, oidx)
 
 
 def test_match_edge_cases(ctx):
