@@ -198,23 +198,23 @@ def run_gpu(args, cfg):
     h_left = torch.from_numpy(pair["left"]).pin_memory()
     h_right = torch.from_numpy(pair["right"]).pin_memory()
 
-    with torch.cuda.stream(stream):
-        d_q, d_t = h_q.to(dev, non_blocking=True), h_t.to(dev, non_blocking=True)
-        d_left, d_right = h_left.to(dev, non_blocking=True), h_right.to(dev, non_blocking=True)
-        d_matches = torch.empty((nq_all, 4), dtype=torch.int32, device=dev)          # erp_dmatch records
-        d_n = torch.zeros(1, dtype=torch.int32, device=dev)
-        d_l3 = torch.empty((nq_all, 3), dtype=torch.float64, device=dev)
-        d_r3 = torch.empty((nq_all, 3), dtype=torch.float64, device=dev)
-        d_l4 = torch.empty((nq_all, 4), dtype=torch.float32, device=dev)
-        d_r4 = torch.empty((nq_all, 4), dtype=torch.float32, device=dev)
-        d_packed = torch.zeros(1, dtype=torch.int64, device=dev)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                 # > 126 MB L2
-        h_n = torch.zeros(1, dtype=torch.int32).pin_memory()
-        h_packed = torch.zeros(1, dtype=torch.int64).pin_memory()
-        if strong:
-            counts = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
-            gathered = torch.empty((world, nq_all // world + 1, 4), dtype=torch.int32, device=dev)
-    stream.synchronize()
+    # device buffers live on torch's default stream (the library only borrows the pointers)
+    d_q, d_t = h_q.to(dev), h_t.to(dev)
+    d_left, d_right = h_left.to(dev), h_right.to(dev)
+    d_matches = torch.empty((nq_all, 4), dtype=torch.int32, device=dev)          # erp_dmatch records
+    d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_l3 = torch.empty((nq_all, 3), dtype=torch.float64, device=dev)
+    d_r3 = torch.empty((nq_all, 3), dtype=torch.float64, device=dev)
+    d_l4 = torch.empty((nq_all, 4), dtype=torch.float32, device=dev)
+    d_r4 = torch.empty((nq_all, 4), dtype=torch.float32, device=dev)
+    d_packed = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                 # > 126 MB L2
+    h_n = torch.zeros(1, dtype=torch.int32).pin_memory()
+    h_packed = torch.zeros(1, dtype=torch.int64).pin_memory()
+    if strong:
+        counts = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
+        gathered = torch.empty((world, nq_all // world + 1, 4), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -320,6 +320,7 @@ def run_gpu(args, cfg):
     d2h = len(mt) * 16 + 2 * len(mt) * 24 + len(mt) + 256
 
     stats = ctx.last_knn_stats()
+    torch.cuda.synchronize()
     ctx.close()
     if rank != 0:
         if world > 1:

@@ -6,7 +6,9 @@
 //
 //   split_kernel (x2)   fp32 rows -> [hi | lo] TF32 pairs (hi = rna_tf32(v), lo = rna_tf32(v - hi)),
 //                       query rows pre-scaled by -2 (exact), train norms |t|^2, max norm
-//   knn2_tc_kernel      persistent, warp specialised: TMA (128B-swizzled K-major boxes) -> smem ring
+//   knn2_tc_kernel      persistent (one CTA per SM owns a contiguous range of (query tile, train tile)
+//                       units, stream-K style, so SMs finish together), warp specialised:
+//                       TMA (128B-swizzled K-major boxes) -> smem ring
 //                       -> tcgen05.mma kind::tf32, three products per 32-wide k chunk
 //                       (lo*hi + hi*hi + hi*lo) accumulated in a TMEM tile of 128 queries x 256 train
 //                       rows, double buffered (2 x 256 columns) so the epilogue of tile i overlaps
@@ -35,16 +37,20 @@ constexpr int KC = 32;                  // floats per k chunk: one 128-byte swiz
 constexpr int UK = 8;                   // UMMA K for kind::tf32
 constexpr int Q_CHUNK_BYTES = BM * KC * 4;   // 16 KB
 constexpr int T_CHUNK_BYTES = BN * KC * 4;   // 32 KB
-constexpr int TC_THREADS = 256;         // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
+constexpr int EPI_GROUPS = 2;           // column groups per tile: 2 x 4 epilogue warps, two per scheduler
+constexpr int EPI_THREADS = EPI_GROUPS * 128;
+constexpr int TC_THREADS = 128 + EPI_THREADS;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 |t|^2 loads, 4.. epilogue
+constexpr int EPI_COLS = BN / EPI_GROUPS;       // columns of a tile each epilogue thread scans
 constexpr int TOPK = 4;
-constexpr int MAX_SPLIT = 16;
+constexpr int MAX_SEG = 64 / (TOPK * EPI_GROUPS);     // segments per query tile: refine_kernel holds <= 64 candidates
 constexpr int SMEM_LIMIT = 232448;      // 227 KB
+constexpr int SMEM_TAIL = 2 * BN * 4 + 256;     // |t|^2 of two tiles + mbarriers + the TMEM base address
 // certificate slack: |s_tc - s_exact| <= KAPPA * (|q|^2 + max|t|^2).  3xTF32 drops lo*lo (2^-22),
 // rounds lo to tf32 (2^-23) and accumulates 3*D/8 partial sums in fp32 (<= 2^-18 for D = 128);
 // 2^-14 leaves a factor > 8.  refine_kernel reports the largest deviation it observes.
 constexpr double KAPPA = 1.0 / 16384.0;
 
-__host__ __device__ constexpr int n_slots(int kch) { return (SMEM_LIMIT - 1024 - 2 * kch * Q_CHUNK_BYTES - 1024) / T_CHUNK_BYTES; }
+__host__ __device__ constexpr int n_slots(int kch) { return (SMEM_LIMIT - 2 * kch * Q_CHUNK_BYTES - SMEM_TAIL) / T_CHUNK_BYTES; }
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -194,10 +200,37 @@ split_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
 struct TcParams {
     int nq, nt;
     int n_qtiles, n_ttiles;
-    int n_split, tiles_per_split;
+    int units_per_cta;        // L: CTA b owns units [b*L, (b+1)*L) of the n_qtiles x n_ttiles grid (query tile major)
+    int n_seg;                // candidate lists per query = n_seg x EPI_GROUPS
     const float* tn;          // n_ttiles * BN norms (+inf padded)
-    int32_t* cand_idx;        // nq x n_split x TOPK
-    float* cand_s;            // nq x n_split x TOPK approximate scores, ascending (inf when missing)
+    int32_t* cand_idx;        // nq x (n_seg * EPI_GROUPS) x TOPK, pre-set to -1
+    float* cand_s;            // same shape: approximate scores, ascending
+};
+
+// A CTA's unit range cut into segments: consecutive train tiles of one query tile.
+struct SegIter {
+    long u, end;
+    int n_ttiles, L;
+    __device__ SegIter(const TcParams& p, int cta)
+    {
+        L = p.units_per_cta; n_ttiles = p.n_ttiles;
+        u = (long)cta * L;
+        long total = (long)p.n_qtiles * p.n_ttiles;
+        end = u + L < total ? u + L : total;
+    }
+    // next segment: query tile, train tiles [t0, t1), list slot of the segment within its query tile
+    __device__ bool next(int& qtile, int& t0, int& t1, int& seg)
+    {
+        if (u >= end) return false;
+        qtile = (int)(u / n_ttiles);
+        long row0 = (long)qtile * n_ttiles;
+        t0 = (int)(u - row0);
+        long rem = end - u;
+        t1 = rem < n_ttiles - t0 ? t0 + (int)rem : n_ttiles;
+        seg = (int)(u / L - row0 / L);      // CTA boundaries (multiples of L) in (row0, u]
+        u += t1 - t0;
+        return true;
+    }
 };
 
 __device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[TOPK], int (&bi)[TOPK])
@@ -213,28 +246,99 @@ __device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[TOPK],
     } else { bs[3] = s; bi[3] = idx; }
 }
 
+// wait for this thread's outstanding tcgen05.ld; the registers are operands so that no use of
+// them can be scheduled above the wait
+__device__ __forceinline__ void tc_wait_ld32(uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld8(uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+                 :
+                 : "memory");
+}
+
+// 32 accumulator columns of one query row.  Common case: s = acc + |t|^2 (32 independent adds), a min
+// tree and ONE warp-uniform threshold test.  Rare case (some lane has a column below its 4th best):
+// only the groups of 8 columns that some lane needs are re-read from TMEM in a rolled loop -- the
+// insert cascade exists once per call site, which keeps the loop inside the instruction cache (fully
+// unrolled it was 60 KB and 3x slower).  The re-computed scores are bit-identical to the first pass.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t taddr, const float4* __restrict__ tn4, int col0,
+                                           float (&bs)[TOPK], int (&bi)[TOPK])
+{
+    float gm[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
+        float s0 = __fadd_rn(__uint_as_float(v[g * 8 + 0]), na.x), s1 = __fadd_rn(__uint_as_float(v[g * 8 + 1]), na.y);
+        float s2 = __fadd_rn(__uint_as_float(v[g * 8 + 2]), na.z), s3 = __fadd_rn(__uint_as_float(v[g * 8 + 3]), na.w);
+        float s4 = __fadd_rn(__uint_as_float(v[g * 8 + 4]), nb.x), s5 = __fadd_rn(__uint_as_float(v[g * 8 + 5]), nb.y);
+        float s6 = __fadd_rn(__uint_as_float(v[g * 8 + 6]), nb.z), s7 = __fadd_rn(__uint_as_float(v[g * 8 + 7]), nb.w);
+        gm[g] = fminf(fminf(fminf(s0, s1), fminf(s2, s3)), fminf(fminf(s4, s5), fminf(s6, s7)));
+    }
+    const float thr = bs[3];
+    const unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
+    unsigned need = __reduce_or_sync(0xffffffffu, mine);
+    while (need) {                                  // warp-uniform
+        const int g = __ffs(need) - 1;
+        need &= need - 1;
+        uint32_t w[8];
+        tc_ld8(taddr + g * 8, w);
+        tc_wait_ld8(w);
+        const float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
+        if ((mine >> g) & 1u) {
+            float e[8];
+            e[0] = __fadd_rn(__uint_as_float(w[0]), na.x); e[1] = __fadd_rn(__uint_as_float(w[1]), na.y);
+            e[2] = __fadd_rn(__uint_as_float(w[2]), na.z); e[3] = __fadd_rn(__uint_as_float(w[3]), na.w);
+            e[4] = __fadd_rn(__uint_as_float(w[4]), nb.x); e[5] = __fadd_rn(__uint_as_float(w[5]), nb.y);
+            e[6] = __fadd_rn(__uint_as_float(w[6]), nb.z); e[7] = __fadd_rn(__uint_as_float(w[7]), nb.w);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (e[j] < bs[3]) top4_insert(e[j], col0 + g * 8 + j, bs, bi);
+        }
+        __syncwarp();
+    }
+}
+
 template <int KCH>   // k chunks of 32 floats per half (hi or lo): dpad = 32 * KCH
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const TcParams p)
 {
     constexpr int NS = n_slots(KCH);
     static_assert(NS >= 2, "T ring too small");
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for the 128B swizzle atoms
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // the 128B swizzle atoms need a 1024-byte aligned base; the budget has no room for a round-up
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* q_smem = smem;                                   // 2*KCH chunks: hi 0..KCH-1, lo KCH..2KCH-1
     uint8_t* t_smem = smem + 2 * KCH * Q_CHUNK_BYTES;         // NS slots
-    uint64_t* bars = reinterpret_cast<uint64_t*>(t_smem + NS * T_CHUNK_BYTES);
+    float* tn_smem = reinterpret_cast<float*>(t_smem + NS * T_CHUNK_BYTES);   // [2][BN], follows the accumulator parity
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tn_smem + 2 * BN);
     uint64_t* full = bars;              // [NS]  TMA -> MMA
     uint64_t* empty = bars + NS;        // [NS]  MMA -> TMA
     uint64_t* qfull = bars + 2 * NS;    // Q tile landed
     uint64_t* qempty = qfull + 1;       // Q tile no longer read
     uint64_t* tfull = qfull + 2;        // [2] accumulator ready
-    uint64_t* tempty = qfull + 4;       // [2] accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 6);
+    uint64_t* tempty = qfull + 4;       // [2] accumulator (and its |t|^2 buffer) drained
+    uint64_t* nfull = qfull + 6;        // [2] |t|^2 of the tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = p.n_qtiles * p.n_split;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
@@ -243,7 +347,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(qfull, 1); mbar_init(qempty, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS / 32); mbar_init(&nfull[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -259,10 +363,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // ================================================================ TMA producer
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, item_n = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, item_n++) {
-                const int qtile = item / p.n_split, split = item - qtile * p.n_split;
-                const int t_begin = split * p.tiles_per_split;
-                const int t_end = min(p.n_ttiles, t_begin + p.tiles_per_split);
+            SegIter it(p, blockIdx.x);
+            int qtile, t_begin, t_end, seg;
+            for (; it.next(qtile, t_begin, t_end, seg); item_n++) {
                 mbar_wait(qempty, (item_n & 1) ^ 1);
                 mbar_expect_tx(qfull, 2 * KCH * Q_CHUNK_BYTES);
 #pragma unroll
@@ -287,10 +390,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, item_n = 0, tile_n = 0;
             const uint32_t q_base = smem_u32(q_smem), t_base = smem_u32(t_smem);
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, item_n++) {
-                const int qtile = item / p.n_split, split = item - qtile * p.n_split;
-                const int t_begin = split * p.tiles_per_split;
-                const int t_end = min(p.n_ttiles, t_begin + p.tiles_per_split);
+            SegIter it(p, blockIdx.x);
+            int qtile, t_begin, t_end, seg;
+            for (; it.next(qtile, t_begin, t_end, seg); item_n++) {
                 mbar_wait(qfull, item_n & 1);
                 for (int tt = t_begin; tt < t_end; tt++, tile_n++) {
                     const uint32_t acc = tile_n & 1;
@@ -327,57 +429,58 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 tc_commit(qempty);
             }
         }
+    } else if (warp == 3) {
+        // ================================================================ |t|^2 producer
+        // one bulk copy of 1 KB per tile into the buffer of the accumulator parity; it may be
+        // overwritten once the epilogue has drained that accumulator (the MMA warp's condition too)
+        if (lane == 0) {
+            uint32_t tile_n = 0;
+            SegIter it(p, blockIdx.x);
+            int qtile, t_begin, t_end, seg;
+            while (it.next(qtile, t_begin, t_end, seg)) {
+                for (int tt = t_begin; tt < t_end; tt++, tile_n++) {
+                    const uint32_t acc = tile_n & 1;
+                    mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&nfull[acc], BN * 4);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(tn_smem + acc * BN)), "l"(p.tn + (size_t)tt * BN), "r"(BN * 4), "r"(smem_u32(&nfull[acc]))
+                                 : "memory");
+                }
+            }
+        }
     } else if (warp >= 4) {
-        // ================================================================ epilogue (4 warps)
+        // ================================================================ epilogue (EPI_GROUPS x 4 warps)
         const int ew = warp & 3;                 // TMEM lane quarter this warp may read
+        const int cg = (warp - 4) >> 2;          // column group of the tile this warp scans
         const int row = ew * 32 + lane;          // query row inside the tile
         uint32_t tile_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int qtile = item / p.n_split, split = item - qtile * p.n_split;
-            const int t_begin = split * p.tiles_per_split;
-            const int t_end = min(p.n_ttiles, t_begin + p.tiles_per_split);
+        SegIter it(p, blockIdx.x);
+        int qtile, t_begin, t_end, seg;
+        while (it.next(qtile, t_begin, t_end, seg)) {
             float bs[TOPK];
             int bi[TOPK];
 #pragma unroll
             for (int j = 0; j < TOPK; j++) { bs[j] = INFINITY; bi[j] = -1; }
             for (int tt = t_begin; tt < t_end; tt++, tile_n++) {
                 const uint32_t acc = tile_n & 1;
+                mbar_wait(&nfull[acc], (tile_n >> 1) & 1);
                 mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
-                const float4* tn4 = reinterpret_cast<const float4*>(p.tn + (size_t)tt * BN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + cg * EPI_COLS;
+                // |t|^2 of this warp's columns: every lane reads the same 16 bytes (shared-memory broadcast)
+                const float4* tn4 = reinterpret_cast<const float4*>(tn_smem + acc * BN + cg * EPI_COLS);
+                const int colbase = tt * BN + cg * EPI_COLS;
+                // TMEM -> registers double buffered: the load of chunk c+1 flies while chunk c is scanned
+                uint32_t va[32], vb[32];
+                tc_ld32(taddr, va);
 #pragma unroll 1
-                for (int cc = 0; cc < BN / 64; cc++) {
-                    uint32_t v0[32], v1[32];
-                    __syncwarp();
-                    tc_ld32(taddr + cc * 64, v0);
-                    tc_ld32(taddr + cc * 64 + 32, v1);
-                    tc_wait_ld();
-                    const int col0 = tt * BN + cc * 64;
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++) {
-                        float4 n = __ldg(tn4 + cc * 16 + j4);
-                        float s0 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 0]), n.x);
-                        float s1 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 1]), n.y);
-                        float s2 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 2]), n.z);
-                        float s3 = __fadd_rn(__uint_as_float(v0[j4 * 4 + 3]), n.w);
-                        if (s0 < bs[3]) top4_insert(s0, col0 + j4 * 4 + 0, bs, bi);
-                        if (s1 < bs[3]) top4_insert(s1, col0 + j4 * 4 + 1, bs, bi);
-                        if (s2 < bs[3]) top4_insert(s2, col0 + j4 * 4 + 2, bs, bi);
-                        if (s3 < bs[3]) top4_insert(s3, col0 + j4 * 4 + 3, bs, bi);
-                    }
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++) {
-                        float4 n = __ldg(tn4 + cc * 16 + 8 + j4);
-                        float s0 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 0]), n.x);
-                        float s1 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 1]), n.y);
-                        float s2 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 2]), n.z);
-                        float s3 = __fadd_rn(__uint_as_float(v1[j4 * 4 + 3]), n.w);
-                        if (s0 < bs[3]) top4_insert(s0, col0 + 32 + j4 * 4 + 0, bs, bi);
-                        if (s1 < bs[3]) top4_insert(s1, col0 + 32 + j4 * 4 + 1, bs, bi);
-                        if (s2 < bs[3]) top4_insert(s2, col0 + 32 + j4 * 4 + 2, bs, bi);
-                        if (s3 < bs[3]) top4_insert(s3, col0 + 32 + j4 * 4 + 3, bs, bi);
-                    }
+                for (int cc = 0; cc < EPI_COLS / 32; cc += 2) {
+                    tc_wait_ld32(va);
+                    tc_ld32(taddr + (cc + 1) * 32, vb);
+                    scan_chunk(va, taddr + cc * 32, tn4 + cc * 8, colbase + cc * 32, bs, bi);
+                    tc_wait_ld32(vb);
+                    if (cc + 2 < EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
+                    scan_chunk(vb, taddr + (cc + 1) * 32, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, bs, bi);
                 }
                 // accumulator drained: hand it back to the MMA warp
                 tc_fence_before();
@@ -386,7 +489,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
             const int qg = qtile * BM + row;
             if (qg < p.nq) {
-                const size_t o = (size_t)qg * p.n_split + split;
+                const size_t o = ((size_t)qg * p.n_seg + seg) * EPI_GROUPS + cg;
                 *reinterpret_cast<int4*>(p.cand_idx + o * TOPK) = make_int4(bi[0], bi[1], bi[2], bi[3]);
                 *reinterpret_cast<float4*>(p.cand_s + o * TOPK) = make_float4(bs[0], bs[1], bs[2], bs[3]);
             }
@@ -407,9 +510,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool lex_less(double d, int i, double bd, int bi) { return d < bd || (d == bd && i < bi); }
 
-// one warp per query; lane j owns candidates j and j + 32 (n_split * TOPK <= 64)
+// one warp per query; lane j owns candidates j and j + 32 (n_groups * TOPK <= 64, n_groups = splits x column groups)
 __global__ void __launch_bounds__(256)
-refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim, int n_split,
+refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim, int n_groups,
               const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_s,
               unsigned* __restrict__ misc /* [0] re-scan count, [1] max |t|^2 bits, [2] max deviation bits */,
               int32_t* __restrict__ idx2, float* __restrict__ dist2, double* __restrict__ d2out,
@@ -417,7 +520,7 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
 {
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (qi >= nq) return;
-    const int ncand = n_split * TOPK;
+    const int ncand = n_groups * TOPK;
     const float* qr = q + (size_t)qi * dim;
 
     double d[2];
@@ -427,7 +530,7 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
     for (int s = 0; s < 2; s++) {
         int c = lane + 32 * s;
         int ti = c < ncand ? cand_idx[(size_t)qi * ncand + c] : -1;
-        sc[s] = c < ncand ? cand_s[(size_t)qi * ncand + c] : INFINITY;
+        sc[s] = (c < ncand && ti >= 0) ? cand_s[(size_t)qi * ncand + c] : INFINITY;   // unused list slots are -1 / unset
         d[s] = INFINITY; id[s] = 0x7fffffff;
         if (ti >= 0 && ti < nt) {
             const float* tr = t + (size_t)ti * dim;
@@ -546,29 +649,28 @@ bool knn2_tc_preferred(int nq, int nt, int dim)
     return knn2_tc_supported(nq, nt, dim) && (double)nq * (double)nt >= 4.0e6;
 }
 
-// choose how many T splits per query tile: minimise the makespan (in T tiles) over the grid
-static void plan(int n_qtiles, int n_ttiles, int sms, int* n_split, int* tps)
+// Stream-K style plan: the n_qtiles x n_ttiles unit grid (query tile major) is cut into equal
+// contiguous ranges, one per CTA.  A query tile may be cut into at most MAX_SEG segments (each
+// writes its own candidate lists), which bounds the range length from below for small nq.
+static void plan(int n_qtiles, int n_ttiles, int sms, int* units_per_cta, int* n_seg, int* grid)
 {
-    long best = -1;
-    int bs = 1;
-    for (int s = 1; s <= MAX_SPLIT && s <= n_ttiles; s++) {
-        int per = (n_ttiles + s - 1) / s;
-        int real = (n_ttiles + per - 1) / per;        // splits that are not empty
-        if (real != s) continue;
-        long items = (long)n_qtiles * s;
-        long waves = (items + sms - 1) / sms;
-        long cost = waves * (per + 1);                // +1: the Q tile load / pipeline refill per item
-        if (best < 0 || cost < best) { best = cost; bs = s; }
-    }
-    *n_split = bs;
-    *tps = (n_ttiles + bs - 1) / bs;
+    long total = (long)n_qtiles * n_ttiles;
+    long L = (total + sms - 1) / sms;
+    long lmin = MAX_SEG > 2 ? (n_ttiles + (MAX_SEG - 2) - 1) / (MAX_SEG - 2) : n_ttiles;   // <= MAX_SEG-2 interior cuts + 1
+    if (L < lmin) L = lmin;
+    if (L < 1) L = 1;
+    *units_per_cta = (int)L;
+    *grid = (int)((total + L - 1) / L);
+    long cuts = (n_ttiles + L - 1) / L;            // multiples of L strictly inside one row: at most this many
+    long segs = cuts + 1;
+    *n_seg = (int)(segs > MAX_SEG ? MAX_SEG : segs);
 }
 
 template <int KCH>
 static int launch_tc(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt, const TcParams& p, int grid)
 {
     constexpr int NS = n_slots(KCH);
-    constexpr int smem = 1024 + 2 * KCH * Q_CHUNK_BYTES + NS * T_CHUNK_BYTES + 1024;
+    constexpr int smem = 2 * KCH * Q_CHUNK_BYTES + NS * T_CHUNK_BYTES + SMEM_TAIL;
     static_assert(smem <= SMEM_LIMIT, "shared memory budget");
     static bool configured = false;
     if (!configured) {
@@ -590,19 +692,21 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     if (!knn2_tc_supported(nq, nt, dim)) { set_error("tcgen05 engine: unsupported shape nq=%d nt=%d dim=%d", nq, nt, dim); return ERP_E_DIM; }
     const int kch = (dim + KC - 1) / KC, dpad = kch * KC;
     const int n_qtiles = cdiv(nq, BM), n_ttiles = cdiv(nt, BN);
-    int n_split, tps;
-    plan(n_qtiles, n_ttiles, ctx->sm_count, &n_split, &tps);
+    int upc, n_seg, grid;
+    plan(n_qtiles, n_ttiles, ctx->sm_count, &upc, &n_seg, &grid);
+    const int n_lists = n_seg * EPI_GROUPS;
 
     int st = ERP_OK;
     float* qs = ctx->scratch<float>(S_TC_Q, (size_t)nq * 2 * dpad, &st);
     float* ts = ctx->scratch<float>(S_TC_T, (size_t)nt * 2 * dpad, &st);
     float* tn = ctx->scratch<float>(S_TC_TN, (size_t)n_ttiles * BN, &st);
-    int32_t* cand = ctx->scratch<int32_t>(S_TC_CAND, (size_t)nq * n_split * TOPK * 2, &st);
+    int32_t* cand = ctx->scratch<int32_t>(S_TC_CAND, (size_t)nq * n_lists * TOPK * 2, &st);
     int32_t* list = ctx->scratch<int32_t>(S_TC_LIST, (size_t)nq + 8, &st);
     int32_t* misc = ctx->scratch<int32_t>(S_TC_MISC, 8, &st);     // [0] re-scan count, [1] max |t|^2 bits, [2] max deviation bits
     ERP_TRY(st);
-    float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_split * TOPK);
+    float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_lists * TOPK);
     ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
+    ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * TOPK * sizeof(int32_t), ctx->stream));   // index -1: empty slot
 
     split_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, dim, dpad, -2.0f, qs, nullptr, nq, nullptr);
     ERP_LAUNCH(ctx, "split_kernel(q)");
@@ -614,10 +718,8 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     ERP_TRY(make_map(&mq, qs, nq, dpad, BM));
     ERP_TRY(make_map(&mt, ts, nt, dpad, BN));
     TcParams p;
-    p.nq = nq; p.nt = nt; p.n_qtiles = n_qtiles; p.n_ttiles = n_ttiles; p.n_split = n_split; p.tiles_per_split = tps;
+    p.nq = nq; p.nt = nt; p.n_qtiles = n_qtiles; p.n_ttiles = n_ttiles; p.units_per_cta = upc; p.n_seg = n_seg;
     p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s;
-    const int n_items = n_qtiles * n_split;
-    const int grid = n_items < ctx->sm_count ? n_items : ctx->sm_count;
 
     ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
     switch (kch) {
@@ -628,15 +730,15 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     }
     ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
 
-    refine_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_split, cand, cand_s,
+    refine_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_lists, cand, cand_s,
                                                         reinterpret_cast<unsigned*>(misc), d_idx2, d_dist2, d_d2, list);
     ERP_LAUNCH(ctx, "refine_kernel");
     ERP_TRY(knn2_exact_rescan(ctx, d_q, nq, d_t, nt, dim, list, misc, nq, d_idx2, d_dist2, d_d2));
 
     ctx->knn_stats[0] = ERP_ENGINE_TCGEN05;
     ctx->knn_stats[1] = -1;                       // re-scan count lives on the device: see erp_ctx_last_knn_stats
-    ctx->knn_stats[2] = n_split;
-    ctx->knn_stats[3] = n_items;
+    ctx->knn_stats[2] = n_seg;
+    ctx->knn_stats[3] = upc;
     ctx->knn_stats[4] = grid;
     ctx->tc_misc_dev = misc;
     return ERP_OK;
