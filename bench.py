@@ -209,8 +209,6 @@ def run_gpu(args, cfg):
     d_r4 = torch.empty((nq_all, 4), dtype=torch.float32, device=dev)
     d_packed = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                 # > 126 MB L2
-    h_n = torch.zeros(1, dtype=torch.int32).pin_memory()
-    h_packed = torch.zeros(1, dtype=torch.int64).pin_memory()
     if strong:
         counts = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
         gathered = torch.empty((world, nq_all // world + 1, 4), dtype=torch.int32, device=dev)
@@ -225,9 +223,8 @@ def run_gpu(args, cfg):
             e0.record(stream)
             ctx.knn2_match_dev(d_q, nq, d_t, nt, dim, RATIO, False, d_matches, d_n)
             e1.record(stream)
-            h_n.copy_(d_n, non_blocking=True)
             stream.synchronize()                       # the match count sizes the RANSAC launches
-            m = int(h_n.item())
+            m = int(d_n.item())
             if strong:
                 # rank-ordered all-gather of the per-rank match lists keeps ascending queryIdx;
                 # local query indices become global by adding each rank's shard offset
@@ -247,9 +244,8 @@ def run_gpu(args, cfg):
             ctx.ransac_local_dev(d_l3, d_r3, d_l4, d_r4, m, 1, hlo, hhi - hlo, SAMPLE, METRIC, TAU, d_packed)
             if strong:
                 sharding.allreduce_best(d_packed, dist)        # the one 8-byte collective
-            h_packed.copy_(d_packed, non_blocking=True)
             stream.synchronize()
-            res = ctx.ransac_finish_dev(d_l3, d_r3, d_l4, d_r4, m, 1, int(h_packed.item()), SAMPLE, METRIC, TAU)
+            res = ctx.ransac_finish_dev(d_l3, d_r3, d_l4, d_r4, m, 1, int(d_packed.item()), SAMPLE, METRIC, TAU)
             e2.record(stream)
         return (e0, e1, e2), m, res
 

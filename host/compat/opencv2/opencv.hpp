@@ -1,0 +1,3 @@
+// OpenCV compat shim: see opencv2/core.hpp
+#pragma once
+#include "opencv2/core.hpp"

@@ -1,0 +1,24 @@
+// XYZ-Euler helpers (reference: src/erp_rotation.cpp:14-63), written against plain arrays.
+#include "erp_rotation.hpp"
+
+cv::Mat erp_rotation::eular2rot(cv::Vec3d theta)
+{
+    const double cx = std::cos(theta[0]), sx = std::sin(theta[0]);
+    const double cy = std::cos(theta[1]), sy = std::sin(theta[1]);
+    const double cz = std::cos(theta[2]), sz = std::sin(theta[2]);
+    // Rx*Ry*Rz expanded
+    const double r[9] = {cy * cz, -cy * sz, sy,
+                         sx * sy * cz + cx * sz, -sx * sy * sz + cx * cz, -sx * cy,
+                         -cx * sy * cz + sx * sz, cx * sy * sz + sx * cz, cx * cy};
+    cv::Mat R(3, 3, CV_64FC1);
+    for (int i = 0; i < 9; i++) R.at<double>(i / 3, i % 3) = r[i];
+    return R;
+}
+
+cv::Vec3d erp_rotation::rot2eular(cv::Mat R)
+{
+    const double r22 = R.at<double>(2, 2), r12 = R.at<double>(1, 2);
+    const double sy = std::sqrt(r22 * r22 + r12 * r12);
+    const double x = sy < 1e-6 ? 0.0 : std::atan2(-r12, r22);
+    return cv::Vec3d(x, std::atan2(R.at<double>(0, 2), sy), std::atan2(-R.at<double>(0, 1), R.at<double>(0, 0)));
+}

@@ -1,0 +1,93 @@
+// feature_matcher.cpp -- host side of the matching boundary.
+#include "feature_matcher.hpp"
+
+#include "erp_host_context.hpp"
+
+using namespace std;
+using namespace cv;
+
+void feature_matcher::init()
+{
+#ifndef ERP_OPENCV_COMPAT
+    // SURF with OpenCV's defaults, as src/feature_matcher.cpp:13-15 (extended = false: 64-D)
+    detector = xfeatures2d::SURF::create();
+    descriptor_extractor = xfeatures2d::SURF::create();
+#endif
+    // no matcher object: the CUDA context is per thread and created on first use
+}
+
+void feature_matcher::deinit() {}
+
+vector<KeyPoint> feature_matcher::detect_key_point(const Mat &image)
+{
+#ifndef ERP_OPENCV_COMPAT
+    vector<KeyPoint> key_point;
+    detector->detect(image, key_point);
+    return key_point;
+#else
+    (void)image;
+    throw cv::Exception("feature_matcher::detect_key_point needs OpenCV xfeatures2d (SURF); this build uses the type shim");
+#endif
+}
+
+Mat feature_matcher::comput_descriptor(const Mat &image, vector<KeyPoint> &key_point)
+{
+#ifndef ERP_OPENCV_COMPAT
+    Mat d;
+    descriptor_extractor->compute(image, key_point, d);
+    return d;
+#else
+    (void)image; (void)key_point;
+    throw cv::Exception("feature_matcher::comput_descriptor needs OpenCV xfeatures2d (SURF); this build uses the type shim");
+#endif
+}
+
+// 2-NN under L2 + ratio test, ascending queryIdx (src/feature_matcher.cpp:42-59), exact brute force
+// instead of the reference's approximate FLANN trees.
+vector<DMatch> feature_matcher::match_two_image(const Mat &descriptor1, const Mat &descriptor2)
+{
+    if (descriptor1.type() != CV_32FC1 || descriptor2.type() != CV_32FC1)
+        throw cv::Exception("match_two_image: descriptors must be CV_32F single channel");
+    if (descriptor1.rows > 0 && descriptor1.cols != descriptor2.cols)
+        throw cv::Exception("match_two_image: descriptor dimensions differ");
+    vector<DMatch> good(descriptor1.rows > 0 ? descriptor1.rows : 0);
+    int n = 0;
+    static_assert(sizeof(DMatch) == sizeof(erp_dmatch), "cv::DMatch and erp_dmatch must share a layout");
+    int st = erp_knn2_match(erp_host::context(),
+                            descriptor1.ptr<float>(0), descriptor1.rows, descriptor1.step,
+                            descriptor2.ptr<float>(0), descriptor2.rows, descriptor2.step,
+                            descriptor1.cols, ratio_thresh, cross_check ? 1 : 0,
+                            reinterpret_cast<erp_dmatch*>(good.data()), &n);
+    // the reference throws cv::Exception out of knnMatch on malformed input (e.g. < 2 train rows)
+    if (st != ERP_OK) throw cv::Exception(string("match_two_image: ") + erp_last_error());
+    good.resize(n);
+    matches = good;
+    return good;
+}
+
+Mat feature_matcher::draw_match(const Mat& im_left, const Mat& im_right, const vector<KeyPoint>& key_left, const vector<KeyPoint>& key_right)
+{
+#ifndef ERP_OPENCV_COMPAT
+    Mat out;
+    drawMatches(im_left, key_left, im_right, key_right, matches, out, Scalar::all(-1), Scalar::all(-1), vector<char>(),
+                DrawMatchesFlags::NOT_DRAW_SINGLE_POINTS);
+    return out;
+#else
+    (void)im_left; (void)im_right; (void)key_left; (void)key_right;
+    throw cv::Exception("feature_matcher::draw_match needs OpenCV features2d; this build uses the type shim");
+#endif
+}
+
+void feature_matcher::do_all(const Mat &im_left, const Mat &im_right, vector<KeyPoint>& left_key, vector<KeyPoint>& right_key, int& match_size, Mat& match_output, int& total_key_num)
+{
+    // single-strip pipeline of src/feature_matcher.cpp:88-128: detect, describe, match, gather
+    vector<KeyPoint> kl = detect_key_point(im_left), kr = detect_key_point(im_right);
+    Mat dl = comput_descriptor(im_left, kl), dr = comput_descriptor(im_right, kr);
+    vector<DMatch> m = match_two_image(dl, dr);
+    total_key_num = (int)kl.size();
+    match_size = (int)m.size();
+    left_key.resize(m.size());
+    right_key.resize(m.size());
+    for (size_t i = 0; i < m.size(); i++) { left_key[i] = kl[m[i].queryIdx]; right_key[i] = kr[m[i].trainIdx]; }
+    match_output = draw_match(im_left, im_right, kl, kr);
+}

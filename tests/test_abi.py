@@ -63,9 +63,11 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle|#include\s+[\"<].*erp_oracle", text, re.M), f
     host = os.path.join(ROOT, "host")
-    if os.path.isdir(host):
-        for f in os.listdir(host):
-            assert "erp_oracle" not in open(os.path.join(host, f), errors="ignore").read()
+    for dirpath, dirs, files in os.walk(host):
+        dirs[:] = [d for d in dirs if d != "_build"]
+        for f in files:
+            text = open(os.path.join(dirpath, f), errors="ignore").read()
+            assert "erp_oracle" not in text and not re.search(r"^\s*(import|from)\s+oracle", text, re.M), f
 
 
 @pytest.mark.parametrize("m,H,S", [(37, 3, 37), (200, 80, 50), (1000, 80, 250)])

@@ -1,0 +1,90 @@
+"""The C++ drop-in classes (host/: feature_matcher, eight_point with the reference's signatures)
+built over the C ABI.  CPU part: they compile and link, and without a GPU the driver fails loudly
+(there is no CPU fallback).  GPU part: the driver's outputs equal the oracle's."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from erp_match_eightpoint_test_b200 import binding, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "host")
+EXE = os.path.join(HOST, "_build", "dropin_main")
+
+
+def _build():
+    from erp_match_eightpoint_test_b200 import build as b
+
+    b.build()
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    assert os.path.exists(EXE)
+
+
+def _write_input(path, q, t, lxy, rxy, W, H):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<5i", q.shape[0], t.shape[0], q.shape[1], W, H))
+        for a in (q, t, lxy, rxy):
+            f.write(np.ascontiguousarray(a, np.float32).tobytes())
+
+
+def _scene(nq=3000, nt=3200, W=4096, H=2048, seed=21):
+    q, t, planted = synth.descriptor_pair(nq, nt, 64, seed=seed)
+    qi = np.nonzero(planted >= 0)[0]
+    kp = synth.keypoint_pair(len(qi), W, H, noise_px=0.3, outlier_frac=0.0, seed=seed + 1)
+    rng = np.random.default_rng(seed)
+    lxy = (rng.uniform(0, 1, (nq, 2)) * [W, H - 1]).astype(np.float32)
+    rxy = (rng.uniform(0, 1, (nt, 2)) * [W, H - 1]).astype(np.float32)
+    lxy[qi] = kp["left_xy"]
+    rxy[planted[qi]] = kp["right_xy"]
+    return q, t, lxy, rxy, W, H
+
+
+def test_host_classes_build_and_refuse_to_run_without_a_gpu(tmp_path):
+    _build()
+    syms = subprocess.run(["nm", "-C", os.path.join(HOST, "_build", "liberp_host.a")], capture_output=True, text=True).stdout
+    for name in ["feature_matcher::match_two_image(cv::Mat const&, cv::Mat const&)", "feature_matcher::init()",
+                 "feature_matcher::detect_key_point(cv::Mat const&)", "feature_matcher::do_all(",
+                 "eight_point::find(int, int, std::vector<cv::KeyPoint", "eight_point::eight_point_estimation(int, int,",
+                 "eight_point::initial_guess(int, int,", "random_array::random_array(int)", "erp_rotation::rot2eular(cv::Mat)"]:
+        assert name in syms, name
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    q, t, lxy, rxy, W, H = _scene(200, 220)
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    _write_input(inp, q, t, lxy, rxy, W, H)
+    r = subprocess.run([EXE, str(inp), str(out)], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and not out.exists()
+
+
+@pytest.mark.gpu
+def test_dropin_driver_matches_oracle(tmp_path):
+    _build()
+    q, t, lxy, rxy, W, H = _scene()
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    _write_input(inp, q, t, lxy, rxy, W, H)
+    r = subprocess.run([EXE, str(inp), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    n = struct.unpack_from("<i", raw, 0)[0]
+    got = np.frombuffer(raw, binding.DMATCH, n, 4)
+    want = O.match(q, t, 0.3, False)
+    assert got.tobytes() == want.tobytes()                       # feature_matcher::match_two_image
+    off = 4 + 16 * n
+    R = np.frombuffer(raw, np.float32, 3, off); T = np.frombuffer(raw, np.float32, 3, off + 12)
+    v = np.frombuffer(raw, np.int32, 2, off + 24)
+    R1 = np.frombuffer(raw, np.float32, 3, off + 32); R2 = np.frombuffer(raw, np.float32, 3, off + 44)
+    Tn = np.frombuffer(raw, np.float32, 3, off + 56)
+    l = O.bearings(lxy[want["queryIdx"]], W, H)
+    rr = O.bearings(rxy[want["trainIdx"]], W, H)
+    ref = O.initial_guess(l, rr, O.ref_sample_table(n))          # eight_point::find
+    assert np.abs(R - ref["R"]).max() < 1e-5 and np.abs(T - ref["T"]).max() < 1e-5
+    e = O.eight_point(l[:64], rr[:64])                           # eight_point::eight_point_estimation
+    a = np.abs(R1 - e["R1"]).max() + np.abs(R2 - e["R2"]).max()
+    b = np.abs(R1 - e["R2"]).max() + np.abs(R2 - e["R1"]).max()
+    assert min(a, b) < 2e-5 and np.abs(np.abs(Tn) - np.abs(e["T"])).max() < 1e-5
+    assert set(v.tolist()) <= {0, 1}
