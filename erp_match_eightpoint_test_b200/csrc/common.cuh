@@ -56,6 +56,7 @@ enum ScratchId {
     S_MASK, S_PARTIAL, S_CONS, S_MISC,
     S_TC_Q, S_TC_T, S_TC_QN, S_TC_TN, S_TC_CAND, S_TC_LIST, S_TC_MISC,
     S_RS_IDX, S_RS_DIST, S_RS_D2, S_RS_PARTIAL,
+    S_SC_E, S_SC_K, S_SC_MISC, S_SC_BOUNDS, S_SC_LIST,
     S_COUNT_
 };
 
@@ -68,6 +69,7 @@ struct erp_ctx {
     int engine = ERP_ENGINE_AUTO;
     uint64_t launches = 0;
     int64_t knn_stats[5] = {0, 0, 0, 0, 0};
+    int32_t* sc_misc_dev = nullptr;                 // device words of the last tensor-core best search: ., max c_lo, list length
     int32_t* tc_misc_dev = nullptr;                 // device words of the last tcgen05 call: re-scan count, ., deviation
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around the dominant distance kernel
     erp::Buf dev[erp::S_COUNT_];
@@ -117,5 +119,11 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
             int32_t* d_idx2, float* d_dist2, double* d_d2);
 bool knn2_tc_supported(int nq, int nt, int dim);
 bool knn2_tc_preferred(int nq, int nt, int dim);
+int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m, float tau,
+                  uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best);
+int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,
+                    const float* d_l4, const float* d_r4, int m, float tau, uint64_t hyp0,
+                    int32_t* d_counts, uint64_t* d_best);
+bool score_tc_preferred(int H, int m);
 
 } // namespace erp

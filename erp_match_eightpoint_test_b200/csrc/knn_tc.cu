@@ -22,9 +22,7 @@
 //                       is >= s_4th + |q|^2 - eps).  Uncertified queries go to a list.
 //   re-scan             the listed queries through the exact fp64 kernel (knn_exact.cu), T-split for
 //                       short lists.  Results are therefore identical to ERP_ENGINE_EXACT_SIMT.
-#include "common.cuh"
-
-#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through the runtime)
+#include "tc_common.cuh"
 
 namespace erp {
 
@@ -52,112 +50,11 @@ constexpr double KAPPA = 1.0 / 16384.0;
 
 __host__ __device__ constexpr int n_slots(int kch) { return (SMEM_LIMIT - 2 * kch * Q_CHUNK_BYTES - SMEM_TAIL) / T_CHUNK_BYTES; }
 
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 256 x 8, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// 32 lanes x 32 consecutive columns: thread i of the warp receives lane (base + i)
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, rows of 128 bytes, 8-row groups of
-// 1024 bytes (SBO), descriptor version 1 (sm_100).  addr may point inside the first swizzle row
-// (k advance of 32 bytes per UMMA K step).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                          // version
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
-// instruction descriptor: D fp32, A/B tf32, both K-major, N = 256, M = 128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------
 // prep: fp32 rows -> [hi | lo] (dpad each), norms
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_rna(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 
 // one warp per row.  out: n x (2*dpad).  norm (optional): n_pad floats, rows >= n get +inf.
 __global__ void __launch_bounds__(256)
@@ -207,32 +104,6 @@ struct TcParams {
     float* cand_s;            // same shape: approximate scores, ascending
 };
 
-// A CTA's unit range cut into segments: consecutive train tiles of one query tile.
-struct SegIter {
-    long u, end;
-    int n_ttiles, L;
-    __device__ SegIter(const TcParams& p, int cta)
-    {
-        L = p.units_per_cta; n_ttiles = p.n_ttiles;
-        u = (long)cta * L;
-        long total = (long)p.n_qtiles * p.n_ttiles;
-        end = u + L < total ? u + L : total;
-    }
-    // next segment: query tile, train tiles [t0, t1), list slot of the segment within its query tile
-    __device__ bool next(int& qtile, int& t0, int& t1, int& seg)
-    {
-        if (u >= end) return false;
-        qtile = (int)(u / n_ttiles);
-        long row0 = (long)qtile * n_ttiles;
-        t0 = (int)(u - row0);
-        long rem = end - u;
-        t1 = rem < n_ttiles - t0 ? t0 + (int)rem : n_ttiles;
-        seg = (int)(u / L - row0 / L);      // CTA boundaries (multiples of L) in (row0, u]
-        u += t1 - t0;
-        return true;
-    }
-};
-
 __device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[TOPK], int (&bi)[TOPK])
 {
     // strict <: equal scores keep the earlier (lower) train index
@@ -244,34 +115,6 @@ __device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[TOPK],
             else { bs[1] = s; bi[1] = idx; }
         } else { bs[2] = s; bi[2] = idx; }
     } else { bs[3] = s; bi[3] = idx; }
-}
-
-// wait for this thread's outstanding tcgen05.ld; the registers are operands so that no use of
-// them can be scheduled above the wait
-__device__ __forceinline__ void tc_wait_ld32(uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
-                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
-                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-                 :
-                 : "memory");
-}
-
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld8(uint32_t (&v)[8])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
-                 :
-                 : "memory");
 }
 
 // 32 accumulator columns of one query row.  Common case: s = acc + |t|^2 (32 independent adds), a min
@@ -363,7 +206,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // ================================================================ TMA producer
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, item_n = 0;
-            SegIter it(p, blockIdx.x);
+            SegIter it(p.n_qtiles, p.n_ttiles, p.units_per_cta, blockIdx.x);
             int qtile, t_begin, t_end, seg;
             for (; it.next(qtile, t_begin, t_end, seg); item_n++) {
                 mbar_wait(qempty, (item_n & 1) ^ 1);
@@ -390,7 +233,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, item_n = 0, tile_n = 0;
             const uint32_t q_base = smem_u32(q_smem), t_base = smem_u32(t_smem);
-            SegIter it(p, blockIdx.x);
+            SegIter it(p.n_qtiles, p.n_ttiles, p.units_per_cta, blockIdx.x);
             int qtile, t_begin, t_end, seg;
             for (; it.next(qtile, t_begin, t_end, seg); item_n++) {
                 mbar_wait(qfull, item_n & 1);
@@ -435,7 +278,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // overwritten once the epilogue has drained that accumulator (the MMA warp's condition too)
         if (lane == 0) {
             uint32_t tile_n = 0;
-            SegIter it(p, blockIdx.x);
+            SegIter it(p.n_qtiles, p.n_ttiles, p.units_per_cta, blockIdx.x);
             int qtile, t_begin, t_end, seg;
             while (it.next(qtile, t_begin, t_end, seg)) {
                 for (int tt = t_begin; tt < t_end; tt++, tile_n++) {
@@ -454,7 +297,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int cg = (warp - 4) >> 2;          // column group of the tile this warp scans
         const int row = ew * 32 + lane;          // query row inside the tile
         uint32_t tile_n = 0;
-        SegIter it(p, blockIdx.x);
+        SegIter it(p.n_qtiles, p.n_ttiles, p.units_per_cta, blockIdx.x);
         int qtile, t_begin, t_end, seg;
         while (it.next(qtile, t_begin, t_end, seg)) {
             float bs[TOPK];
@@ -601,46 +444,6 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-
-// rows x (2*dpad) fp32, row major; box = 32 floats x box_rows, 128B swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const float* base, int rows, int dpad, int box_rows)
-{
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ERP_E_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)(2 * dpad), (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)(2 * dpad) * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ERP_E_CUDA; }
-    return ERP_OK;
-}
-
 bool knn2_tc_supported(int nq, int nt, int dim) { return nq >= 1 && nt >= 2 && dim >= 4 && dim % 4 == 0 && dim <= 128; }
 
 // AUTO policy: tensor cores once the problem is large enough to amortise the extra passes
@@ -715,8 +518,8 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     ERP_LAUNCH(ctx, "split_kernel(t)");
 
     CUtensorMap mq, mt;
-    ERP_TRY(make_map(&mq, qs, nq, dpad, BM));
-    ERP_TRY(make_map(&mt, ts, nt, dpad, BN));
+    ERP_TRY(make_map(&mq, qs, nq, 2 * dpad, BM));
+    ERP_TRY(make_map(&mt, ts, nt, 2 * dpad, BN));
     TcParams p;
     p.nq = nq; p.nt = nt; p.n_qtiles = n_qtiles; p.n_ttiles = n_ttiles; p.units_per_cta = upc; p.n_seg = n_seg;
     p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s;

@@ -7,50 +7,12 @@
 //     Eh   = (float)(E * sqrt(2)/|E|_F)
 //     k_ab = l_a * r_b
 //     res  = fma(Eh8,k8, ... fma(Eh1,k1, Eh0*k0))
-#include "common.cuh"
+#include "score_common.cuh"
 
 namespace erp {
 
 constexpr int TH = 128;         // hypotheses per block: their scaled E stay in shared memory
 constexpr int SC_THREADS = 256;
-
-template <int METRIC>
-__device__ __forceinline__ bool inlier(const float* __restrict__ E, const float k[9], float4 l, float4 r,
-                                       float tau, float tau2, float sin2)
-{
-    float res = __fmul_rn(E[0], k[0]);
-#pragma unroll
-    for (int i = 1; i < 9; i++) res = __fmaf_rn(E[i], k[i], res);
-    if (METRIC == ERP_METRIC_ALGEBRAIC) return fabsf(res) < tau;
-    float n0 = __fmaf_rn(E[2], r.z, __fmaf_rn(E[1], r.y, __fmul_rn(E[0], r.x)));
-    float n1 = __fmaf_rn(E[5], r.z, __fmaf_rn(E[4], r.y, __fmul_rn(E[3], r.x)));
-    float n2 = __fmaf_rn(E[8], r.z, __fmaf_rn(E[7], r.y, __fmul_rn(E[6], r.x)));
-    float nn = __fmaf_rn(n2, n2, __fmaf_rn(n1, n1, __fmul_rn(n0, n0)));
-    float rr = __fmul_rn(res, res);
-    if (METRIC == ERP_METRIC_ANGULAR) return rr < __fmul_rn(sin2, nn);
-    float m0 = __fmaf_rn(E[6], l.z, __fmaf_rn(E[3], l.y, __fmul_rn(E[0], l.x)));
-    float m1 = __fmaf_rn(E[7], l.z, __fmaf_rn(E[4], l.y, __fmul_rn(E[1], l.x)));
-    float m2 = __fmaf_rn(E[8], l.z, __fmaf_rn(E[5], l.y, __fmul_rn(E[2], l.x)));
-    float mm = __fmaf_rn(m2, m2, __fmaf_rn(m1, m1, __fmul_rn(m0, m0)));
-    return rr < __fmul_rn(tau2, __fadd_rn(nn, mm));
-}
-
-__device__ __forceinline__ void kron9(float4 l, float4 r, float k[9])
-{
-    k[0] = __fmul_rn(l.x, r.x); k[1] = __fmul_rn(l.x, r.y); k[2] = __fmul_rn(l.x, r.z);
-    k[3] = __fmul_rn(l.y, r.x); k[4] = __fmul_rn(l.y, r.y); k[5] = __fmul_rn(l.y, r.z);
-    k[6] = __fmul_rn(l.z, r.x); k[7] = __fmul_rn(l.z, r.y); k[8] = __fmul_rn(l.z, r.z);
-}
-
-__device__ __forceinline__ void scale_E(const double* __restrict__ E, float* __restrict__ Eh)
-{
-    double n = 0;
-#pragma unroll
-    for (int i = 0; i < 9; i++) n += E[i] * E[i];
-    double s = n > 0 ? sqrt(2.0) / sqrt(n) : 0.0;
-#pragma unroll
-    for (int i = 0; i < 9; i++) Eh[i] = (float)(E[i] * s);
-}
 
 // grid (ceil(H/TH), msplit).  Each thread keeps C correspondences (their 9 products k_ab) in
 // registers and walks the block's hypothesis tile, whose 9 coefficients arrive as shared-memory
@@ -61,15 +23,20 @@ template <int METRIC, int C>
 __global__ void __launch_bounds__(SC_THREADS)
 score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
              const float4* __restrict__ r4, int m, float tau, float tau2, float sin2,
-             int32_t* __restrict__ counts)
+             int32_t* __restrict__ counts,
+             const int32_t* __restrict__ hlist, const int32_t* __restrict__ hlist_len)
 {
+    // with hlist: row i of the launch is hypothesis hlist[i], i < *hlist_len (blocks past the end
+    // exit: the host does not know the length); counts are indexed by list position
     __shared__ __align__(16) float Es[TH][12];
     __shared__ int cs[TH];
+    if (hlist) H = min(H, *hlist_len);
     const int h0 = blockIdx.x * TH;
+    if (h0 >= H) return;
     for (int t = threadIdx.x; t < TH; t += SC_THREADS) {
         int h = h0 + t;
         float e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (h < H) scale_E(E + (size_t)h * 9, e);
+        if (h < H) scale_E(E + (size_t)(hlist ? hlist[h] : h) * 9, e);
 #pragma unroll
         for (int i = 0; i < 9; i++) Es[t][i] = e[i];
         cs[t] = 0;
@@ -114,11 +81,13 @@ score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
 
 // packed best over a count array: (count << 32) | (0xFFFFFFFF - global id)
 __global__ void best_kernel(const int32_t* __restrict__ counts, int H, uint64_t hyp0,
-                            unsigned long long* __restrict__ best)
+                            unsigned long long* __restrict__ best,
+                            const int32_t* __restrict__ hlist, const int32_t* __restrict__ hlist_len)
 {
     unsigned long long b = 0;
+    if (hlist) H = min(H, *hlist_len);
     for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
-        unsigned long long id = hyp0 + (unsigned long long)h;
+        unsigned long long id = hyp0 + (unsigned long long)(hlist ? hlist[h] : h);
         unsigned long long p = ((unsigned long long)(uint32_t)counts[h] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)id);
         b = p > b ? p : b;
     }
@@ -180,12 +149,32 @@ int score_launch(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, cons
     const float4* l4 = (const float4*)d_l4;
     const float4* r4 = (const float4*)d_r4;
     switch (metric) {
-    case ERP_METRIC_ALGEBRAIC: score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts); break;
-    case ERP_METRIC_SAMPSON: score_kernel<ERP_METRIC_SAMPSON, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts); break;
-    case ERP_METRIC_ANGULAR: score_kernel<ERP_METRIC_ANGULAR, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts); break;
+    case ERP_METRIC_ALGEBRAIC: score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts, nullptr, nullptr); break;
+    case ERP_METRIC_SAMPSON: score_kernel<ERP_METRIC_SAMPSON, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts, nullptr, nullptr); break;
+    case ERP_METRIC_ANGULAR: score_kernel<ERP_METRIC_ANGULAR, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts, nullptr, nullptr); break;
     default: set_error("unknown metric %d", metric); return ERP_E_ARG;
     }
     ERP_LAUNCH(ctx, "score_kernel");
+    return ERP_OK;
+}
+
+// exact counts of the listed hypotheses, then their packed best merged into *d_best
+int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,
+                    const float* d_l4, const float* d_r4, int m, float tau, uint64_t hyp0,
+                    int32_t* d_counts /* H_max, scratch */, uint64_t* d_best)
+{
+    float tau2, sin2;
+    thresholds(tau, tau2, sin2);
+    ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H_max, ctx->stream));
+    // the list is usually short: always split the correspondences so that it still fills the machine
+    int msplit = max(1, min(cdiv(m, SC_THREADS * 8), 16));
+    dim3 grid(cdiv(H_max, TH), msplit);
+    score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m,
+                                                                              tau, tau2, sin2, d_counts, d_list, d_len);
+    ERP_LAUNCH(ctx, "score_kernel(list)");
+    best_kernel<<<min(cdiv(H_max, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(d_counts, H_max, hyp0,
+                                                                                  (unsigned long long*)d_best, d_list, d_len);
+    ERP_LAUNCH(ctx, "best_kernel(list)");
     return ERP_OK;
 }
 
@@ -227,7 +216,7 @@ ERP_API int erp_score_dev(erp_ctx* ctx, const double* d_E, int H, const float* d
     else ERP_TRY(score_launch(ctx, d_E, H, d_l4, d_r4, m, metric, tau, d_counts));
     if (d_best_packed) {
         best_kernel<<<min(cdiv(H, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(d_counts, H, hyp_offset,
-                                                                                (unsigned long long*)d_best_packed);
+                                                                                (unsigned long long*)d_best_packed, nullptr, nullptr);
         ERP_LAUNCH(ctx, "best_kernel");
     }
     return ERP_OK;
@@ -255,7 +244,11 @@ ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double*
         int n = H - h0 < CH ? H - h0 : CH;
         ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, n, S, seed, hyp_offset + h0, G));
         ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
-        ERP_TRY(erp_score_dev(ctx, E, n, d_l4, d_r4, m, metric, tau, hyp_offset + h0, counts, d_packed));
+        if (metric == ERP_METRIC_ALGEBRAIC &&
+            (ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m))))
+            ERP_TRY(score_tc_best(ctx, E, n, d_l4, d_r4, m, tau, hyp_offset + h0, counts, d_packed));
+        else
+            ERP_TRY(erp_score_dev(ctx, E, n, d_l4, d_r4, m, metric, tau, hyp_offset + h0, counts, d_packed));
     }
     return ERP_OK;
 }

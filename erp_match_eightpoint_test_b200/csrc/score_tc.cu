@@ -1,0 +1,334 @@
+// score_tc.cu -- best-hypothesis search on the tensor cores.  The H x M residual matrix
+//     res[h][c] = sum_k Eh[h][k] * (l_c (x) r_c)[k],  k = 0..8          (src/epipolar_tool.cpp:100-107)
+// is a GEMM with a 9-long contraction.  One tcgen05 pass with K = 32 carries the three 3xTF32
+// products at once:
+//     A row (hypothesis)     = [ Eh_hi(9) | Eh_hi(9) | Eh_lo(9) | 0 x 5 ]
+//     B row (correspondence) = [ K_hi(9)  | K_lo(9)  | K_hi(9)  | 0 x 5 ]      (128 bytes = one swizzle row)
+// so a 128 x 256 tile of residuals costs four UMMA instructions and never leaves the SM.  The
+// epilogue (one hypothesis row per thread, tcgen05.ld 32x32b) counts, per hypothesis,
+//     c_hi = #{ |res| < tau + delta }  >=  the exact inlier count of the SIMT kernel / the oracle,
+// where delta bounds |res_3xTF32 - res_fp32chain| (it scales with sqrt(2) * max|l||r|): two
+// instructions per residual (FSET + FADD).  Then, exactly (score_kernel, score.cu):
+//     L* = count of the hypothesis with the largest c_hi           (a lower bound of the best count)
+//     winner = best exact count over { h : c_hi[h] >= L* }         (nothing outside can reach L*)
+// so the packed best is bit-identical to scoring everything with the fp32 fma chain, at a fraction
+// of the FP32-pipe work.
+//
+// Work is cut stream-K style over (hypothesis tile, correspondence tile) units; a hypothesis tile
+// cut between two CTAs adds its partial counts atomically.
+#include "score_common.cuh"
+#include "tc_common.cuh"
+
+namespace erp {
+
+constexpr int SM_ROWS = 128;                 // hypotheses per tile (UMMA M)
+constexpr int SN_ROWS = 256;                 // correspondences per tile (UMMA N)
+constexpr int SA_BYTES = SM_ROWS * 128;      // 16 KB
+constexpr int SB_BYTES = SN_ROWS * 128;      // 32 KB
+constexpr int S_NSLOT = 6;                   // B ring
+constexpr int S_EPI_GROUPS = 2;
+constexpr int S_EPI_THREADS = S_EPI_GROUPS * 128;
+constexpr int S_THREADS = 128 + S_EPI_THREADS;
+constexpr int S_EPI_COLS = SN_ROWS / S_EPI_GROUPS;
+constexpr int S_SMEM = 2 * SA_BYTES + S_NSLOT * SB_BYTES + 256;
+static_assert(S_SMEM <= TC_SMEM_LIMIT, "shared memory budget");
+constexpr uint32_t S_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SN_ROWS >> 3) << 17) | ((uint32_t)(SM_ROWS >> 4) << 24);
+// |res_tc - res_chain| <= S_KAPPA * sqrt(2) * max_c |l_c||r_c|: 3xTF32 (2^-20) + the chain's own
+// rounding (9 * 2^-24) with a factor ~8 to spare
+constexpr float S_KAPPA = 1.0f / 65536.0f;
+
+// ---- operand preparation ---------------------------------------------------------------
+__global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __restrict__ Es /* H x 32 */)
+{
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    float e[9], hi[9], lo[9];
+    scale_E(E + (size_t)h * 9, e);
+#pragma unroll
+    for (int i = 0; i < 9; i++) { hi[i] = tf32_rna(e[i]); lo[i] = tf32_rna(__fsub_rn(e[i], hi[i])); }
+    float row[32];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { row[i] = hi[i]; row[9 + i] = hi[i]; row[18 + i] = lo[i]; }
+#pragma unroll
+    for (int i = 27; i < 32; i++) row[i] = 0.f;
+    float4* o = reinterpret_cast<float4*>(Es + (size_t)h * 32);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+}
+
+__global__ void prep_k_kernel(const float4* __restrict__ l4, const float4* __restrict__ r4, int m,
+                              float* __restrict__ Ks /* m x 32 */, unsigned* __restrict__ kmax_bits)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    float nrm = 0.f;
+    if (c < m) {
+        float4 l = l4[c], r = r4[c];
+        float k[9], hi[9], lo[9];
+        kron9(l, r, k);
+#pragma unroll
+        for (int i = 0; i < 9; i++) { hi[i] = tf32_rna(k[i]); lo[i] = tf32_rna(__fsub_rn(k[i], hi[i])); }
+        float row[32];
+#pragma unroll
+        for (int i = 0; i < 9; i++) { row[i] = hi[i]; row[9 + i] = lo[i]; row[18 + i] = hi[i]; }
+#pragma unroll
+        for (int i = 27; i < 32; i++) row[i] = 0.f;
+        float4* o = reinterpret_cast<float4*>(Ks + (size_t)c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+        nrm = sqrtf((l.x * l.x + l.y * l.y + l.z * l.z) * (r.x * r.x + r.y * r.y + r.z * r.z));
+    }
+    // non-negative floats (inf, NaN included) order like their bit patterns
+    unsigned b = __float_as_uint(nrm);
+    b = __reduce_max_sync(0xffffffffu, b);
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(kmax_bits, b);
+}
+
+// ---- the scoring kernel ------------------------------------------------------------------
+struct ScoreTcParams {
+    int H, m;
+    int n_htiles, n_ctiles, units_per_cta;
+    float tau;
+    const unsigned* kmax_bits;
+    int32_t* upper;               // H, zeroed by the caller: c_hi, partial sums are added
+};
+
+// 32 residuals of one hypothesis row: FSET.BF (1.0f when |res| < thr) + FADD into four independent
+// accumulators.  Counts stay exact in fp32 up to 2^24 correspondences.
+__device__ __forceinline__ float lt_one(uint32_t bits, float thr)
+{
+    float r;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(fabsf(__uint_as_float(bits))), "f"(thr));
+    return r;
+}
+__device__ __forceinline__ void count_chunk(const uint32_t (&v)[32], float hi, float (&acc)[4])
+{
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        acc[0] = __fadd_rn(acc[0], lt_one(v[j], hi));
+        acc[1] = __fadd_rn(acc[1], lt_one(v[j + 1], hi));
+        acc[2] = __fadd_rn(acc[2], lt_one(v[j + 2], hi));
+        acc[3] = __fadd_rn(acc[3], lt_one(v[j + 3], hi));
+    }
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_k, const ScoreTcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* a_smem = smem;                               // [2] hypothesis tiles
+    uint8_t* b_smem = smem + 2 * SA_BYTES;                // [S_NSLOT] correspondence tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + S_NSLOT * SB_BYTES);
+    uint64_t* full = bars;                  // [S_NSLOT]
+    uint64_t* empty = bars + S_NSLOT;       // [S_NSLOT]
+    uint64_t* afull = bars + 2 * S_NSLOT;   // [2]
+    uint64_t* aempty = afull + 2;           // [2]
+    uint64_t* tfull = afull + 4;            // [2]
+    uint64_t* tempty = afull + 6;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_e); tma_prefetch_desc(&map_k); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S_NSLOT; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1);
+            mbar_init(&tfull[i], 1); mbar_init(&tempty[i], S_EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, seg_n = 0;
+            SegIter it(p.n_htiles, p.n_ctiles, p.units_per_cta, blockIdx.x);
+            int ht, c0, c1, seg;
+            for (; it.next(ht, c0, c1, seg); seg_n++) {
+                const uint32_t ab = seg_n & 1;
+                mbar_wait(&aempty[ab], ((seg_n >> 1) & 1) ^ 1);
+                mbar_expect_tx(&afull[ab], SA_BYTES);
+                tma_load_2d(&map_e, &afull[ab], a_smem + ab * SA_BYTES, 0, ht * SM_ROWS);
+                for (int ct = c0; ct < c1; ct++) {
+                    mbar_wait(&empty[slot], ph ^ 1);
+                    mbar_expect_tx(&full[slot], SB_BYTES);
+                    tma_load_2d(&map_k, &full[slot], b_smem + slot * SB_BYTES, 0, ct * SN_ROWS);
+                    if (++slot == S_NSLOT) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, seg_n = 0, tile_n = 0;
+            const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+            SegIter it(p.n_htiles, p.n_ctiles, p.units_per_cta, blockIdx.x);
+            int ht, c0, c1, seg;
+            for (; it.next(ht, c0, c1, seg); seg_n++) {
+                const uint32_t ab = seg_n & 1;
+                mbar_wait(&afull[ab], (seg_n >> 1) & 1);
+                const uint32_t a = a_base + ab * SA_BYTES;
+                for (int ct = c0; ct < c1; ct++, tile_n++) {
+                    const uint32_t acc = tile_n & 1;
+                    mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
+                    mbar_wait(&full[slot], ph);
+                    tc_fence_after();
+                    const uint32_t b = b_base + slot * SB_BYTES;
+                    const uint32_t d_tmem = tmem_base + acc * SN_ROWS;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        tc_mma_tf32(d_tmem, smem_desc_sw128(a + k * 32), smem_desc_sw128(b + k * 32), S_IDESC, k != 0);
+                    tc_commit(&empty[slot]);
+                    tc_commit(&tfull[acc]);
+                    if (++slot == S_NSLOT) { slot = 0; ph ^= 1; }
+                }
+                tc_commit(&aempty[ab]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================ epilogue
+        const int ew = warp & 3, cg = (warp - 4) >> 2;
+        const int row = ew * 32 + lane;
+        // band around tau inside which the tensor-core value cannot decide the test
+        const float kmax = __uint_as_float(*p.kmax_bits);
+        const float delta = S_KAPPA * 1.41421356f * kmax;
+        float hi = p.tau + delta;
+        if (!(delta < INFINITY)) hi = INFINITY;                         // non-finite input: every finite residual may be an inlier
+        uint32_t tile_n = 0;
+        SegIter it(p.n_htiles, p.n_ctiles, p.units_per_cta, blockIdx.x);
+        int ht, c0, c1, seg;
+        while (it.next(ht, c0, c1, seg)) {
+            const int h = ht * SM_ROWS + row;
+            float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+            int pad_total = 0;
+            for (int ct = c0; ct < c1; ct++, tile_n++) {
+                const uint32_t acc = tile_n & 1;
+                mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * SN_ROWS + cg * S_EPI_COLS;
+                const int colbase = ct * SN_ROWS + cg * S_EPI_COLS;
+                uint32_t va[32], vb[32];
+                tc_ld32(taddr, va);
+#pragma unroll
+                for (int cc = 0; cc < S_EPI_COLS / 32; cc += 2) {
+                    tc_wait_ld32(va);
+                    tc_ld32(taddr + (cc + 1) * 32, vb);
+                    count_chunk(va, hi, acc4);
+                    tc_wait_ld32(vb);
+                    if (cc + 2 < S_EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
+                    count_chunk(vb, hi, acc4);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                // zero-filled columns past m have res = 0 exactly and were counted
+                pad_total += S_EPI_COLS - min(max(p.m - colbase, 0), S_EPI_COLS);
+            }
+            if (h < p.H) {
+                int n = (int)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+                if (0.f < hi) n -= pad_total;
+                if (n) atomicAdd(p.upper + h, n);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// packed (c_hi << 32 | ~h) maximum: the hypothesis with the largest upper bound, lowest index on ties
+__global__ void upper_argmax_kernel(const int32_t* __restrict__ upper, int H, unsigned long long* __restrict__ best)
+{
+    unsigned long long b = 0;
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+        unsigned long long v = ((unsigned long long)(uint32_t)upper[h] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)h);
+        b = v > b ? v : b;
+    }
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_down_sync(0xffffffffu, b, o); b = y > b ? y : b; }
+    if ((threadIdx.x & 31) == 0) atomicMax(best, b);
+}
+__global__ void first_candidate_kernel(const unsigned long long* __restrict__ best, int32_t* __restrict__ list, int32_t* __restrict__ len)
+{
+    list[0] = (int32_t)(0xFFFFFFFFu - (uint32_t)(*best & 0xFFFFFFFFull));
+    *len = 1;
+}
+// list = { h : c_hi[h] >= L* }, L* = the exact count the first candidate obtained
+__global__ void upper_select_kernel(const int32_t* __restrict__ upper, int H, const int32_t* __restrict__ exact_first,
+                                    int32_t* __restrict__ list, int32_t* __restrict__ n_list)
+{
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = h < H && upper[h] >= *exact_first;
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (!bal) return;
+    int lane = threadIdx.x & 31, base = 0;
+    if (lane == 0) base = atomicAdd(n_list, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) list[base + __popc(bal & ((1u << lane) - 1))] = h;
+}
+
+bool score_tc_preferred(int H, int m) { return (double)H * (double)m >= 3.0e7 && m >= 1 && m < (1 << 24) && H >= 1; }
+
+// merges into *d_best the packed (count << 32 | ~id) of the best of the H hypotheses, exactly as
+// erp_score_dev + best_kernel would (algebraic residual)
+int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m, float tau,
+                  uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best)
+{
+    if (m >= (1 << 24)) { set_error("score_tc_best: more than 2^24 correspondences"); return ERP_E_LIMIT; }
+    int st = ERP_OK;
+    float* Es = ctx->scratch<float>(S_SC_E, (size_t)H * 32, &st);
+    float* Ks = ctx->scratch<float>(S_SC_K, (size_t)m * 32, &st);
+    // misc words: [0] max|l||r| bits, [2] first list length, [3] final list length, [4..5] packed argmax of c_hi
+    unsigned* misc = ctx->scratch<unsigned>(S_SC_MISC, 8, &st);
+    int32_t* upper = ctx->scratch<int32_t>(S_SC_BOUNDS, (size_t)H, &st);
+    int32_t* list = ctx->scratch<int32_t>(S_SC_LIST, (size_t)H + 1, &st);
+    ERP_TRY(st);
+    ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(unsigned), ctx->stream));
+    ERP_CUDA(cudaMemsetAsync(upper, 0, sizeof(int32_t) * (size_t)H, ctx->stream));
+    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es);
+    ERP_LAUNCH(ctx, "prep_e_kernel");
+    prep_k_kernel<<<cdiv(m, 256), 256, 0, ctx->stream>>>((const float4*)d_l4, (const float4*)d_r4, m, Ks, misc);
+    ERP_LAUNCH(ctx, "prep_k_kernel");
+    CUtensorMap me, mk;
+    ERP_TRY(make_map(&me, Es, H, 32, SM_ROWS));
+    ERP_TRY(make_map(&mk, Ks, m, 32, SN_ROWS));
+    ScoreTcParams p;
+    p.H = H; p.m = m; p.n_htiles = cdiv(H, SM_ROWS); p.n_ctiles = cdiv(m, SN_ROWS);
+    long total = (long)p.n_htiles * p.n_ctiles;
+    long L = (total + ctx->sm_count - 1) / ctx->sm_count;
+    p.units_per_cta = (int)L;
+    int grid = (int)((total + L - 1) / L);
+    p.tau = tau; p.kmax_bits = misc; p.upper = upper;
+    static bool configured = false;
+    if (!configured) {
+        ERP_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
+        configured = true;
+    }
+    score_tc_kernel<<<grid, S_THREADS, S_SMEM, ctx->stream>>>(me, mk, p);
+    ERP_LAUNCH(ctx, "score_tc_kernel");
+    unsigned long long* amax = reinterpret_cast<unsigned long long*>(misc + 4);
+    upper_argmax_kernel<<<min(cdiv(H, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(upper, H, amax);
+    ERP_LAUNCH(ctx, "upper_argmax_kernel");
+    first_candidate_kernel<<<1, 1, 0, ctx->stream>>>(amax, list + H, (int32_t*)(misc + 2));
+    ERP_LAUNCH(ctx, "first_candidate_kernel");
+    // exact count of the most promising hypothesis: counts_scratch[0] = L*
+    ERP_TRY(score_list_best(ctx, d_E, 1, list + H, (const int32_t*)(misc + 2), d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best));
+    upper_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, H, d_counts_scratch, list, (int32_t*)(misc + 3));
+    ERP_LAUNCH(ctx, "upper_select_kernel");
+    ctx->sc_misc_dev = (int32_t*)misc;
+    return score_list_best(ctx, d_E, H, list, (const int32_t*)(misc + 3), d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best);
+}
+
+} // namespace erp

@@ -234,6 +234,27 @@ def test_score_counts_bit_exact(ctx, scene, metric, tau, m):
     assert np.array_equal(mask, O.inlier_mask(kp["E"], l[:m], r[:m], metric, tau)) and n == mask.sum() == got[300]
 
 
+@pytest.mark.parametrize("H,m,tau", [(5000, 3000, 0.002), (129, 257, 0.002), (20000, 777, 0.01), (3000, 3000, 1e-5),
+                                      (1500, 100, 0.002), (40000, 2500, 0.0005)])
+def test_tensor_core_best_search_is_exact(ctx, scene, H, m, tau):
+    """score_tc.cu bounds every hypothesis' inlier count with a 3xTF32 residual GEMM and re-scores the
+    contenders exactly: winner, count (the packed word) and inlier mask must equal the all-SIMT path
+    and the oracle, also when residuals crowd the threshold or tau is below the band width."""
+    kp, l, r = scene
+    rng = np.random.default_rng(H + m)
+    ll = np.concatenate([l, l[rng.integers(0, len(l), max(0, m - len(l)))]])[:m]
+    rr = np.concatenate([r, r[rng.integers(0, len(r), max(0, m - len(r)))]])[:m]
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    simt = ctx.ransac(ll, rr, seed=4, hyp_offset=10, H=H, S=8, metric=0, tau=tau)
+    ctx.set_engine(binding.ENGINE_TCGEN05)
+    tc = ctx.ransac(ll, rr, seed=4, hyp_offset=10, H=H, S=8, metric=0, tau=tau)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert tc["packed"] == simt["packed"]
+    assert np.array_equal(tc["mask"], simt["mask"]) and tc["count"] == simt["count"]
+    if H * m <= 2 * 10 ** 6:
+        assert tc["packed"] == O.ransac(ll, rr, seed=4, hyp0=10, H=H, S=8, metric=0, tau=tau)["packed"]
+
+
 def test_refit_on_inliers(ctx, scene):
     kp, l, r = scene
     mask = O.inlier_mask(kp["E"], l, r)
