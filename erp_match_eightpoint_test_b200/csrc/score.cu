@@ -126,6 +126,8 @@ int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, cons
                int H, int S, uint64_t seed, uint64_t hyp0, double* d_G);
 int gram_masked(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const uint8_t* d_mask, double* d_G);
 int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose);
+int solve_min8(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples, int H,
+               uint64_t seed, uint64_t hyp0, double* d_E, float* d_pose);
 
 static inline void thresholds(float tau, float& tau2, float& sin2)
 {
@@ -236,14 +238,17 @@ ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double*
     const int CH = 1 << 18;   // hypotheses per pass: 9.4 MB of Gram + 18.9 MB of E scratch
     int st = ERP_OK;
     int chunk = H < CH ? H : CH;
-    double* G = ctx->scratch<double>(S_GRAM, (size_t)chunk * 45, &st);
+    double* G = S == 8 ? nullptr : ctx->scratch<double>(S_GRAM, (size_t)chunk * 45, &st);
     double* E = ctx->scratch<double>(S_E, (size_t)chunk * 9, &st);
     int32_t* counts = ctx->scratch<int32_t>(S_COUNTS, chunk, &st);
     ERP_TRY(st);
     for (int h0 = 0; h0 < H; h0 += CH) {
         int n = H - h0 < CH ? H - h0 : CH;
-        ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, n, S, seed, hyp_offset + h0, G));
-        ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
+        if (S == 8) ERP_TRY(solve_min8(ctx, d_l3, d_r3, m, nullptr, n, seed, hyp_offset + h0, E, nullptr));
+        else {
+            ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, n, S, seed, hyp_offset + h0, G));
+            ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
+        }
         if (metric == ERP_METRIC_ALGEBRAIC &&
             (ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m))))
             ERP_TRY(score_tc_best(ctx, E, n, d_l4, d_r4, m, tau, hyp_offset + h0, counts, d_packed));
@@ -270,8 +275,12 @@ ERP_API int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double
     double *G = misc, *Eb = misc + 45, *Gr = misc + 54, *Er = misc + 99;
     float* pose = reinterpret_cast<float*>(misc + 108);
     int32_t* n_in = reinterpret_cast<int32_t*>(misc + 116);
-    ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, 1, S, seed, hyp, G));   // replay the winning sample
-    ERP_TRY(solve_batch(ctx, G, 1, Eb, nullptr));
+    // replay the winning sample with the arithmetic that scored it
+    if (S == 8) ERP_TRY(solve_min8(ctx, d_l3, d_r3, m, nullptr, 1, seed, hyp, Eb, nullptr));
+    else {
+        ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, 1, S, seed, hyp, G));
+        ERP_TRY(solve_batch(ctx, G, 1, Eb, nullptr));
+    }
     ERP_TRY(mask_launch(ctx, Eb, d_l4, d_r4, m, metric, tau, d_mask, n_in));
     ERP_TRY(gram_masked(ctx, d_l3, d_r3, m, d_mask, Gr));                   // refit on the inliers
     ERP_TRY(solve_batch(ctx, Gr, 1, Er, pose));
