@@ -62,45 +62,59 @@ def make_pair(cfg, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region.  The sampler is started
+    before the warm-up (nvidia-smi needs ~100 ms to come up, a step takes ~13 ms) and every sample is
+    time-stamped; mark() brackets the timed region and stop() keeps the samples inside it."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
+
         if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             out, _ = self.p.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
             out, _ = self.p.communicate()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        if not rows:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
-                    samples=len(sm), reasons=sorted(reasons))
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        where = "timed region"
+        if not inside:      # region shorter than the sampling period: the warm-up ran the same kernels
+            inside, where = rows, "warm-up + timed region"
+        reasons = sorted({n for r in inside for n in r[4]})
+        return dict(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                    power_w_max=float(max(r[3] for r in inside)), samples=len(inside), window=where, reasons=reasons)
 
 
 def peaks():
@@ -115,7 +129,7 @@ def peaks():
 # CPU arm: the reference's algorithm on the host cores (oracle port; the reference itself needs
 # OpenCV 3.4 C++ + xfeatures2d, which this image does not have -- DESIGN.md)
 # --------------------------------------------------------------------------------------------
-def cpu_sample(cfg, pair, q_rows=1024, hyps=4096):
+def cpu_sample(cfg, pair, q_rows=8192, hyps=32768):
     """A bounded sample of the workload: q_rows queries against the full train set, and
     `hyps` RANSAC hypotheses scored over the planted correspondences."""
     import oracle as O
@@ -142,21 +156,21 @@ def run_reference(args, cfg):
         return
     pair = make_pair(cfg, 0xE8B0 + 3)
     for _ in range(args.warmup):
-        cpu_sample(cfg, pair, 256, 512)
+        cpu_sample(cfg, pair, 512, 1024)
     tm = tr = 0.0
     s = None
     for _ in range(args.steps):
         s = cpu_sample(cfg, pair)
         tm += s["t_match"]; tr += s["t_ransac"]
-    value = args.steps * 1024 * cfg["nt"] / tm
+    value = args.steps * min(8192, cfg["nq"]) * cfg["nt"] / tm
     line = {
         "impl": "reference", "metric": "2nn_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tm + tr) / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 data, f64 accumulate", "data": "synthetic",
         "config": {"workload": cfg["desc"], "engine": "CPU oracle port of the reference path (OpenMP)", "sample": s["sample"]},
-        "ransac_hyps_per_s": args.steps * 4096 / tr,
+        "ransac_hyps_per_s": args.steps * 32768 / tr,
         "cpu_baseline": {"value": value, "unit": "dist-evals/s", "cores": s["cores"], "kind": "port", "sample": s["sample"],
-                         "ransac_hyps_per_s": args.steps * 4096 / tr},
+                         "ransac_hyps_per_s": args.steps * 32768 / tr},
         "e2e": {"value": value, "unit": "dist-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -258,16 +272,19 @@ def run_gpu(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler is already running)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 0)):
         flush_l2()
         step(False)
     barrier()
 
     # ---- timed region: exactly K steps, L2 flushed between them (flush excluded from the sums)
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     launches0 = ctx.launch_count
-    t_match = t_ransac = t_kernel = 0.0
+    t_match = t_ransac = t_kernel = t_score = 0.0
+    n_score = 0
     m = 0
     res = None
     wall0 = time.perf_counter()
@@ -278,16 +295,20 @@ def run_gpu(args, cfg):
         t_match += e0.elapsed_time(e1)
         t_ransac += e1.elapsed_time(e2)
         t_kernel += ctx.last_knn_kernel_ms()
+        sc_ms, n_score = ctx.last_score_kernel_ms()
+        t_score += sc_ms
     barrier()
+    if sampler:
+        sampler.mark_end()
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if sampler else None
 
     # max over ranks of the device-timed sums
-    tt = torch.tensor([t_match, t_ransac, t_kernel], dtype=torch.float64, device=dev)
+    tt = torch.tensor([t_match, t_ransac, t_kernel, t_score], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_match, t_ransac, t_kernel = [float(x) for x in tt.tolist()]
+    t_match, t_ransac, t_kernel, t_score = [float(x) for x in tt.tolist()]
 
     # ---- end-to-end through the host-buffer C ABI (what the C++ class wrappers call)
     pq, pt = h_q.numpy(), h_t.numpy()
@@ -345,11 +366,25 @@ def run_gpu(args, cfg):
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get(engine)
+        traffic = json.load(open(tr_path)).get(engine + ":" + args.workload)      # dram bytes per launch (ncu --set full)
+    # the second kernel of the step: hypothesis scoring.  Algorithmic work = 2*9 flop per residual;
+    # the tensor-core pass is followed by a 2-instruction-per-residual FP32 epilogue, which is what bounds it
+    sc_s = t_score * 1e-3 / args.steps
+    residuals = float(hhi - hlo) * m
+    score_roof = None
+    if sc_s > 0:
+        score_roof = {"kernel": "score_tc_kernel (3xTF32 residual GEMM + counting epilogue)" if stats["engine"] == 2 or args.engine in (None, 0, 2)
+                      else "score_kernel (SIMT)", "bound": "fp32-issue", "launches_per_step": n_score,
+                      "kernel_ms": t_score / args.steps, "residuals_per_s": residuals / sc_s,
+                      "achieved": residuals * 18.0 / sc_s / 1e12, "unit": "TFLOP/s",
+                      "peak": peak, "frac": residuals * 18.0 / sc_s / 1e12 / peak,
+                      "note": "algorithmic 18 flop per residual against the same 3xTF32 tensor peak; the epilogue issues "
+                              "2 FP32-pipe instructions per residual: %.2f of the 148x128-lane issue rate at the sampled clock"
+                              % (residuals * 2.0 / sc_s / (148 * 128 * 1.0e6 * ((clocks or {}).get("sm_mhz") or 1965.0)))}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        s = cpu_sample(cfg, pair, q_rows=4096, hyps=16384)
+        s = cpu_sample(cfg, pair, q_rows=min(65536, cfg["nq"]), hyps=min(262144, cfg["hyps"]))
         cpu = {"value": s["evals_per_s"], "unit": "dist-evals/s", "cores": s["cores"], "kind": "port", "sample": s["sample"],
                "ransac_hyps_per_s": s["hyps_per_s"], "seconds": s["t_match"] + s["t_ransac"]}
 
@@ -360,7 +395,7 @@ def run_gpu(args, cfg):
         if engine.startswith("tcgen05") else "f32 data; f64 direct-form accumulate", "data": "synthetic",
         "config": {"workload": cfg["desc"], "engine": engine, "nq_per_gpu": nq, "nt": nt, "dim": dim,
                    "hyps_per_gpu": hhi - hlo, "correspondences": m, "sample_size": SAMPLE, "ratio": RATIO, "tau": TAU,
-                   "l2": "flushed between timed steps (256 MiB write); inputs 51 MB < 126 MB L2",
+                   "l2": "flushed between timed steps (256 MiB write)",
                    "sharding": "query rows + hypothesis ids per rank, all-gather matches, 8-byte max all-reduce" if strong
                    else "one ERP pair per rank, no collective"},
         "match_ms": t_match / args.steps, "ransac_ms": t_ransac / args.steps,
@@ -370,6 +405,7 @@ def run_gpu(args, cfg):
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel_ms": t_kernel / args.steps,
                      "peak_from": f"{pk['src']} bf16 {pk['bf16']} TFLOP/s / 2 (tf32) / 3 (3xTF32); algorithmic 2*D flop per dist-eval"},
+        "roofline_scoring": score_roof,
         "e2e": {"value": world * nq * nt * e2e_steps / t_e2e_match if not strong else nq_all * nt * e2e_steps / t_e2e_match,
                 "unit": "dist-evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "match_ms": 1e3 * t_e2e_match / e2e_steps, "ransac_ms": 1e3 * t_e2e_ransac / e2e_steps,
@@ -387,7 +423,7 @@ def run_gpu(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "erp_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "erp_ctx_last_knn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "erp_ctx_last_knn_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "erp_ctx_last_score_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "erp_gather_bearings_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "erp_knn2_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
@@ -201,6 +202,11 @@ class Context:
         ms = C.c_float(0)
         _check(lib().erp_ctx_last_knn_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def last_score_kernel_ms(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        _check(lib().erp_ctx_last_score_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     # ---- matching (host buffers)
     def knn2_match(self, q, t, ratio: float = 0.3, cross_check: bool = False) -> np.ndarray:

@@ -114,6 +114,7 @@ ERP_API void erp_ctx_destroy(erp_ctx* ctx)
     for (auto& b : ctx->pinned) b.release();
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    for (cudaEvent_t e : ctx->ev_score) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -143,6 +144,22 @@ ERP_API int erp_ctx_last_knn_kernel_ms(erp_ctx* ctx, float* ms)
     DeviceGuard g(ctx->device);
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));
     ERP_CUDA(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+    return ERP_OK;
+}
+
+ERP_API int erp_ctx_last_score_kernel_ms(erp_ctx* ctx, float* ms, int* launches)
+{
+    ERP_ARG(ctx && ms, ERP_E_ARG, "erp_ctx_last_score_kernel_ms: bad argument");
+    DeviceGuard g(ctx->device);
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    float total = 0.f;
+    for (int i = 0; i + 1 < ctx->n_ev_score; i += 2) {
+        float t = 0.f;
+        ERP_CUDA(cudaEventElapsedTime(&t, ctx->ev_score[i], ctx->ev_score[i + 1]));
+        total += t;
+    }
+    *ms = total;
+    if (launches) *launches = ctx->n_ev_score / 2;
     return ERP_OK;
 }
 

@@ -72,6 +72,8 @@ struct erp_ctx {
     int32_t* sc_misc_dev = nullptr;                 // device words of the last tensor-core best search: ., max c_lo, list length
     int32_t* tc_misc_dev = nullptr;                 // device words of the last tcgen05 call: re-scan count, ., deviation
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around the dominant distance kernel
+    std::vector<cudaEvent_t> ev_score;              // pairs around the scoring kernel launches of the last RANSAC call
+    int n_ev_score = 0;                             // events used by that call
     erp::Buf dev[erp::S_COUNT_];
     erp::Buf pinned[8];
 
@@ -110,6 +112,19 @@ struct DeviceGuard {
 };
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// next event of the scoring-kernel timer (created on demand, reused across calls)
+inline int score_event(erp_ctx* ctx, cudaEvent_t* ev)
+{
+    if (ctx->n_ev_score == (int)ctx->ev_score.size()) {
+        cudaEvent_t e;
+        ERP_CUDA(cudaEventCreate(&e));
+        ctx->ev_score.push_back(e);
+    }
+    *ev = ctx->ev_score[ctx->n_ev_score++];
+    ERP_CUDA(cudaEventRecord(*ev, ctx->stream));
+    return ERP_OK;
+}
 
 // ---- internal device-level entry points shared across translation units ----
 int knn2_exact(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,

@@ -242,6 +242,7 @@ ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double*
     double* E = ctx->scratch<double>(S_E, (size_t)chunk * 9, &st);
     int32_t* counts = ctx->scratch<int32_t>(S_COUNTS, chunk, &st);
     ERP_TRY(st);
+    ctx->n_ev_score = 0;
     for (int h0 = 0; h0 < H; h0 += CH) {
         int n = H - h0 < CH ? H - h0 : CH;
         if (S == 8) ERP_TRY(solve_min8(ctx, d_l3, d_r3, m, nullptr, n, seed, hyp_offset + h0, E, nullptr));
@@ -252,8 +253,12 @@ ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double*
         if (metric == ERP_METRIC_ALGEBRAIC &&
             (ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m))))
             ERP_TRY(score_tc_best(ctx, E, n, d_l4, d_r4, m, tau, hyp_offset + h0, counts, d_packed));
-        else
+        else {
+            cudaEvent_t e0, e1;
+            ERP_TRY(score_event(ctx, &e0));
             ERP_TRY(erp_score_dev(ctx, E, n, d_l4, d_r4, m, metric, tau, hyp_offset + h0, counts, d_packed));
+            ERP_TRY(score_event(ctx, &e1));
+        }
     }
     return ERP_OK;
 }

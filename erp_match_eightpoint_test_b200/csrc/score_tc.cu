@@ -316,8 +316,11 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
         ERP_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
         configured = true;
     }
+    cudaEvent_t e0, e1;
+    ERP_TRY(score_event(ctx, &e0));
     score_tc_kernel<<<grid, S_THREADS, S_SMEM, ctx->stream>>>(me, mk, p);
     ERP_LAUNCH(ctx, "score_tc_kernel");
+    ERP_TRY(score_event(ctx, &e1));
     unsigned long long* amax = reinterpret_cast<unsigned long long*>(misc + 4);
     upper_argmax_kernel<<<min(cdiv(H, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(upper, H, amax);
     ERP_LAUNCH(ctx, "upper_argmax_kernel");

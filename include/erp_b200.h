@@ -96,6 +96,9 @@ int  erp_ctx_last_knn_stats(erp_ctx* ctx, int64_t out[5]);
 /* device time of the dominant distance kernel of the last erp_knn2* call, from CUDA events the
  * library records on its own stream around that launch (synchronises the stream) */
 int  erp_ctx_last_knn_kernel_ms(erp_ctx* ctx, float* ms);
+/* summed device time of the hypothesis-scoring kernel launches of the last erp_ransac_local_dev /
+ * erp_ransac call (same event mechanism); *launches (optional) = how many launches that was */
+int  erp_ctx_last_score_kernel_ms(erp_ctx* ctx, float* ms, int* launches);
 
 /* ---------------------------------------------------------------- matching
  * replaces feature_matcher::match_two_image      src/feature_matcher.hpp:36, .cpp:42-59
