@@ -14,8 +14,10 @@
 // so the packed best is bit-identical to scoring everything with the fp32 fma chain, at a fraction
 // of the FP32-pipe work.
 //
-// Work is cut stream-K style over (hypothesis tile, correspondence tile) units; a hypothesis tile
-// cut between two CTAs adds its partial counts atomically.
+// Work is cut stream-K style over (pair of hypothesis tiles, correspondence tile) units -- each 32 KB
+// correspondence tile that TMA brings in feeds two 128-row accumulators, which halves the L2 -> shared
+// memory traffic per MMA (with one it was the limiter: tensor pipe 42 % active).  A pair cut between two
+// CTAs adds its partial counts atomically.
 #include "score_common.cuh"
 #include "tc_common.cuh"
 
@@ -25,12 +27,13 @@ constexpr int SM_ROWS = 128;                 // hypotheses per tile (UMMA M)
 constexpr int SN_ROWS = 256;                 // correspondences per tile (UMMA N)
 constexpr int SA_BYTES = SM_ROWS * 128;      // 16 KB
 constexpr int SB_BYTES = SN_ROWS * 128;      // 32 KB
-constexpr int S_NSLOT = 6;                   // B ring
+constexpr int S_SUB = 2;                     // hypothesis tiles that share every correspondence tile (halves the L2 -> smem feed)
+constexpr int S_NSLOT = 5;                   // B ring
 constexpr int S_EPI_GROUPS = 2;
 constexpr int S_EPI_THREADS = S_EPI_GROUPS * 128;
 constexpr int S_THREADS = 128 + S_EPI_THREADS;
 constexpr int S_EPI_COLS = SN_ROWS / S_EPI_GROUPS;
-constexpr int S_SMEM = 2 * SA_BYTES + S_NSLOT * SB_BYTES + 256;
+constexpr int S_SMEM = 2 * S_SUB * SA_BYTES + S_NSLOT * SB_BYTES + 256;
 static_assert(S_SMEM <= TC_SMEM_LIMIT, "shared memory budget");
 constexpr uint32_t S_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SN_ROWS >> 3) << 17) | ((uint32_t)(SM_ROWS >> 4) << 24);
 // |res_tc - res_chain| <= S_KAPPA * sqrt(2) * max_c |l_c||r_c|: 3xTF32 (2^-20) + the chain's own
@@ -116,8 +119,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    uint8_t* a_smem = smem;                               // [2] hypothesis tiles
-    uint8_t* b_smem = smem + 2 * SA_BYTES;                // [S_NSLOT] correspondence tiles
+    uint8_t* a_smem = smem;                               // [2 buffers][S_SUB] hypothesis tiles
+    uint8_t* b_smem = smem + 2 * S_SUB * SA_BYTES;        // [S_NSLOT] correspondence tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + S_NSLOT * SB_BYTES);
     uint64_t* full = bars;                  // [S_NSLOT]
     uint64_t* empty = bars + S_NSLOT;       // [S_NSLOT]
@@ -156,8 +159,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
             for (; it.next(ht, c0, c1, seg); seg_n++) {
                 const uint32_t ab = seg_n & 1;
                 mbar_wait(&aempty[ab], ((seg_n >> 1) & 1) ^ 1);
-                mbar_expect_tx(&afull[ab], SA_BYTES);
-                tma_load_2d(&map_e, &afull[ab], a_smem + ab * SA_BYTES, 0, ht * SM_ROWS);
+                mbar_expect_tx(&afull[ab], S_SUB * SA_BYTES);
+#pragma unroll
+                for (int sub = 0; sub < S_SUB; sub++)
+                    tma_load_2d(&map_e, &afull[ab], a_smem + (ab * S_SUB + sub) * SA_BYTES, 0, (ht * S_SUB + sub) * SM_ROWS);
                 for (int ct = c0; ct < c1; ct++) {
                     mbar_wait(&empty[slot], ph ^ 1);
                     mbar_expect_tx(&full[slot], SB_BYTES);
@@ -176,19 +181,22 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
             for (; it.next(ht, c0, c1, seg); seg_n++) {
                 const uint32_t ab = seg_n & 1;
                 mbar_wait(&afull[ab], (seg_n >> 1) & 1);
-                const uint32_t a = a_base + ab * SA_BYTES;
-                for (int ct = c0; ct < c1; ct++, tile_n++) {
-                    const uint32_t acc = tile_n & 1;
-                    mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
+                for (int ct = c0; ct < c1; ct++) {
                     mbar_wait(&full[slot], ph);
-                    tc_fence_after();
                     const uint32_t b = b_base + slot * SB_BYTES;
-                    const uint32_t d_tmem = tmem_base + acc * SN_ROWS;
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        tc_mma_tf32(d_tmem, smem_desc_sw128(a + k * 32), smem_desc_sw128(b + k * 32), S_IDESC, k != 0);
+                    for (int sub = 0; sub < S_SUB; sub++, tile_n++) {
+                        const uint32_t acc = tile_n & 1;
+                        const uint32_t a = a_base + (ab * S_SUB + sub) * SA_BYTES;
+                        mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + acc * SN_ROWS;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            tc_mma_tf32(d_tmem, smem_desc_sw128(a + k * 32), smem_desc_sw128(b + k * 32), S_IDESC, k != 0);
+                        tc_commit(&tfull[acc]);
+                    }
                     tc_commit(&empty[slot]);
-                    tc_commit(&tfull[acc]);
                     if (++slot == S_NSLOT) { slot = 0; ph ^= 1; }
                 }
                 tc_commit(&aempty[ab]);
@@ -207,36 +215,46 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
         SegIter it(p.n_htiles, p.n_ctiles, p.units_per_cta, blockIdx.x);
         int ht, c0, c1, seg;
         while (it.next(ht, c0, c1, seg)) {
-            const int h = ht * SM_ROWS + row;
-            float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-            int pad_total = 0;
-            for (int ct = c0; ct < c1; ct++, tile_n++) {
-                const uint32_t acc = tile_n & 1;
-                mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * SN_ROWS + cg * S_EPI_COLS;
-                const int colbase = ct * SN_ROWS + cg * S_EPI_COLS;
-                uint32_t va[32], vb[32];
-                tc_ld32(taddr, va);
+            float acc4[S_SUB][4];
 #pragma unroll
-                for (int cc = 0; cc < S_EPI_COLS / 32; cc += 2) {
-                    tc_wait_ld32(va);
-                    tc_ld32(taddr + (cc + 1) * 32, vb);
-                    count_chunk(va, hi, acc4);
-                    tc_wait_ld32(vb);
-                    if (cc + 2 < S_EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
-                    count_chunk(vb, hi, acc4);
+            for (int sub = 0; sub < S_SUB; sub++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc4[sub][i] = 0.f;
+            int pad_total = 0;
+            for (int ct = c0; ct < c1; ct++) {
+                const int colbase = ct * SN_ROWS + cg * S_EPI_COLS;
+#pragma unroll
+                for (int sub = 0; sub < S_SUB; sub++, tile_n++) {
+                    const uint32_t acc = tile_n & 1;
+                    mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * SN_ROWS + cg * S_EPI_COLS;
+                    uint32_t va[32], vb[32];
+                    tc_ld32(taddr, va);
+#pragma unroll
+                    for (int cc = 0; cc < S_EPI_COLS / 32; cc += 2) {
+                        tc_wait_ld32(va);
+                        tc_ld32(taddr + (cc + 1) * 32, vb);
+                        count_chunk(va, hi, acc4[sub]);
+                        tc_wait_ld32(vb);
+                        if (cc + 2 < S_EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
+                        count_chunk(vb, hi, acc4[sub]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
                 // zero-filled columns past m have res = 0 exactly and were counted
                 pad_total += S_EPI_COLS - min(max(p.m - colbase, 0), S_EPI_COLS);
             }
-            if (h < p.H) {
-                int n = (int)((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
-                if (0.f < hi) n -= pad_total;
-                if (n) atomicAdd(p.upper + h, n);
+#pragma unroll
+            for (int sub = 0; sub < S_SUB; sub++) {
+                const int h = (ht * S_SUB + sub) * SM_ROWS + row;
+                if (h < p.H) {
+                    int n = (int)((acc4[sub][0] + acc4[sub][1]) + (acc4[sub][2] + acc4[sub][3]));
+                    if (0.f < hi) n -= pad_total;
+                    if (n) atomicAdd(p.upper + h, n);
+                }
             }
         }
     }
@@ -305,7 +323,7 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
     ERP_TRY(make_map(&me, Es, H, 32, SM_ROWS));
     ERP_TRY(make_map(&mk, Ks, m, 32, SN_ROWS));
     ScoreTcParams p;
-    p.H = H; p.m = m; p.n_htiles = cdiv(H, SM_ROWS); p.n_ctiles = cdiv(m, SN_ROWS);
+    p.H = H; p.m = m; p.n_htiles = cdiv(H, SM_ROWS * S_SUB); p.n_ctiles = cdiv(m, SN_ROWS);      // n_htiles counts tile PAIRS
     long total = (long)p.n_htiles * p.n_ctiles;
     long L = (total + ctx->sm_count - 1) / ctx->sm_count;
     p.units_per_cta = (int)L;
