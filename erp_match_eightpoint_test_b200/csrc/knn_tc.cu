@@ -37,7 +37,7 @@ constexpr int Q_CHUNK_BYTES = BM * KC * 4;   // 16 KB
 constexpr int T_CHUNK_BYTES = BN * KC * 4;   // 32 KB
 constexpr int EPI_GROUPS = 2;           // column groups per tile: 2 x 4 epilogue warps, two per scheduler
 constexpr int EPI_THREADS = EPI_GROUPS * 128;
-constexpr int TC_THREADS = 128 + EPI_THREADS;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 |t|^2 loads, 4.. epilogue
+constexpr int TC_THREADS = 128 + EPI_THREADS;   // warps 0..7 epilogue, then TMEM alloc, |t|^2 loads, TMA, MMA
 constexpr int EPI_COLS = BN / EPI_GROUPS;       // columns of a tile each epilogue thread scans
 constexpr int TOPK = 4;
 constexpr int MAX_SEG = 64 / (TOPK * EPI_GROUPS);     // segments per query tile: refine_kernel holds <= 64 candidates
@@ -181,19 +181,22 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t* nfull = qfull + 6;        // [2] |t|^2 of the tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 8);
 
+    // the scheduler favours the highest warp id among eligible warps: the single-thread feeders
+    // (TMA, MMA) sit on top so that the epilogue warps never delay them
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_ALLOC = EPI_THREADS / 32, W_NORM = W_ALLOC + 1, W_TMA = W_ALLOC + 2, W_MMA = W_ALLOC + 3;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == W_TMA && lane == 0) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_t);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == W_MMA && lane == 0) {
         for (int i = 0; i < NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(qfull, 1); mbar_init(qempty, 1);
         for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_THREADS / 32); mbar_init(&nfull[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -202,7 +205,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // ================================================================ TMA producer
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, item_n = 0;
@@ -228,7 +231,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ================================================================ MMA issuer
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, item_n = 0, tile_n = 0;
@@ -272,7 +275,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 tc_commit(qempty);
             }
         }
-    } else if (warp == 3) {
+    } else if (warp == W_NORM) {
         // ================================================================ |t|^2 producer
         // one bulk copy of 1 KB per tile into the buffer of the accumulator parity; it may be
         // overwritten once the epilogue has drained that accumulator (the MMA warp's condition too)
@@ -291,10 +294,10 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < W_ALLOC) {
         // ================================================================ epilogue (EPI_GROUPS x 4 warps)
         const int ew = warp & 3;                 // TMEM lane quarter this warp may read
-        const int cg = (warp - 4) >> 2;          // column group of the tile this warp scans
+        const int cg = warp >> 2;                // column group of the tile this warp scans
         const int row = ew * 32 + lane;          // query row inside the tile
         uint32_t tile_n = 0;
         SegIter it(p.n_qtiles, p.n_ttiles, p.units_per_cta, blockIdx.x);
@@ -342,7 +345,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
