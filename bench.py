@@ -132,7 +132,10 @@ def peaks():
 def cpu_sample(cfg, pair, q_rows=8192, hyps=32768):
     """A bounded sample of the workload: q_rows queries against the full train set, and
     `hyps` RANSAC hypotheses scored over the planted correspondences."""
+    # all host cores: torchrun exports OMP_NUM_THREADS=1, which would throttle the CPU arm
     import oracle as O
+
+    O.set_num_threads(len(os.sched_getaffinity(0)))
 
     q = pair["q"][:q_rows]
     t0 = time.perf_counter()

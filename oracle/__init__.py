@@ -57,6 +57,10 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 

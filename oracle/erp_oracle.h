@@ -45,6 +45,7 @@ typedef struct {
 enum { ORC_METRIC_ALGEBRAIC = 0, ORC_METRIC_SAMPSON = 1, ORC_METRIC_ANGULAR = 2 };
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* torchrun exports OMP_NUM_THREADS=1: the timed CPU arm undoes it */
 
 /* ---- matching (feature_matcher.cpp:42-59, exact-L2 limit of FLANN) ---- */
 /* idx/dist: nq x 2, d2: nq x 2 (fp64 squared distances, may be NULL).  nt >= 2. */
