@@ -14,6 +14,13 @@
 // so the packed best is bit-identical to scoring everything with the fp32 fma chain, at a fraction
 // of the FP32-pipe work.
 //
+// Progressive pruning (exact): the bound is accumulated in three passes over the correspondences.
+// Pass A covers the first 2048; its best-looking hypothesis is scored exactly -> L*.  Pass B extends
+// every bound until a hypothesis that is still empty could no longer reach L* (about m - L*
+// correspondences); hypotheses with  bound so far + correspondences not yet seen < L*  are dropped,
+// and pass C finishes only the survivors (typically a few % of H).  All lengths stay on the device:
+// the kernel reads its hypothesis count and correspondence-tile range from memory.
+//
 // Work is cut stream-K style over (pair of hypothesis tiles, correspondence tile) units -- each 32 KB
 // correspondence tile that TMA brings in feeds two 128-row accumulators, which halves the L2 -> shared
 // memory traffic per MMA (with one it was the limiter: tensor pipe 42 % active).  A pair cut between two
@@ -41,12 +48,15 @@ constexpr uint32_t S_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SN
 constexpr float S_KAPPA = 1.0f / 65536.0f;
 
 // ---- operand preparation ---------------------------------------------------------------
-__global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __restrict__ Es /* H x 32 */)
+// row i of Es = split scaled E of hypothesis list[i] (i < *list_len) or of hypothesis i
+__global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __restrict__ Es /* H x 32 */,
+                              const int32_t* __restrict__ list, const int32_t* __restrict__ list_len)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) H = min(H, *list_len);
     if (h >= H) return;
     float e[9], hi[9], lo[9];
-    scale_E(E + (size_t)h * 9, e);
+    scale_E(E + (size_t)(list ? list[h] : h) * 9, e);
 #pragma unroll
     for (int i = 0; i < 9; i++) { hi[i] = tf32_rna(e[i]); lo[i] = tf32_rna(__fsub_rn(e[i], hi[i])); }
     float row[32];
@@ -88,11 +98,25 @@ __global__ void prep_k_kernel(const float4* __restrict__ l4, const float4* __res
 
 // ---- the scoring kernel ------------------------------------------------------------------
 struct ScoreTcParams {
-    int H, m;
-    int n_htiles, n_ctiles, units_per_cta;
+    int m;
     float tau;
     const unsigned* kmax_bits;
-    int32_t* upper;               // H, zeroed by the caller: c_hi, partial sums are added
+    const int32_t* dyn;           // device: { hypotheses (rows of the A matrix), first correspondence tile, end tile }
+    int32_t* upper;               // one counter per A row, zeroed by the caller: partial sums are added
+};
+
+// the launch's unit grid, read from device memory by every role
+struct ScoreShape {
+    int H, ct_begin, n_htiles, n_ctiles, units_per_cta;
+    __device__ explicit ScoreShape(const ScoreTcParams& p)
+    {
+        H = p.dyn[0]; ct_begin = p.dyn[1];
+        n_ctiles = max(p.dyn[2] - ct_begin, 0);
+        n_htiles = (H + SM_ROWS * S_SUB - 1) / (SM_ROWS * S_SUB);            // tile PAIRS
+        long total = (long)n_htiles * n_ctiles;
+        units_per_cta = (int)((total + gridDim.x - 1) / gridDim.x);
+        if (units_per_cta < 1) units_per_cta = 1;
+    }
 };
 
 // 32 residuals of one hypothesis row: FSET.BF (1.0f when |res| < thr) + FADD into four independent
@@ -158,9 +182,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
         // ================================================================ TMA producer
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, seg_n = 0;
-            SegIter it(p.n_htiles, p.n_ctiles, p.units_per_cta, blockIdx.x);
+            const ScoreShape sh(p);
+            SegIter it(sh.n_htiles, sh.n_ctiles, sh.units_per_cta, blockIdx.x);
             int ht, c0, c1, seg;
             for (; it.next(ht, c0, c1, seg); seg_n++) {
+                c0 += sh.ct_begin; c1 += sh.ct_begin;
                 const uint32_t ab = seg_n & 1;
                 mbar_wait(&aempty[ab], ((seg_n >> 1) & 1) ^ 1);
                 mbar_expect_tx(&afull[ab], S_SUB * SA_BYTES);
@@ -180,7 +206,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, seg_n = 0, tile_n = 0;
             const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
-            SegIter it(p.n_htiles, p.n_ctiles, p.units_per_cta, blockIdx.x);
+            const ScoreShape sh(p);
+            SegIter it(sh.n_htiles, sh.n_ctiles, sh.units_per_cta, blockIdx.x);
             int ht, c0, c1, seg;
             for (; it.next(ht, c0, c1, seg); seg_n++) {
                 const uint32_t ab = seg_n & 1;
@@ -216,9 +243,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
         float hi = p.tau + delta;
         if (!(delta < INFINITY)) hi = INFINITY;                         // non-finite input: every finite residual may be an inlier
         uint32_t tile_n = 0;
-        SegIter it(p.n_htiles, p.n_ctiles, p.units_per_cta, blockIdx.x);
+        const ScoreShape sh(p);
+        SegIter it(sh.n_htiles, sh.n_ctiles, sh.units_per_cta, blockIdx.x);
         int ht, c0, c1, seg;
         while (it.next(ht, c0, c1, seg)) {
+            c0 += sh.ct_begin; c1 += sh.ct_begin;
             float acc4[S_SUB][4];
 #pragma unroll
             for (int sub = 0; sub < S_SUB; sub++)
@@ -254,7 +283,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
 #pragma unroll
             for (int sub = 0; sub < S_SUB; sub++) {
                 const int h = (ht * S_SUB + sub) * SM_ROWS + row;
-                if (h < p.H) {
+                if (h < sh.H) {
                     int n = (int)((acc4[sub][0] + acc4[sub][1]) + (acc4[sub][2] + acc4[sub][3]));
                     if (0.f < hi) n -= pad_total;
                     if (n) atomicAdd(p.upper + h, n);
@@ -271,7 +300,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
     }
 }
 
-// packed (c_hi << 32 | ~h) maximum: the hypothesis with the largest upper bound, lowest index on ties
+// packed (bound << 32 | ~h) maximum: the hypothesis with the largest bound, lowest index on ties
 __global__ void upper_argmax_kernel(const int32_t* __restrict__ upper, int H, unsigned long long* __restrict__ best)
 {
     unsigned long long b = 0;
@@ -282,26 +311,84 @@ __global__ void upper_argmax_kernel(const int32_t* __restrict__ upper, int H, un
     for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_down_sync(0xffffffffu, b, o); b = y > b ? y : b; }
     if ((threadIdx.x & 31) == 0) atomicMax(best, b);
 }
+
+// device words shared by the passes (int32 view of the misc scratch)
+enum { W_KMAX = 0, W_LEN1 = 2, W_LENF = 3, W_AMAX = 4 /* 2 words */, W_DYN_A = 8, W_DYN_B = 12, W_DYN_C = 16, W_LSTAR = 20,
+       W_REMAIN = 21, W_WORDS = 24 };
+
+__global__ void set_dyn_kernel(int32_t* __restrict__ dyn, int H, int ct_begin, int ct_end)
+{
+    dyn[0] = H; dyn[1] = ct_begin; dyn[2] = ct_end;
+}
+
 __global__ void first_candidate_kernel(const unsigned long long* __restrict__ best, int32_t* __restrict__ list, int32_t* __restrict__ len)
 {
     list[0] = (int32_t)(0xFFFFFFFFu - (uint32_t)(*best & 0xFFFFFFFFull));
     *len = 1;
 }
-// list = { h : c_hi[h] >= L* }, L* = the exact count the first candidate obtained
-__global__ void upper_select_kernel(const int32_t* __restrict__ upper, int H, const int32_t* __restrict__ exact_first,
-                                    int32_t* __restrict__ list, int32_t* __restrict__ n_list)
+
+// after pass A: L* is known (exact count of the best-looking hypothesis).  Pass B extends the bounds
+// to tile ct1: far enough that a hypothesis with nothing so far can no longer reach L*.
+__global__ void plan_passes_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ exact_first, int H, int m, int n0, int n_ct)
+{
+    const int lstar = *exact_first;
+    w[W_LSTAR] = lstar;
+    // correspondences a discarded hypothesis may still be missing: m - seen < L*  <=>  seen > m - L*
+    long need = (long)m - lstar;
+    need += need / 8 + 2 * SN_ROWS;                        // slack: bad hypotheses still collect a few inliers
+    int ct1 = (int)((need + SN_ROWS - 1) / SN_ROWS);
+    if (ct1 < n0) ct1 = n0;
+    if (ct1 > n_ct || lstar * 4 < m) ct1 = n_ct;           // weak best model: pruning cannot pay, finish in pass B
+    w[W_DYN_B] = H; w[W_DYN_B + 1] = n0; w[W_DYN_B + 2] = ct1;
+    w[W_DYN_C] = 0; w[W_DYN_C + 1] = ct1; w[W_DYN_C + 2] = n_ct;           // [0] = survivors, counted by the select kernel
+    long seen = (long)ct1 * SN_ROWS;
+    w[W_REMAIN] = seen >= m ? 0 : (int)(m - seen);
+}
+
+// survivors of pass B: bound so far + correspondences not yet seen >= L*
+__global__ void survivor_select_kernel(const int32_t* __restrict__ upper, int H, int32_t* __restrict__ w, int32_t* __restrict__ list)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = h < H && upper[h] >= *exact_first;
+    bool keep = h < H && upper[h] + w[W_REMAIN] >= w[W_LSTAR];
     unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (!bal) return;
     int lane = threadIdx.x & 31, base = 0;
-    if (lane == 0) base = atomicAdd(n_list, __popc(bal));
+    if (lane == 0) base = atomicAdd(&w[W_DYN_C], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) list[base + __popc(bal & ((1u << lane) - 1))] = h;
+}
+
+// contenders: survivors whose completed bound still reaches L*
+__global__ void final_select_kernel(const int32_t* __restrict__ upper, const int32_t* __restrict__ upper2,
+                                    const int32_t* __restrict__ survivors, int32_t* __restrict__ w, int32_t* __restrict__ list)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int h = s < w[W_DYN_C] ? survivors[s] : -1;
+    bool keep = h >= 0 && upper[h] + upper2[s] >= w[W_LSTAR];
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (!bal) return;
+    int lane = threadIdx.x & 31, base = 0;
+    if (lane == 0) base = atomicAdd(&w[W_LENF], __popc(bal));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (keep) list[base + __popc(bal & ((1u << lane) - 1))] = h;
 }
 
 bool score_tc_preferred(int H, int m) { return (double)H * (double)m >= 3.0e7 && m >= 1 && m < (1 << 24) && H >= 1; }
+
+static int launch_score_tc(erp_ctx* ctx, const CUtensorMap& me, const CUtensorMap& mk, const ScoreTcParams& p)
+{
+    static bool configured = false;
+    if (!configured) {
+        ERP_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
+        configured = true;
+    }
+    cudaEvent_t e0, e1;
+    ERP_TRY(score_event(ctx, &e0));
+    score_tc_kernel<<<ctx->sm_count, S_THREADS, S_SMEM, ctx->stream>>>(me, mk, p);
+    ERP_LAUNCH(ctx, "score_tc_kernel");
+    ERP_TRY(score_event(ctx, &e1));
+    return ERP_OK;
+}
 
 // merges into *d_best the packed (count << 32 | ~id) of the best of the H hypotheses, exactly as
 // erp_score_dev + best_kernel would (algebraic residual)
@@ -311,49 +398,57 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
     if (m >= (1 << 24)) { set_error("score_tc_best: more than 2^24 correspondences"); return ERP_E_LIMIT; }
     int st = ERP_OK;
     float* Es = ctx->scratch<float>(S_SC_E, (size_t)H * 32, &st);
+    float* Es2 = ctx->scratch<float>(S_SC_E2, (size_t)H * 32, &st);
     float* Ks = ctx->scratch<float>(S_SC_K, (size_t)m * 32, &st);
-    // misc words: [0] max|l||r| bits, [2] first list length, [3] final list length, [4..5] packed argmax of c_hi
-    unsigned* misc = ctx->scratch<unsigned>(S_SC_MISC, 8, &st);
-    int32_t* upper = ctx->scratch<int32_t>(S_SC_BOUNDS, (size_t)H, &st);
-    int32_t* list = ctx->scratch<int32_t>(S_SC_LIST, (size_t)H + 1, &st);
+    int32_t* w = ctx->scratch<int32_t>(S_SC_MISC, W_WORDS, &st);
+    int32_t* upper = ctx->scratch<int32_t>(S_SC_BOUNDS, (size_t)H * 2, &st);   // [H] all hypotheses, [H] pass C rows
+    int32_t* list = ctx->scratch<int32_t>(S_SC_LIST, (size_t)H * 2 + 1, &st);  // [H] survivors, [H] contenders, [1] first
     ERP_TRY(st);
-    ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(unsigned), ctx->stream));
-    ERP_CUDA(cudaMemsetAsync(upper, 0, sizeof(int32_t) * (size_t)H, ctx->stream));
-    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es);
+    int32_t *upper2 = upper + H, *survivors = list, *contenders = list + H, *first = list + 2 * (size_t)H;
+    const int n_ct = cdiv(m, SN_ROWS), n0 = n_ct < 8 ? n_ct : 8;
+    ERP_CUDA(cudaMemsetAsync(w, 0, W_WORDS * sizeof(int32_t), ctx->stream));
+    set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(w + W_DYN_A, H, 0, n0);
+    ERP_LAUNCH(ctx, "set_dyn_kernel");
+    ERP_CUDA(cudaMemsetAsync(upper, 0, sizeof(int32_t) * (size_t)H * 2, ctx->stream));
+    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es, nullptr, nullptr);
     ERP_LAUNCH(ctx, "prep_e_kernel");
-    prep_k_kernel<<<cdiv(m, 256), 256, 0, ctx->stream>>>((const float4*)d_l4, (const float4*)d_r4, m, Ks, misc);
+    prep_k_kernel<<<cdiv(m, 256), 256, 0, ctx->stream>>>((const float4*)d_l4, (const float4*)d_r4, m, Ks, (unsigned*)(w + W_KMAX));
     ERP_LAUNCH(ctx, "prep_k_kernel");
-    CUtensorMap me, mk;
+    CUtensorMap me, me2, mk;
     ERP_TRY(make_map(&me, Es, H, 32, SM_ROWS));
+    ERP_TRY(make_map(&me2, Es2, H, 32, SM_ROWS));
     ERP_TRY(make_map(&mk, Ks, m, 32, SN_ROWS));
     ScoreTcParams p;
-    p.H = H; p.m = m; p.n_htiles = cdiv(H, SM_ROWS * S_SUB); p.n_ctiles = cdiv(m, SN_ROWS);      // n_htiles counts tile PAIRS
-    long total = (long)p.n_htiles * p.n_ctiles;
-    long L = (total + ctx->sm_count - 1) / ctx->sm_count;
-    p.units_per_cta = (int)L;
-    int grid = (int)((total + L - 1) / L);
-    p.tau = tau; p.kmax_bits = misc; p.upper = upper;
-    static bool configured = false;
-    if (!configured) {
-        ERP_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
-        configured = true;
-    }
-    cudaEvent_t e0, e1;
-    ERP_TRY(score_event(ctx, &e0));
-    score_tc_kernel<<<grid, S_THREADS, S_SMEM, ctx->stream>>>(me, mk, p);
-    ERP_LAUNCH(ctx, "score_tc_kernel");
-    ERP_TRY(score_event(ctx, &e1));
-    unsigned long long* amax = reinterpret_cast<unsigned long long*>(misc + 4);
+    p.m = m; p.tau = tau; p.kmax_bits = (const unsigned*)(w + W_KMAX);
+
+    // pass A: every hypothesis, the first n0 correspondence tiles
+    p.dyn = w + W_DYN_A; p.upper = upper;
+    ERP_TRY(launch_score_tc(ctx, me, mk, p));
+    unsigned long long* amax = reinterpret_cast<unsigned long long*>(w + W_AMAX);
     upper_argmax_kernel<<<min(cdiv(H, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(upper, H, amax);
     ERP_LAUNCH(ctx, "upper_argmax_kernel");
-    first_candidate_kernel<<<1, 1, 0, ctx->stream>>>(amax, list + H, (int32_t*)(misc + 2));
+    first_candidate_kernel<<<1, 1, 0, ctx->stream>>>(amax, first, w + W_LEN1);
     ERP_LAUNCH(ctx, "first_candidate_kernel");
-    // exact count of the most promising hypothesis: counts_scratch[0] = L*
-    ERP_TRY(score_list_best(ctx, d_E, 1, list + H, (const int32_t*)(misc + 2), d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best));
-    upper_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, H, d_counts_scratch, list, (int32_t*)(misc + 3));
-    ERP_LAUNCH(ctx, "upper_select_kernel");
-    ctx->sc_misc_dev = (int32_t*)misc;
-    return score_list_best(ctx, d_E, H, list, (const int32_t*)(misc + 3), d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best);
+    // exact count of the most promising hypothesis over ALL correspondences: counts_scratch[0] = L*
+    ERP_TRY(score_list_best(ctx, d_E, 1, first, w + W_LEN1, d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best));
+    plan_passes_kernel<<<1, 1, 0, ctx->stream>>>(w, d_counts_scratch, H, m, n0, n_ct);
+    ERP_LAUNCH(ctx, "plan_passes_kernel");
+
+    // pass B: every hypothesis, tiles [n0, ct1)
+    p.dyn = w + W_DYN_B;
+    ERP_TRY(launch_score_tc(ctx, me, mk, p));
+    survivor_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, H, w, survivors);
+    ERP_LAUNCH(ctx, "survivor_select_kernel");
+
+    // pass C: the survivors, tiles [ct1, n_ct)
+    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es2, survivors, w + W_DYN_C);
+    ERP_LAUNCH(ctx, "prep_e_kernel(survivors)");
+    p.dyn = w + W_DYN_C; p.upper = upper2;
+    ERP_TRY(launch_score_tc(ctx, me2, mk, p));
+    final_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, upper2, survivors, w, contenders);
+    ERP_LAUNCH(ctx, "final_select_kernel");
+    ctx->sc_misc_dev = w;
+    return score_list_best(ctx, d_E, H, contenders, w + W_LENF, d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best);
 }
 
 } // namespace erp

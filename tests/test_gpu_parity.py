@@ -255,6 +255,23 @@ def test_tensor_core_best_search_is_exact(ctx, scene, H, m, tau):
         assert tc["packed"] == O.ransac(ll, rr, seed=4, hyp0=10, H=H, S=8, metric=0, tau=tau)["packed"]
 
 
+@pytest.mark.parametrize("m,outliers,H", [(20000, 0.3, 30000), (20000, 0.85, 30000), (6000, 0.5, 50000), (2048, 0.3, 20000)])
+def test_tensor_core_best_search_with_pruning(ctx, m, outliers, H):
+    """Three-pass progressive pruning (bounds on a prefix, exact L*, survivors only for the rest): the
+    winner must not depend on it, for high and low inlier ratios (pruning switches itself off)."""
+    kp = synth.keypoint_pair(m, 8192, 4096, outlier_frac=outliers, seed=m + H)
+    l, r = O.bearings(kp["left_xy"], 8192, 4096), O.bearings(kp["right_xy"], 8192, 4096)
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    simt = ctx.ransac(l, r, seed=9, hyp_offset=0, H=H, S=8, metric=0, tau=0.002)
+    ctx.set_engine(binding.ENGINE_TCGEN05)
+    tc = ctx.ransac(l, r, seed=9, hyp_offset=0, H=H, S=8, metric=0, tau=0.002)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert tc["packed"] == simt["packed"] and tc["count"] == simt["count"]
+    assert np.array_equal(tc["mask"], simt["mask"])
+    if outliers <= 0.5:
+        assert e_dist(tc["E_refit"], kp["E"]) < 2e-2
+
+
 def test_refit_on_inliers(ctx, scene):
     kp, l, r = scene
     mask = O.inlier_mask(kp["E"], l, r)
