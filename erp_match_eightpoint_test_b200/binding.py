@@ -55,6 +55,7 @@ _SIGNATURES = {
     "erp_ctx_last_knn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "erp_ctx_last_knn_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "erp_ctx_last_score_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "erp_ctx_last_score_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "erp_gather_bearings_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "erp_knn2_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
@@ -207,6 +208,11 @@ class Context:
         ms, n = C.c_float(0), C.c_int(0)
         _check(lib().erp_ctx_last_score_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def last_score_stats(self):
+        out = (C.c_int64 * 6)()
+        _check(lib().erp_ctx_last_score_stats(self._h, out))
+        return dict(hyps=out[0], tiles_all=out[1], tiles_total=out[2], survivors=out[3], contenders=out[4], lstar=out[5])
 
     # ---- matching (host buffers)
     def knn2_match(self, q, t, ratio: float = 0.3, cross_check: bool = False) -> np.ndarray:

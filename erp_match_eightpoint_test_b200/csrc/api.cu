@@ -163,6 +163,24 @@ ERP_API int erp_ctx_last_score_kernel_ms(erp_ctx* ctx, float* ms, int* launches)
     return ERP_OK;
 }
 
+ERP_API int erp_ctx_last_score_stats(erp_ctx* ctx, int64_t out[6])
+{
+    ERP_ARG(ctx && out, ERP_E_ARG, "erp_ctx_last_score_stats: bad argument");
+    for (int i = 0; i < 6; i++) out[i] = 0;
+    if (!ctx->sc_misc_dev) return ERP_OK;
+    DeviceGuard g(ctx->device);
+    int32_t w[24];
+    ERP_CUDA(cudaMemcpyAsync(w, ctx->sc_misc_dev, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    out[0] = w[12];            // hypotheses of the chunk
+    out[1] = w[14];            // correspondence tiles (of 256) every hypothesis was bounded on
+    out[2] = w[18];            // correspondence tiles in total
+    out[3] = w[16];            // survivors that were bounded on the rest
+    out[4] = w[3];             // contenders scored exactly
+    out[5] = w[20];            // L*: exact count of the first contender
+    return ERP_OK;
+}
+
 ERP_API int erp_ctx_last_knn_stats(erp_ctx* ctx, int64_t out[5])
 {
     ERP_ARG(ctx && out, ERP_E_ARG, "erp_ctx_last_knn_stats: bad argument");

@@ -99,6 +99,10 @@ int  erp_ctx_last_knn_kernel_ms(erp_ctx* ctx, float* ms);
 /* summed device time of the hypothesis-scoring kernel launches of the last erp_ransac_local_dev /
  * erp_ransac call (same event mechanism); *launches (optional) = how many launches that was */
 int  erp_ctx_last_score_kernel_ms(erp_ctx* ctx, float* ms, int* launches);
+/* the last tensor-core best-hypothesis search (last chunk of the last RANSAC call): [0] hypotheses,
+ * [1] correspondence tiles (256 each) every hypothesis was bounded on, [2] tiles in total,
+ * [3] survivors bounded on the remaining tiles, [4] contenders scored exactly, [5] L* */
+int  erp_ctx_last_score_stats(erp_ctx* ctx, int64_t out[6]);
 
 /* ---------------------------------------------------------------- matching
  * replaces feature_matcher::match_two_image      src/feature_matcher.hpp:36, .cpp:42-59
