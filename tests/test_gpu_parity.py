@@ -355,3 +355,48 @@ def test_cfg2_full_size_properties(ctx):
     assert e_dist(res["E_refit"], kp["E"]) < 5e-3 and res["count"] > 0.55 * len(m)
     assert res["mask"].sum() == res["count"]
     assert (res["mask"][kp["inlier"]].mean() > 0.8) and (res["mask"][~kp["inlier"]].mean() < 0.1)
+
+
+def test_cfg3_full_size_tensor_core_equals_exact_engine(ctx):
+    """configs[2] at full size on one GPU: 100k x 100k SURF-64.  The tcgen05 engine must return
+    exactly what the fp64 SIMT engine returns for every one of the 100k queries, certify (nearly) all
+    of them itself, and the 1M-hypothesis RANSAC must find the planted geometry; a 1/64 sub-sample of
+    the queries is also checked against the CPU oracle."""
+    q, t, planted = synth.descriptor_pair(100000, 100000, 64, seed=synth.SEED_BASE + 3)
+    ctx.set_engine(binding.ENGINE_TCGEN05)
+    idx, dist = ctx.knn2_raw(q, t)
+    st = ctx.last_knn_stats()
+    m = ctx.knn2_match(q, t, ratio=0.3)
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    eidx, edist = ctx.knn2_raw(q, t)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert np.array_equal(idx, eidx) and np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
+    assert st["rescanned"] <= 100 and st["deviation"] < 2.0 ** -14 / 4
+    assert len(m) == (planted >= 0).sum() and (planted[m["queryIdx"]] == m["trainIdx"]).all()
+    assert (np.diff(m["queryIdx"]) > 0).all()
+    sub = np.arange(0, 100000, 64)
+    oidx, odist, _ = O.knn2(q[sub], t)
+    assert np.array_equal(idx[sub], oidx) and np.array_equal(dist[sub], odist)
+    kp = synth.keypoint_pair(len(m), 8192, 4096, seed=synth.SEED_BASE + 4)
+    l, r = ctx.bearings(kp["left_xy"], 8192, 4096), ctx.bearings(kp["right_xy"], 8192, 4096)
+    res = ctx.ransac(l, r, seed=1, hyp_offset=0, H=1000000)
+    ps = ctx.last_score_stats()
+    assert e_dist(res["E_refit"], kp["E"]) < 5e-3 and res["count"] > 0.6 * len(m)
+    assert res["mask"].sum() == res["count"] == res["n_refit"]
+    assert 0 < ps["survivors"] < ps["hyps"] // 4 and ps["lstar"] <= res["count"]      # pruning was active and sound
+    # hypothesis sharding: the max of the packed words of two id ranges is the single-range winner
+    a = ctx.ransac(l, r, seed=1, hyp_offset=0, H=400000)
+    b = ctx.ransac(l, r, seed=1, hyp_offset=400000, H=600000)
+    assert max(a["packed"], b["packed"]) == res["packed"]
+
+
+@pytest.mark.parametrize("engine", [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05])
+def test_cfg4_style_surf128_cross_check(ctx, engine):
+    """configs[3] reduced: extended 128-D descriptors with cross-check matching, both engines."""
+    q, t, _ = synth.descriptor_pair(6000, 7000, 128, seed=41)
+    ctx.set_engine(engine)
+    got = ctx.knn2_match(q, t, ratio=-1.0, cross_check=True)
+    got_r = ctx.knn2_match(q, t, ratio=0.3, cross_check=True)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert got.tobytes() == O.match(q, t, ratio=-1.0, cross_check=True).tobytes()
+    assert got_r.tobytes() == O.match(q, t, ratio=0.3, cross_check=True).tobytes()
