@@ -93,6 +93,13 @@ _SIGNATURES = {
     "erp_find": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_int,
                            C.c_void_p, C.c_void_p]),
     "erp_libstdcxx_sample_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    "erp_rotate_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "erp_rotate_image_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "erp_crop_rotated_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_float, C.c_void_p, C.c_size_t]),
+    "erp_crop_rotated_image_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_float, C.c_void_p, C.c_size_t]),
+    "erp_rotate_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "erp_rotate_keypoints": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int]),
+    "erp_rotate_keypoints_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int]),
 }
 
 
@@ -346,6 +353,38 @@ class Context:
         _check(lib().erp_ransac_finish_dev(self._h, _ptr(d_l3), _ptr(d_r3), _ptr(d_l4), _ptr(d_r4), m, seed, packed, S,
                                            metric, tau, _ptr(d_mask), C.byref(res)))
         return self._result(res)
+
+    # ---- rows next to the hot path
+    def rotate_image(self, im, R) -> np.ndarray:
+        """erp_rotation::rotate_image (src/erp_rotation.cpp:94-122) on an (H, W, 3) uint8 image."""
+        im = np.ascontiguousarray(im, np.uint8)
+        out = np.empty_like(im)
+        _check(lib().erp_rotate_image(self._h, _ptr(im), im.shape[1], im.shape[0], im.strides[0], _ptr(_f64(R).reshape(9)),
+                                      _ptr(out), out.strides[0]))
+        return out
+
+    def rotate_image_dev(self, d_im, W, H, R, d_out):
+        _check(lib().erp_rotate_image_dev(self._h, _ptr(d_im), W, H, W * 3, _ptr(_f64(R).reshape(9)), _ptr(d_out), W * 3))
+
+    def crop_rotated_image(self, im, pitch_deg: float) -> np.ndarray:
+        """spherical_surf::crop_rotated_image (src/spherical_surf.cpp:16-48)."""
+        im = np.ascontiguousarray(im, np.uint8)
+        out = np.empty((im.shape[0] // 4, im.shape[1], 3), np.uint8)
+        _check(lib().erp_crop_rotated_image(self._h, _ptr(im), im.shape[1], im.shape[0], im.strides[0], pitch_deg,
+                                            _ptr(out), out.strides[0]))
+        return out
+
+    def rotate_pixels(self, rc, R, W, H) -> np.ndarray:
+        rc = np.ascontiguousarray(rc, np.int32)
+        out = np.empty_like(rc)
+        _check(lib().erp_rotate_pixels(self._h, _ptr(rc), rc.shape[0], _ptr(_f64(R).reshape(9)), W, H, _ptr(out)))
+        return out
+
+    def rotate_keypoints(self, xy, pitch_inv_deg: float, W, H) -> np.ndarray:
+        """spherical_surf::rotate_keypoint (src/spherical_surf.cpp:50-63); returns the rotated copy."""
+        xy = np.array(xy, np.float32, copy=True, order="C")
+        _check(lib().erp_rotate_keypoints(self._h, _ptr(xy), 8, xy.shape[0], pitch_inv_deg, W, H))
+        return xy
 
     # ---- reference mode
     def initial_guess(self, l3, r3, samples=None, H=80, S=None):

@@ -1,6 +1,8 @@
 // XYZ-Euler helpers (reference: src/erp_rotation.cpp:14-63), written against plain arrays.
 #include "erp_rotation.hpp"
 
+#include "erp_host_context.hpp"
+
 cv::Mat erp_rotation::eular2rot(cv::Vec3d theta)
 {
     const double cx = std::cos(theta[0]), sx = std::sin(theta[0]);
@@ -21,4 +23,30 @@ cv::Vec3d erp_rotation::rot2eular(cv::Mat R)
     const double sy = std::sqrt(r22 * r22 + r12 * r12);
     const double x = sy < 1e-6 ? 0.0 : std::atan2(-r12, r22);
     return cv::Vec3d(x, std::atan2(R.at<double>(0, 2), sy), std::atan2(-R.at<double>(0, 1), R.at<double>(0, 0)));
+}
+
+static void mat9(const cv::Mat& R, double* m)
+{
+    if (R.rows != 3 || R.cols != 3 || R.type() != CV_64FC1) throw cv::Exception("erp_rotation: rotation matrix must be 3x3 CV_64F");
+    for (int i = 0; i < 9; i++) m[i] = R.at<double>(i / 3, i % 3);
+}
+
+cv::Vec2i erp_rotation::rotate_pixel(const cv::Vec2i& in_vec, cv::Mat& rot_mat, int width, int height)
+{
+    double m[9];
+    mat9(rot_mat, m);
+    int in[2] = {in_vec[0], in_vec[1]}, out[2] = {0, 0};
+    erp_host::check(erp_rotate_pixels(erp_host::context(), in, 1, m, width, height, out), "erp_rotation::rotate_pixel");
+    return cv::Vec2i(out[0], out[1]);
+}
+
+cv::Mat erp_rotation::rotate_image(const cv::Mat& im, cv::Mat& rot_mat)
+{
+    if (im.type() != CV_8UC3) throw cv::Exception("erp_rotation::rotate_image: CV_8UC3 image expected");
+    double m[9];
+    mat9(rot_mat, m);
+    cv::Mat out(im.rows, im.cols, im.type());
+    erp_host::check(erp_rotate_image(erp_host::context(), im.data, im.cols, im.rows, im.step, m, out.data, out.step),
+                    "erp_rotation::rotate_image");
+    return out;
 }

@@ -1,6 +1,6 @@
-// erp_rotation.hpp -- the two pure functions of the reference's erp_rotation class that the hot
-// path needs on the host (src/erp_rotation.hpp:13-14, src/erp_rotation.cpp:14-63).  rotate_pixel /
-// rotate_image are image warps outside the hot path ("next").
+// erp_rotation.hpp -- drop-in for the reference's src/erp_rotation.hpp:9-19.  eular2rot / rot2eular
+// are host arithmetic (src/erp_rotation.cpp:14-63); rotate_pixel / rotate_image run on the B200
+// through the C ABI (erp_rotate_pixels, erp_rotate_image; src/erp_rotation.cpp:66-122).
 #pragma once
 #include <cmath>
 
@@ -18,4 +18,7 @@ class erp_rotation
 public:
     cv::Mat eular2rot(cv::Vec3d theta);      // R = Rx * Ry * Rz, XYZ Euler
     cv::Vec3d rot2eular(cv::Mat R);
+    // in_vec = (row, col).  One pixel per call costs a device round trip: batch through erp_rotate_pixels.
+    cv::Vec2i rotate_pixel(const cv::Vec2i& in_vec, cv::Mat& rot_mat, int width, int height);
+    cv::Mat rotate_image(const cv::Mat& im, cv::Mat& rot_mat);
 };

@@ -201,6 +201,26 @@ int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3,
                           uint64_t packed, int S, int metric, float tau,
                           uint8_t* d_mask /* m or NULL */, erp_ransac_result* result /* host */);
 
+/* ---------------------------------------------------------------- rows next to the hot path
+ * 8-bit, 3-channel images (cv::Mat CV_8UC3), strides in bytes.  Unmapped output pixels are written 0
+ * (the reference leaves them uninitialised).
+ * erp_rotation::rotate_image          src/erp_rotation.cpp:94-122 (inverse mapping with rot_mat.inv()) */
+int erp_rotate_image(erp_ctx* ctx, const uint8_t* im, int width, int height, size_t stride_bytes,
+                     const double* R9, uint8_t* out, size_t out_stride_bytes);
+int erp_rotate_image_dev(erp_ctx* ctx, const uint8_t* d_im, int width, int height, size_t stride_bytes,
+                         const double* R9 /* host */, uint8_t* d_out, size_t out_stride_bytes);
+/* spherical_surf::crop_rotated_image  src/spherical_surf.cpp:16-48: out is (height/4) x width */
+int erp_crop_rotated_image(erp_ctx* ctx, const uint8_t* im, int width, int height, size_t stride_bytes,
+                           float pitch_rot_deg, uint8_t* out, size_t out_stride_bytes);
+int erp_crop_rotated_image_dev(erp_ctx* ctx, const uint8_t* d_im, int width, int height, size_t stride_bytes,
+                               float pitch_rot_deg, uint8_t* d_out, size_t out_stride_bytes);
+/* erp_rotation::rotate_pixel          src/erp_rotation.cpp:66-92 on n (row, col) int32 pairs */
+int erp_rotate_pixels(erp_ctx* ctx, const int32_t* rc, int n, const double* R9, int width, int height, int32_t* out);
+/* spherical_surf::rotate_keypoint     src/spherical_surf.cpp:50-63, in place on (x, y) float pairs
+ * (stride 28 == sizeof(cv::KeyPoint)) */
+int erp_rotate_keypoints(erp_ctx* ctx, void* xy, size_t stride_bytes, int n, float pitch_rot_inv_deg, int width, int height);
+int erp_rotate_keypoints_dev(erp_ctx* ctx, void* d_xy, size_t stride_bytes, int n, float pitch_rot_inv_deg, int width, int height);
+
 /* ---------------------------------------------------------------- reference mode
  * eight_point::initial_guess  src/eight_point.hpp:20-23, .cpp:87-150
  * samples: H x S table (H = 80, S = int(m*0.25) in the reference) or NULL to replay

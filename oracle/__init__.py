@@ -101,6 +101,42 @@ def bearings(xy, W, H):
     return out
 
 
+def inv3(A):
+    A = _f64(A).reshape(9)
+    out = np.empty(9)
+    lib().orc_inv3(_p(A), _p(out))
+    return out.reshape(3, 3)
+
+
+def rotate_pixels(rc, R, W, H):
+    """erp_rotation::rotate_pixel on (n,2) int32 (row, col) pairs."""
+    rc = np.ascontiguousarray(rc, np.int32)
+    out = np.empty_like(rc)
+    lib().orc_rotate_pixels(_p(rc), rc.shape[0], _p(_f64(R).reshape(9)), int(W), int(H), _p(out))
+    return out
+
+
+def rotate_image(im, R):
+    """erp_rotation::rotate_image on an (H, W, 3) uint8 image."""
+    im = np.ascontiguousarray(im, np.uint8)
+    out = np.empty_like(im)
+    lib().orc_rotate_image(_p(im), im.shape[1], im.shape[0], _p(_f64(R).reshape(9)), _p(out))
+    return out
+
+
+def crop_rotated_image(im, pitch_deg):
+    im = np.ascontiguousarray(im, np.uint8)
+    out = np.empty((im.shape[0] // 4, im.shape[1], 3), np.uint8)
+    lib().orc_crop_rotated_image(_p(im), im.shape[1], im.shape[0], C.c_float(pitch_deg), _p(out))
+    return out
+
+
+def rotate_keypoints(xy, pitch_inv_deg, W, H):
+    xy = np.array(xy, np.float32, copy=True, order="C")
+    lib().orc_rotate_keypoints(_p(xy), 8, xy.shape[0], C.c_float(pitch_inv_deg), int(W), int(H))
+    return xy
+
+
 def eular2rot(theta):
     R = np.empty(9, np.float64)
     lib().orc_eular2rot(_p(_f64(theta)), _p(R))

@@ -44,6 +44,102 @@ int orc_num_threads(void)
 }
 
 /* ------------------------------------------------------------------------- */
+/* image / keypoint rotation: src/erp_rotation.cpp:66-122, src/spherical_surf.cpp:16-63 */
+/* ------------------------------------------------------------------------- */
+int orc_inv3(const double* S, double* t)
+{
+    /* cv::invert, n == 3, CV_64F: determinant by the first row, then the adjugate times 1/det */
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    if (d == 0.0) { memset(t, 0, 9 * sizeof(double)); return 0; }
+    d = 1.0 / d;
+    t[0] = (S[4] * S[8] - S[5] * S[7]) * d;
+    t[1] = (S[2] * S[7] - S[1] * S[8]) * d;
+    t[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+    t[3] = (S[5] * S[6] - S[3] * S[8]) * d;
+    t[4] = (S[0] * S[8] - S[2] * S[6]) * d;
+    t[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+    t[6] = (S[3] * S[7] - S[4] * S[6]) * d;
+    t[7] = (S[1] * S[6] - S[0] * S[7]) * d;
+    t[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+    return 1;
+}
+
+void orc_rotate_pixel(const int32_t* in, const double* R, int width, int height, int32_t* out)
+{
+    /* :68  Vec2d(M_PI*in[0]/height, 2*M_PI*in[1]/width)  -- evaluated left to right in double */
+    double lat = M_PI * in[0] / height, lon = 2 * M_PI * in[1] / width;
+    double c0 = -sin(lat) * cos(lon), c1 = sin(lat) * sin(lon), c2 = cos(lat);       /* :71-73 */
+    double r0 = R[0] * c0 + R[1] * c1 + R[2] * c2;                                      /* :77-79 */
+    double r1 = R[3] * c0 + R[4] * c1 + R[5] * c2;
+    double r2 = R[6] * c0 + R[7] * c1 + R[8] * c2;
+    double a = acos(r2), b = atan2(r1, -r0);                                            /* :82-83 */
+    if (b < 0) b += M_PI * 2;
+    out[0] = (int32_t)(height * a / M_PI);                                              /* :88-89 */
+    out[1] = (int32_t)(width * b / (2 * M_PI));
+}
+
+void orc_rotate_pixels(const int32_t* in, int n, const double* R, int width, int height, int32_t* out)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) orc_rotate_pixel(in + 2 * (size_t)i, R, width, height, out + 2 * (size_t)i);
+}
+
+void orc_rotate_image(const uint8_t* im, int width, int height, const double* R, uint8_t* out)
+{
+    double Rinv[9];
+    orc_inv3(R, Rinv);                                   /* :103 rot_mat.inv() */
+    memset(out, 0, (size_t)width * height * 3);          /* the reference leaves unmapped pixels uninitialised */
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < height; i++)
+        for (int j = 0; j < width; j++) {
+            int32_t in[2] = {i, j}, o[2];
+            orc_rotate_pixel(in, Rinv, width, height, o);
+            if (o[0] >= 0 && o[1] >= 0 && o[0] < height && o[1] < width)
+                memcpy(out + ((size_t)i * width + j) * 3, im + ((size_t)o[0] * width + o[1]) * 3, 3);
+        }
+}
+
+static void pitch_matrix(float pitch_deg, double* R)
+{
+    /* eular2rot(Vec3f(0, RAD(pitch), 0)): the angle passes through a float (spherical_surf.cpp:26,52) */
+    float ang = (float)(M_PI * pitch_deg / 180.0);
+    double th[3] = {0.0, (double)ang, 0.0};
+    orc_eular2rot(th, R);
+}
+
+void orc_crop_rotated_image(const uint8_t* im, int width, int height, float pitch_rot_deg, uint8_t* out)
+{
+    double R[9];
+    pitch_matrix(pitch_rot_deg, R);
+    int oh = height / 4;
+    memset(out, 0, (size_t)oh * width * 3);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < oh; i++)
+        for (int j = 0; j < width; j++) {
+            int32_t in[2] = {i + height * 3 / 8, j}, o[2];       /* :31 */
+            orc_rotate_pixel(in, R, width, height, o);
+            if (o[0] >= 0 && o[1] >= 0 && o[0] < height && o[1] < width)
+                memcpy(out + ((size_t)i * width + j) * 3, im + ((size_t)o[0] * width + o[1]) * 3, 3);
+        }
+}
+
+void orc_rotate_keypoints(void* xy, int stride_bytes, int n, float pitch_rot_inv_deg, int width, int height)
+{
+    double R[9];
+    pitch_matrix(pitch_rot_inv_deg, R);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        float* p = (float*)((char*)xy + (size_t)i * stride_bytes);
+        int32_t in[2], o[2];
+        in[0] = (int32_t)(p[1] + height * 3 / 8);            /* :57  int offset_i = pt.y + height*3/8 (float sum) */
+        in[1] = (int32_t)p[0];                               /* :58  Vec2i(offset_i, pt.x) */
+        orc_rotate_pixel(in, R, width, height, o);
+        p[0] = (float)o[1];                                  /* :61-62 */
+        p[1] = (float)o[0];
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* matching: src/feature_matcher.cpp:42-59                                   */
 /* ------------------------------------------------------------------------- */
 /*

@@ -65,6 +65,19 @@ void orc_bearings(const void* xy, int stride_bytes, int n, int W, int H, double*
 void orc_eular2rot(const double* theta3, double* R9);   /* erp_rotation.cpp:14-40 */
 void orc_rot2eular(const double* R9, double* e3);       /* erp_rotation.cpp:43-63 */
 
+/* ---- image / keypoint rotation (SURVEY section 8f "next" rows) ---- */
+/* cv::Mat::inv() of a 3x3 CV_64F matrix: OpenCV's closed-form cofactor path (modules/core/src/lapack.cpp) */
+int orc_inv3(const double* A9, double* out9);
+/* erp_rotation::rotate_pixel, erp_rotation.cpp:66-92; in/out are (row, col) */
+void orc_rotate_pixel(const int32_t* rc_in, const double* R9, int width, int height, int32_t* rc_out);
+void orc_rotate_pixels(const int32_t* rc_in, int n, const double* R9, int width, int height, int32_t* rc_out);
+/* erp_rotation::rotate_image, erp_rotation.cpp:94-122 (8-bit, 3 channels; unmapped pixels are left 0) */
+void orc_rotate_image(const uint8_t* im, int width, int height, const double* R9, uint8_t* out);
+/* spherical_surf::crop_rotated_image, spherical_surf.cpp:16-48: out is (height/4) x width x 3 */
+void orc_crop_rotated_image(const uint8_t* im, int width, int height, float pitch_rot_deg, uint8_t* out);
+/* spherical_surf::rotate_keypoint, spherical_surf.cpp:50-63: xy (x, y) float pairs, in place */
+void orc_rotate_keypoints(void* xy, int stride_bytes, int n, float pitch_rot_inv_deg, int width, int height);
+
 /* OpenCV SVD::compute semantics (no FULL_UV).  A: m x n row-major.
  * k = min(m,n).  w: k, u: m x k, vt: k x n.  u/vt may be NULL. */
 void orc_svd(const double* A, int m, int n, double* w, double* u, double* vt);

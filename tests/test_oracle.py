@@ -209,3 +209,29 @@ def test_ransac_recovers_pose_and_shards_agree():
     b = O.ransac(l, r, seed=7, hyp0=300, H=300)
     assert max(a["packed"], b["packed"]) == full["packed"]     # the allreduce(max) contract
     assert np.array_equal(np.concatenate([a["counts"], b["counts"]]), full["counts"])
+
+
+def test_inv3_is_opencv_closed_form():
+    """cv::Mat::inv() on 3x3 CV_64F (erp_rotation.cpp:103): the oracle's closed form is bit-identical to cv2.invert."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        A = rng.normal(size=(3, 3))
+        assert np.array_equal(O.inv3(A), cv2.invert(A)[1])
+    R = O.eular2rot([0.3, -1.1, 2.0])
+    assert np.array_equal(O.inv3(R), cv2.invert(R)[1]) and np.abs(O.inv3(R) - R.T).max() < 1e-15
+
+
+def test_rotate_pixel_round_trip_and_image_identity():
+    """rotate_pixel with R then R^-1 returns to the start within a pixel (one_image_test-style known answer),
+    and rotating an image by a rotation and back reproduces most of it."""
+    R = O.eular2rot([0.2, 0.1, -0.4])
+    rng = np.random.default_rng(1)
+    W, H = 2048, 1024
+    rc = np.stack([rng.integers(H // 3, 2 * H // 3, 5000), rng.integers(0, W, 5000)], 1).astype(np.int32)      # away from the poles
+    back = O.rotate_pixels(O.rotate_pixels(rc, R, W, H), R.T, W, H)
+    d = np.abs(back - rc)
+    d[:, 1] = np.minimum(d[:, 1], W - d[:, 1])
+    assert d.max() <= 3
+    kp = O.rotate_keypoints([[100.0, 40.0], [2000.5, 200.25]], 0.0, W, H)     # pitch 0: only the strip offset H*3/8
+    assert np.array_equal(kp[:, 1], [40 + H * 3 // 8, 200 + H * 3 // 8]) and np.abs(kp[:, 0] - [100, 2000]).max() <= 1
