@@ -100,6 +100,10 @@ _SIGNATURES = {
     "erp_rotate_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "erp_rotate_keypoints": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int]),
     "erp_rotate_keypoints_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int]),
+    "erp_draw_epipole": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_size_t]),
+    "erp_draw_epipole_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_size_t]),
 }
 
 
@@ -385,6 +389,14 @@ class Context:
         xy = np.array(xy, np.float32, copy=True, order="C")
         _check(lib().erp_rotate_keypoints(self._h, _ptr(xy), 8, xy.shape[0], pitch_inv_deg, W, H))
         return xy
+
+    def draw_epipole(self, E, left_xy, right_xy, im_w, im_h, out_w, out_h) -> np.ndarray:
+        """epipolar_tool::draw_epipole (src/epipolar_tool.cpp:84-128) for <= 7 selected correspondences."""
+        left_xy, right_xy = _f32(left_xy), _f32(right_xy)
+        out = np.empty((out_h, out_w, 3), np.uint8)
+        _check(lib().erp_draw_epipole(self._h, _ptr(_f64(E).reshape(9)), _ptr(left_xy), _ptr(right_xy), 8, left_xy.shape[0],
+                                      im_w, im_h, out_w, out_h, _ptr(out), out.strides[0]))
+        return out
 
     # ---- reference mode
     def initial_guess(self, l3, r3, samples=None, H=80, S=None):

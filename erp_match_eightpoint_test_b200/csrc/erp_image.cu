@@ -94,6 +94,53 @@ warp_image_kernel(const uint8_t* __restrict__ im, int W, int H, size_t stride, R
     } else { o[0] = 0; o[1] = 0; o[2] = 0; }
 }
 
+// ---- epipolar_tool::draw_epipole (/root/reference/src/epipolar_tool.cpp:84-128), one thread per pixel.
+// Sequential semantics of the reference loop (its collapse(3) pragma races): the last key whose
+// residual passes colours the pixel, then the 11 x 11 dots are painted in key order, clipped.
+struct EpiParams {
+    double e[9];
+    double l[7][3];
+    int di[7], dj[7];
+    int n_key;
+};
+__constant__ uint8_t kEpiColor[7][3] = {{0, 0, 255}, {0, 127, 255}, {0, 255, 255}, {0, 255, 0}, {255, 0, 0}, {135, 0, 75}, {211, 0, 148}};
+
+__global__ void __launch_bounds__(WT_X* WT_Y)
+draw_epipole_kernel(EpiParams P, int out_w, int out_h, uint8_t* __restrict__ out, size_t ostride)
+{
+    __shared__ double s_lat[WT_Y][2], s_lon[WT_X][2];
+    const double PI = 3.14159265358979323846;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j = blockIdx.x * WT_X + tx, i = blockIdx.y * WT_Y + ty;
+    if (ty == 0) {
+        double s, c;
+        sincos(2 * PI * ((double)j / out_w), &s, &c);
+        s_lon[tx][0] = s; s_lon[tx][1] = c;
+    } else if (ty == 1 && tx < WT_Y) {
+        double s, c;
+        sincos(PI * ((double)(blockIdx.y * WT_Y + tx) / out_h), &s, &c);
+        s_lat[tx][0] = s; s_lat[tx][1] = c;
+    }
+    __syncthreads();
+    if (i >= out_h || j >= out_w) return;
+    const double sl = s_lat[ty][0], cl = s_lat[ty][1], so = s_lon[tx][0], co = s_lon[tx][1];
+    const double p0 = -sl * co, p1 = sl * so, p2 = cl;
+    const double* e = P.e;
+    const double q0 = p0 * e[0] + p1 * e[3] + p2 * e[6];
+    const double q1 = p0 * e[1] + p1 * e[4] + p2 * e[7];
+    const double q2 = p0 * e[2] + p1 * e[5] + p2 * e[8];
+    int col = -1;
+    for (int k = 0; k < P.n_key; k++) {
+        double result = P.l[k][0] * q0 + P.l[k][1] * q1 + P.l[k][2] * q2;
+        if (fabs(result) < 0.002) col = k;
+    }
+    for (int k = 0; k < P.n_key; k++)
+        if (i >= P.di[k] - 5 && i <= P.di[k] + 5 && j >= P.dj[k] - 5 && j <= P.dj[k] + 5) col = k;
+    uint8_t* o = out + (size_t)i * ostride + (size_t)j * 3;
+    if (col >= 0) { o[0] = kEpiColor[col][0]; o[1] = kEpiColor[col][1]; o[2] = kEpiColor[col][2]; }
+    else { o[0] = 0; o[1] = 0; o[2] = 0; }
+}
+
 // cv::Mat::inv() for 3x3 CV_64F (closed form of OpenCV's lapack.cpp), evaluated on the host
 static bool inv3_host(const double* S, double* t)
 {
@@ -237,6 +284,54 @@ ERP_API int erp_rotate_keypoints(erp_ctx* ctx, void* xy, size_t stride_bytes, in
     ERP_CUDA(cudaMemcpy2DAsync(d, 8, xy, stride_bytes, 8, n, cudaMemcpyHostToDevice, ctx->stream));
     ERP_TRY(erp_rotate_keypoints_dev(ctx, d, 8, n, pitch_rot_inv_deg, width, height));
     ERP_CUDA(cudaMemcpy2DAsync(xy, stride_bytes, d, 8, 8, n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+// left_xy / right_xy: the n_key (<= 7) selected correspondences, (x, y) float pairs on the HOST
+ERP_API int erp_draw_epipole_dev(erp_ctx* ctx, const double* E9, const void* left_xy, const void* right_xy, size_t stride_bytes,
+                                 int n_key, int im_width, int im_height, int out_width, int out_height,
+                                 uint8_t* d_out, size_t out_stride_bytes)
+{
+    ERP_ARG(ctx && E9 && d_out && n_key >= 0 && n_key <= 7 && im_width > 0 && im_height > 0 && out_width > 0 && out_height > 0,
+            ERP_E_ARG, "erp_draw_epipole_dev: bad argument (at most 7 keys: the reference has 7 colours)");
+    ERP_ARG(n_key == 0 || (left_xy && right_xy && stride_bytes >= 8), ERP_E_ARG, "erp_draw_epipole_dev: null keypoints");
+    ERP_ARG(out_stride_bytes >= (size_t)out_width * 3, ERP_E_ARG, "erp_draw_epipole_dev: stride smaller than a row");
+    EpiParams P;
+    memcpy(P.e, E9, sizeof P.e);
+    P.n_key = n_key;
+    const double PI = 3.14159265358979323846;
+    const double rw = (double)out_width / (double)im_width, rh = (double)out_height / (double)im_height;
+    for (int k = 0; k < 7; k++) { P.di[k] = P.dj[k] = -1000; P.l[k][0] = P.l[k][1] = P.l[k][2] = 0.0; }
+    for (int k = 0; k < n_key; k++) {
+        const float* lp = (const float*)((const char*)left_xy + (size_t)k * stride_bytes);
+        const float* rp = (const float*)((const char*)right_xy + (size_t)k * stride_bytes);
+        // epipolar_tool.cpp:38-45: float quotient, fp64 trig (host libm, as the reference's constructor)
+        volatile double lon = 2 * PI * (lp[0] / im_width), lat = PI * (lp[1] / im_height);
+        P.l[k][0] = -sin(lat) * cos(lon); P.l[k][1] = sin(lat) * sin(lon); P.l[k][2] = cos(lat);
+        P.di[k] = (int)(rp[1] * rh);
+        P.dj[k] = (int)(rp[0] * rw);
+    }
+    DeviceGuard g(ctx->device);
+    dim3 grid(cdiv(out_width, WT_X), cdiv(out_height, WT_Y)), block(WT_X, WT_Y);
+    draw_epipole_kernel<<<grid, block, 0, ctx->stream>>>(P, out_width, out_height, d_out, out_stride_bytes);
+    ERP_LAUNCH(ctx, "draw_epipole_kernel");
+    return ERP_OK;
+}
+
+ERP_API int erp_draw_epipole(erp_ctx* ctx, const double* E9, const void* left_xy, const void* right_xy, size_t stride_bytes,
+                             int n_key, int im_width, int im_height, int out_width, int out_height,
+                             uint8_t* out, size_t out_stride_bytes)
+{
+    ERP_ARG(ctx && out && out_width > 0 && out_height > 0, ERP_E_ARG, "erp_draw_epipole: bad argument");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    uint8_t* d_out = ctx->scratch<uint8_t>(S_IMG_OUT, (size_t)out_width * out_height * 3, &st);
+    ERP_TRY(st);
+    ERP_TRY(erp_draw_epipole_dev(ctx, E9, left_xy, right_xy, stride_bytes, n_key, im_width, im_height, out_width, out_height,
+                                 d_out, (size_t)out_width * 3));
+    ERP_CUDA(cudaMemcpy2DAsync(out, out_stride_bytes, d_out, (size_t)out_width * 3, (size_t)out_width * 3, out_height,
+                               cudaMemcpyDeviceToHost, ctx->stream));
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));
     return ERP_OK;
 }

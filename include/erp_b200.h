@@ -221,6 +221,17 @@ int erp_rotate_pixels(erp_ctx* ctx, const int32_t* rc, int n, const double* R9, 
 int erp_rotate_keypoints(erp_ctx* ctx, void* xy, size_t stride_bytes, int n, float pitch_rot_inv_deg, int width, int height);
 int erp_rotate_keypoints_dev(erp_ctx* ctx, void* d_xy, size_t stride_bytes, int n, float pitch_rot_inv_deg, int width, int height);
 
+/* epipolar_tool::draw_epipole           src/epipolar_tool.cpp:84-128 (ctor geometry :35-81 included).
+ * left_xy / right_xy: HOST (x, y) float pairs of the n_key <= 7 selected correspondences (stride 28 ==
+ * sizeof(cv::KeyPoint)); E9 in the tool's convention (result = l . (E^T p), |result| < 0.002).
+ * Sequential loop semantics, dots clipped to the image (the reference races and writes out of bounds). */
+int erp_draw_epipole(erp_ctx* ctx, const double* E9, const void* left_xy, const void* right_xy, size_t stride_bytes,
+                     int n_key, int im_width, int im_height, int out_width, int out_height,
+                     uint8_t* out, size_t out_stride_bytes);
+int erp_draw_epipole_dev(erp_ctx* ctx, const double* E9, const void* left_xy, const void* right_xy, size_t stride_bytes,
+                         int n_key, int im_width, int im_height, int out_width, int out_height,
+                         uint8_t* d_out, size_t out_stride_bytes);
+
 /* ---------------------------------------------------------------- reference mode
  * eight_point::initial_guess  src/eight_point.hpp:20-23, .cpp:87-150
  * samples: H x S table (H = 80, S = int(m*0.25) in the reference) or NULL to replay

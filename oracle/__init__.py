@@ -137,6 +137,15 @@ def rotate_keypoints(xy, pitch_inv_deg, W, H):
     return xy
 
 
+def draw_epipole(E, left_xy, right_xy, im_w, im_h, out_w, out_h):
+    """epipolar_tool::draw_epipole for the given (already selected) correspondences."""
+    left_xy, right_xy = _f32(left_xy), _f32(right_xy)
+    out = np.empty((out_h, out_w, 3), np.uint8)
+    lib().orc_draw_epipole(_p(_f64(E).reshape(9)), _p(left_xy), _p(right_xy), 8, left_xy.shape[0], int(im_w), int(im_h),
+                           int(out_w), int(out_h), _p(out))
+    return out
+
+
 def eular2rot(theta):
     R = np.empty(9, np.float64)
     lib().orc_eular2rot(_p(_f64(theta)), _p(R))

@@ -139,6 +139,42 @@ void orc_rotate_keypoints(void* xy, int stride_bytes, int n, float pitch_rot_inv
     }
 }
 
+/* epipolar_tool.cpp:18-24 (BGR) */
+static const uint8_t kEpiColor[7][3] = {{0, 0, 255}, {0, 127, 255}, {0, 255, 255}, {0, 255, 0}, {255, 0, 0}, {135, 0, 75}, {211, 0, 148}};
+
+void orc_draw_epipole(const double* e, const void* left_xy, const void* right_xy, int stride_bytes, int n_key,
+                      int im_w, int im_h, int out_w, int out_h, uint8_t* out)
+{
+    if (n_key > 7) n_key = 7;
+    double l[7][3];
+    int di[7], dj[7];
+    double rw = (double)out_w / (double)im_w, rh = (double)out_h / (double)im_h;       /* :28-29 */
+    for (int k = 0; k < n_key; k++) {
+        const float* lp = (const float*)((const char*)left_xy + (size_t)k * stride_bytes);
+        const float* rp = (const float*)((const char*)right_xy + (size_t)k * stride_bytes);
+        double lon = 2 * M_PI * (lp[0] / im_w), lat = M_PI * (lp[1] / im_h);            /* :38-39 float quotient */
+        l[k][0] = -sin(lat) * cos(lon); l[k][1] = sin(lat) * sin(lon); l[k][2] = cos(lat);
+        di[k] = (int)(rp[1] * rh);                                                      /* :113-114 float * double */
+        dj[k] = (int)(rp[0] * rw);
+    }
+    memset(out, 0, (size_t)out_w * out_h * 3);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < out_h; i++)
+        for (int j = 0; j < out_w; j++) {
+            double lon = 2 * M_PI * ((double)j / out_w), lat = M_PI * ((double)i / out_h);   /* :70-71 */
+            double p[3] = {-sin(lat) * cos(lon), sin(lat) * sin(lon), cos(lat)};
+            uint8_t* o = out + ((size_t)i * out_w + j) * 3;
+            for (int k = 0; k < n_key; k++) {
+                double result = l[k][0] * (p[0] * e[0] + p[1] * e[3] + p[2] * e[6])          /* :103-105 */
+                              + l[k][1] * (p[0] * e[1] + p[1] * e[4] + p[2] * e[7])
+                              + l[k][2] * (p[0] * e[2] + p[1] * e[5] + p[2] * e[8]);
+                if (fabs(result) < 0.002) memcpy(o, kEpiColor[k], 3);
+            }
+            for (int k = 0; k < n_key; k++)                                                  /* :113-123, clipped */
+                if (i >= di[k] - 5 && i <= di[k] + 5 && j >= dj[k] - 5 && j <= dj[k] + 5) memcpy(o, kEpiColor[k], 3);
+        }
+}
+
 /* ------------------------------------------------------------------------- */
 /* matching: src/feature_matcher.cpp:42-59                                   */
 /* ------------------------------------------------------------------------- */

@@ -75,6 +75,12 @@ void orc_rotate_pixels(const int32_t* rc_in, int n, const double* R9, int width,
 void orc_rotate_image(const uint8_t* im, int width, int height, const double* R9, uint8_t* out);
 /* spherical_surf::crop_rotated_image, spherical_surf.cpp:16-48: out is (height/4) x width x 3 */
 void orc_crop_rotated_image(const uint8_t* im, int width, int height, float pitch_rot_deg, uint8_t* out);
+/* epipolar_tool (ctor geometry + draw_epipole), epipolar_tool.cpp:7-128, sequential semantics: per
+ * pixel the LAST key whose |l^T E^T p| < 0.002 colours it, then the 11x11 dots of the right keypoints
+ * are painted in key order (clipped to the image: the reference writes out of bounds).
+ * left_xy/right_xy: (x, y) float pairs of the n_key selected correspondences; out: out_h x out_w x 3 */
+void orc_draw_epipole(const double* E9, const void* left_xy, const void* right_xy, int stride_bytes, int n_key,
+                      int im_w, int im_h, int out_w, int out_h, uint8_t* out);
 /* spherical_surf::rotate_keypoint, spherical_surf.cpp:50-63: xy (x, y) float pairs, in place */
 void orc_rotate_keypoints(void* xy, int stride_bytes, int n, float pitch_rot_inv_deg, int width, int height);
 

@@ -87,3 +87,23 @@ def test_rotate_keypoints(ctx, pitch_inv):
     assert bad.mean() <= (0.25 if pitch_inv in (0.0, 90.0) else 2e-2), bad.mean()     # see test_crop_rotated_image
     d = np.abs(got[bad] - want[bad])
     assert ((d[:, 0] <= 1) | (d[:, 0] >= W - 1)).all() and (d[:, 1] <= 1).all()     # neighbours (longitude wraps)
+
+
+@pytest.mark.parametrize("out_wh", [(640, 360), (1024, 512)])
+def test_draw_epipole(ctx, out_wh):
+    """epipolar_tool::draw_epipole (manual_estimation_test/main.cpp:64,102): E = R^-1 [t]x from a known pose."""
+    from erp_match_eightpoint_test_b200 import synth
+    kp = synth.keypoint_pair(400, 4096, 2048, noise_px=0.2, outlier_frac=0.0, seed=13)
+    E_tool = kp["E"].T                                   # the tool uses the transposed convention (SURVEY D2)
+    sel = [5, 17, 99, 123, 250, 301, 377]
+    l, r = kp["left_xy"][sel], kp["right_xy"][sel]
+    got = ctx.draw_epipole(E_tool, l, r, 4096, 2048, *out_wh)
+    want = O.draw_epipole(E_tool, l, r, 4096, 2048, *out_wh)
+    assert got.shape == want.shape == (out_wh[1], out_wh[0], 3)
+    bad = (got != want).any(-1)
+    assert bad.mean() <= 1e-4, bad.sum()
+    assert (want.sum(-1) > 0).mean() > 0.005             # curves and dots were drawn
+    # the epipolar curve of key k passes through the right keypoint of key k: its dot centre is coloured
+    for k in range(7):
+        i, j = int(r[k, 1] * out_wh[1] / 2048), int(r[k, 0] * out_wh[0] / 4096)
+        assert got[i, j].sum() > 0

@@ -49,7 +49,9 @@ def test_host_classes_build_and_refuse_to_run_without_a_gpu(tmp_path):
     for name in ["feature_matcher::match_two_image(cv::Mat const&, cv::Mat const&)", "feature_matcher::init()",
                  "feature_matcher::detect_key_point(cv::Mat const&)", "feature_matcher::do_all(",
                  "eight_point::find(int, int, std::vector<cv::KeyPoint", "eight_point::eight_point_estimation(int, int,",
-                 "eight_point::initial_guess(int, int,", "random_array::random_array(int)", "erp_rotation::rot2eular(cv::Mat)"]:
+                 "eight_point::initial_guess(int, int,", "random_array::random_array(int)", "erp_rotation::rot2eular(cv::Mat)",
+                 "erp_rotation::rotate_image(cv::Mat const&, cv::Mat&)", "erp_rotation::rotate_pixel(",
+                 "epipolar_tool::epipolar_tool(std::vector<cv::KeyPoint", "epipolar_tool::draw_epipole(cv::Mat&)"]:
         assert name in syms, name
     import torch
     if torch.cuda.is_available():
