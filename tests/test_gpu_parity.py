@@ -400,3 +400,21 @@ def test_cfg4_style_surf128_cross_check(ctx, engine):
     ctx.set_engine(binding.ENGINE_AUTO)
     assert got.tobytes() == O.match(q, t, ratio=-1.0, cross_check=True).tobytes()
     assert got_r.tobytes() == O.match(q, t, ratio=0.3, cross_check=True).tobytes()
+
+
+def test_rotation_grid_known_answer(ctx):
+    """The reference's own test design: a grid of XYZ Euler rotations (one_image_test/main.cpp:73-80 uses
+    {0,5,10,15,20} deg per axis) and the only numeric bar in the repository, mean |Euler error| < 1 deg
+    (two_synthesis_image_test/main.cpp:132-141), on synthetic two-view keypoints through eight_point::find."""
+    worst = 0.0
+    for k, euler in enumerate([(0, 0, 0), (5, 0, 0), (0, 10, 0), (0, 0, 15), (20, 5, 10), (10, 20, 5), (15, 15, 15), (20, 20, 20)]):
+        kp = synth.keypoint_pair(800, 4096, 2048, euler_deg=euler, noise_px=0.3, outlier_frac=0.0, seed=900 + k)
+        R, T = ctx.find(4096, 2048, kp["left_xy"], kp["right_xy"])
+        l, r = O.bearings(kp["left_xy"], 4096, 2048), O.bearings(kp["right_xy"], 4096, 2048)
+        want = O.initial_guess(l, r, O.ref_sample_table(800))
+        assert np.abs(R - want["R"]).max() < POSE_TOL and np.abs(T - want["T"]).max() < POSE_TOL
+        # E = [t]x R^T in synth, so find() returns the Euler vector of R^T (l^T E r = 0 convention)
+        err = np.rad2deg(np.abs(R - O.rot2eular(kp["R"].T))).mean()
+        worst = max(worst, err)
+        assert abs(abs(float(np.dot(T, kp["t"]))) - 1.0) < 5e-3          # translation direction up to sign
+    assert worst < 1.0, worst
