@@ -235,7 +235,7 @@ ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double*
     ERP_ARG(hyp_offset + (uint64_t)H <= 0xFFFFFFFFull, ERP_E_LIMIT, "hypothesis ids must fit 32 bits");
     DeviceGuard g(ctx->device);
     ERP_CUDA(cudaMemsetAsync(d_packed, 0, sizeof(uint64_t), ctx->stream));
-    const int CH = 1 << 18;   // hypotheses per pass: 9.4 MB of Gram + 18.9 MB of E scratch
+    const int CH = 1 << 20;   // hypotheses per pass: 75 MB of E, 2 x 134 MB of split rows (S != 8: 377 MB of Gram)
     int st = ERP_OK;
     int chunk = H < CH ? H : CH;
     double* G = S == 8 ? nullptr : ctx->scratch<double>(S_GRAM, (size_t)chunk * 45, &st);
