@@ -5,7 +5,7 @@ of ``include/erp_b200.h``).  This package is the thin Python face of that ABI us
 tests and ``bench.py``; the C++ drop-in classes live under ``host/``.
 """
 from .binding import (  # noqa: F401
-    DMATCH, ENGINE_AUTO, ENGINE_EXACT_SIMT, ENGINE_TCGEN05, METRIC_ALGEBRAIC, METRIC_ANGULAR,
+    DMATCH, ENGINE_AUTO, ENGINE_EXACT_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_1X, METRIC_ALGEBRAIC, METRIC_ANGULAR,
     METRIC_SAMPSON, POSE_FLOATS, Context, ErpError, LIB_PATH, lib, libstdcxx_sample_table,
 )
 

@@ -133,7 +133,7 @@ ERP_API int erp_ctx_synchronize(erp_ctx* ctx)
 
 ERP_API int erp_ctx_set_engine(erp_ctx* ctx, int engine)
 {
-    ERP_ARG(ctx && engine >= ERP_ENGINE_AUTO && engine <= ERP_ENGINE_TCGEN05, ERP_E_ARG, "erp_ctx_set_engine: bad argument");
+    ERP_ARG(ctx && engine >= ERP_ENGINE_AUTO && engine <= ERP_ENGINE_TCGEN05_1X, ERP_E_ARG, "erp_ctx_set_engine: bad argument");
     ctx->engine = engine;
     return ERP_OK;
 }
@@ -185,7 +185,7 @@ ERP_API int erp_ctx_last_knn_stats(erp_ctx* ctx, int64_t out[5])
 {
     ERP_ARG(ctx && out, ERP_E_ARG, "erp_ctx_last_knn_stats: bad argument");
     memcpy(out, ctx->knn_stats, sizeof ctx->knn_stats);
-    if (ctx->knn_stats[0] == ERP_ENGINE_TCGEN05 && ctx->tc_misc_dev) {
+    if ((ctx->knn_stats[0] == ERP_ENGINE_TCGEN05 || ctx->knn_stats[0] == ERP_ENGINE_TCGEN05_1X) && ctx->tc_misc_dev) {
         // the re-scan count and the observed deviation live on the device
         DeviceGuard g(ctx->device);
         int32_t w[4] = {0, 0, 0, 0};
@@ -219,10 +219,11 @@ ERP_API int erp_knn2_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_
     if (nq == 0) return ERP_OK;
     ERP_ARG(d_q && d_t, ERP_E_ARG, "erp_knn2_dev: null descriptors");
     DeviceGuard g(ctx->device);
-    bool tc = ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_preferred(nq, nt, dim));
-    if (ctx->engine == ERP_ENGINE_TCGEN05)
-        ERP_ARG(knn2_tc_supported(nq, nt, dim), ERP_E_DIM, "tcgen05 engine does not support nq=%d nt=%d dim=%d", nq, nt, dim);
-    if (tc) return knn2_tc(ctx, d_q, nq, d_t, nt, dim, d_idx2, d_dist2, d_d2);
+    const bool forced = ctx->engine == ERP_ENGINE_TCGEN05 || ctx->engine == ERP_ENGINE_TCGEN05_1X;
+    if (forced) ERP_ARG(knn2_tc_supported(nq, nt, dim), ERP_E_DIM, "tcgen05 engine does not support nq=%d nt=%d dim=%d", nq, nt, dim);
+    if (ctx->engine == ERP_ENGINE_TCGEN05) return knn2_tc(ctx, d_q, nq, d_t, nt, dim, d_idx2, d_dist2, d_d2);
+    if (ctx->engine == ERP_ENGINE_TCGEN05_1X || (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_preferred(nq, nt, dim)))
+        return knn2_tc1(ctx, d_q, nq, d_t, nt, dim, d_idx2, d_dist2, d_d2);
     ctx->knn_stats[0] = ERP_ENGINE_EXACT_SIMT; ctx->knn_stats[1] = 0; ctx->knn_stats[2] = 1; ctx->knn_stats[3] = cdiv(nq, 64);
     ctx->knn_stats[4] = 0;
     ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
@@ -258,10 +259,12 @@ ERP_API int erp_nn1_reverse_dev(erp_ctx* ctx, const float* d_q, int nq, const fl
     int32_t* idx2 = ctx->scratch<int32_t>(S_RS_IDX, (size_t)nt * 2, &st);
     double* d2 = ctx->scratch<double>(S_RS_D2, (size_t)nt * 2, &st);
     ERP_TRY(st);
-    bool tc = nq >= 2 && (ctx->engine == ERP_ENGINE_TCGEN05 ? knn2_tc_supported(nt, nq, dim) : (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_preferred(nt, nq, dim)));
+    const bool forced = ctx->engine == ERP_ENGINE_TCGEN05 || ctx->engine == ERP_ENGINE_TCGEN05_1X;
+    bool tc = nq >= 2 && (forced ? knn2_tc_supported(nt, nq, dim) : (ctx->engine == ERP_ENGINE_AUTO && knn2_tc_preferred(nt, nq, dim)));
     if (tc) {
-        ERP_TRY(knn2_tc(ctx, d_t, nt, d_q, nq, dim, idx2, nullptr, d2));
-        // tc path has no index offset: add it while compacting
+        // (the tensor-core paths have no index offset: it is added while compacting)
+        if (ctx->engine == ERP_ENGINE_TCGEN05) ERP_TRY(knn2_tc(ctx, d_t, nt, d_q, nq, dim, idx2, nullptr, d2));
+        else ERP_TRY(knn2_tc1(ctx, d_t, nt, d_q, nq, dim, idx2, nullptr, d2));
     } else {
         ERP_TRY(knn2_exact(ctx, d_t, nt, d_q, nq, dim, nullptr, 0, 0, idx2, nullptr, d2));
     }

@@ -135,6 +135,14 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
             int32_t* d_idx2, float* d_dist2, double* d_d2);
 bool knn2_tc_supported(int nq, int nt, int dim);
 bool knn2_tc_preferred(int nq, int nt, int dim);
+int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+             int32_t* d_idx2, float* d_dist2, double* d_d2);
+int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, int n_lists, int topk, double kappa,
+                  const int32_t* cand, const float* cand_s, const float* cand_thr, unsigned* misc, int32_t* d_idx2, float* d_dist2,
+                  double* d_d2, int32_t* rescan_list);
+int knn2_exact_rescan(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+                      const int32_t* d_list, const int32_t* d_count, int max_rows,
+                      int32_t* d_idx2, float* d_dist2, double* d_d2);
 int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m, float tau,
                   uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best);
 int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,

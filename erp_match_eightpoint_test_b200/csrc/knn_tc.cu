@@ -100,64 +100,12 @@ struct TcParams {
     int units_per_cta;        // L: CTA b owns units [b*L, (b+1)*L) of the n_qtiles x n_ttiles grid (query tile major)
     int n_seg;                // candidate lists per query = n_seg x EPI_GROUPS
     const float* tn;          // n_ttiles * BN norms (+inf padded)
+    const float* qn;          // nq query norms |q|^2
+    const unsigned* tn_max_bits;
+    float* cand_thr;          // nq x lists: lower bound of the approximate score of every non-candidate of the list
     int32_t* cand_idx;        // nq x (n_seg * EPI_GROUPS) x TOPK, pre-set to -1
     float* cand_s;            // same shape: approximate scores, ascending
 };
-
-__device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[TOPK], int (&bi)[TOPK])
-{
-    // strict <: equal scores keep the earlier (lower) train index
-    if (s < bs[2]) {
-        bs[3] = bs[2]; bi[3] = bi[2];
-        if (s < bs[1]) {
-            bs[2] = bs[1]; bi[2] = bi[1];
-            if (s < bs[0]) { bs[1] = bs[0]; bi[1] = bi[0]; bs[0] = s; bi[0] = idx; }
-            else { bs[1] = s; bi[1] = idx; }
-        } else { bs[2] = s; bi[2] = idx; }
-    } else { bs[3] = s; bi[3] = idx; }
-}
-
-// 32 accumulator columns of one query row.  Common case: s = acc + |t|^2 (32 independent adds), a min
-// tree and ONE warp-uniform threshold test.  Rare case (some lane has a column below its 4th best):
-// only the groups of 8 columns that some lane needs are re-read from TMEM in a rolled loop -- the
-// insert cascade exists once per call site, which keeps the loop inside the instruction cache (fully
-// unrolled it was 60 KB and 3x slower).  The re-computed scores are bit-identical to the first pass.
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t taddr, const float4* __restrict__ tn4, int col0,
-                                           float (&bs)[TOPK], int (&bi)[TOPK])
-{
-    float gm[4];
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-        float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
-        float s0 = __fadd_rn(__uint_as_float(v[g * 8 + 0]), na.x), s1 = __fadd_rn(__uint_as_float(v[g * 8 + 1]), na.y);
-        float s2 = __fadd_rn(__uint_as_float(v[g * 8 + 2]), na.z), s3 = __fadd_rn(__uint_as_float(v[g * 8 + 3]), na.w);
-        float s4 = __fadd_rn(__uint_as_float(v[g * 8 + 4]), nb.x), s5 = __fadd_rn(__uint_as_float(v[g * 8 + 5]), nb.y);
-        float s6 = __fadd_rn(__uint_as_float(v[g * 8 + 6]), nb.z), s7 = __fadd_rn(__uint_as_float(v[g * 8 + 7]), nb.w);
-        gm[g] = fminf(fminf(fminf(s0, s1), fminf(s2, s3)), fminf(fminf(s4, s5), fminf(s6, s7)));
-    }
-    const float thr = bs[3];
-    const unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
-    unsigned need = __reduce_or_sync(0xffffffffu, mine);
-    while (need) {                                  // warp-uniform
-        const int g = __ffs(need) - 1;
-        need &= need - 1;
-        uint32_t w[8];
-        tc_ld8(taddr + g * 8, w);
-        tc_wait_ld8(w);
-        const float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
-        if ((mine >> g) & 1u) {
-            float e[8];
-            e[0] = __fadd_rn(__uint_as_float(w[0]), na.x); e[1] = __fadd_rn(__uint_as_float(w[1]), na.y);
-            e[2] = __fadd_rn(__uint_as_float(w[2]), na.z); e[3] = __fadd_rn(__uint_as_float(w[3]), na.w);
-            e[4] = __fadd_rn(__uint_as_float(w[4]), nb.x); e[5] = __fadd_rn(__uint_as_float(w[5]), nb.y);
-            e[6] = __fadd_rn(__uint_as_float(w[6]), nb.z); e[7] = __fadd_rn(__uint_as_float(w[7]), nb.w);
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (e[j] < bs[3]) top4_insert(e[j], col0 + g * 8 + j, bs, bi);
-        }
-        __syncwarp();
-    }
-}
 
 template <int KCH>   // k chunks of 32 floats per half (hi or lo): dpad = 32 * KCH
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -307,6 +255,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             int bi[TOPK];
 #pragma unroll
             for (int j = 0; j < TOPK; j++) { bs[j] = INFINITY; bi[j] = -1; }
+            const int qrow = qtile * BM + row;
+            const float slack = slack_of(qrow < p.nq ? p.qn[qrow] : 0.f, __uint_as_float(*p.tn_max_bits), (float)KAPPA);
             for (int tt = t_begin; tt < t_end; tt++, tile_n++) {
                 const uint32_t acc = tile_n & 1;
                 mbar_wait(&nfull[acc], (tile_n >> 1) & 1);
@@ -323,10 +273,10 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 for (int cc = 0; cc < EPI_COLS / 32; cc += 2) {
                     tc_wait_ld32(va);
                     tc_ld32(taddr + (cc + 1) * 32, vb);
-                    scan_chunk(va, taddr + cc * 32, tn4 + cc * 8, colbase + cc * 32, bs, bi);
+                    scan_chunk(va, taddr + cc * 32, tn4 + cc * 8, colbase + cc * 32, slack, bs, bi);
                     tc_wait_ld32(vb);
                     if (cc + 2 < EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
-                    scan_chunk(vb, taddr + (cc + 1) * 32, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, bs, bi);
+                    scan_chunk(vb, taddr + (cc + 1) * 32, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, slack, bs, bi);
                 }
                 // accumulator drained: hand it back to the MMA warp
                 tc_fence_before();
@@ -338,6 +288,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const size_t o = ((size_t)qg * p.n_seg + seg) * EPI_GROUPS + cg;
                 *reinterpret_cast<int4*>(p.cand_idx + o * TOPK) = make_int4(bi[0], bi[1], bi[2], bi[3]);
                 *reinterpret_cast<float4*>(p.cand_s + o * TOPK) = make_float4(bs[0], bs[1], bs[2], bs[3]);
+                p.cand_thr[o] = fminf(bs[3], __fadd_rn(bs[1], slack));
             }
         }
     }
@@ -358,15 +309,15 @@ __device__ __forceinline__ bool lex_less(double d, int i, double bd, int bi) { r
 
 // one warp per query; lane j owns candidates j and j + 32 (n_groups * TOPK <= 64, n_groups = splits x column groups)
 __global__ void __launch_bounds__(256)
-refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim, int n_groups,
-              const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_s,
+refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim, int n_groups, int topk, double kappa,
+              const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_s, const float* __restrict__ cand_thr,
               unsigned* __restrict__ misc /* [0] re-scan count, [1] max |t|^2 bits, [2] max deviation bits */,
               int32_t* __restrict__ idx2, float* __restrict__ dist2, double* __restrict__ d2out,
               int32_t* __restrict__ rescan_list)
 {
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (qi >= nq) return;
-    const int ncand = n_groups * TOPK;
+    const int ncand = n_groups * topk;
     const float* qr = q + (size_t)qi * dim;
 
     double d[2];
@@ -393,12 +344,12 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
             d[s] = a; id[s] = ti;
         }
     }
-    // certificate inputs: the smallest 4th-best approximate score over the splits, |q|^2, max |t|^2
+    // certificate inputs: the smallest per-list bound (every non-candidate of a list has an approximate
+    // score >= its bound; lists that were never written keep the 0x7f.. fill = "no non-candidates"), |q|^2, max |t|^2
     float thr = INFINITY;
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        int c = lane + 32 * s;
-        if (c < ncand && (c & (TOPK - 1)) == TOPK - 1) thr = fminf(thr, sc[s]);
+    for (int l = lane; l < n_groups; l += 32) {
+        float b = cand_thr[(size_t)qi * n_groups + l];
+        thr = fminf(thr, b > 3.0e38f ? INFINITY : b);
     }
     for (int o = 16; o > 0; o >>= 1) thr = fminf(thr, __shfl_xor_sync(0xffffffffu, thr, o));
     double qn = 0.0;
@@ -431,7 +382,7 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
 
     if (lane == 0) {
         if (dev > 0.f) atomicMax(misc + 2, __float_as_uint(dev));
-        const double eps = KAPPA * scale;
+        const double eps = kappa * scale;
         // non-finite input anywhere (NaN compares false, inf norms) -> exact re-scan
         bool finite_in = scale < (double)INFINITY && scale == scale;
         bool certified = finite_in && I1 != 0x7fffffff &&
@@ -445,6 +396,17 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
             rescan_list[pos] = qi;
         }
     }
+}
+
+// topk must be a power of two, n_lists * topk <= 64
+int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, int n_lists, int topk, double kappa,
+                  const int32_t* cand, const float* cand_s, const float* cand_thr, unsigned* misc, int32_t* d_idx2, float* d_dist2,
+                  double* d_d2, int32_t* rescan_list)
+{
+    refine_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_lists, topk, kappa, cand, cand_s, cand_thr, misc,
+                                                        d_idx2, d_dist2, d_d2, rescan_list);
+    ERP_LAUNCH(ctx, "refine_kernel");
+    return ERP_OK;
 }
 
 bool knn2_tc_supported(int nq, int nt, int dim) { return nq >= 1 && nt >= 2 && dim >= 4 && dim % 4 == 0 && dim <= 128; }
@@ -506,15 +468,18 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     float* qs = ctx->scratch<float>(S_TC_Q, (size_t)nq * 2 * dpad, &st);
     float* ts = ctx->scratch<float>(S_TC_T, (size_t)nt * 2 * dpad, &st);
     float* tn = ctx->scratch<float>(S_TC_TN, (size_t)n_ttiles * BN, &st);
-    int32_t* cand = ctx->scratch<int32_t>(S_TC_CAND, (size_t)nq * n_lists * TOPK * 2, &st);
+    int32_t* cand = ctx->scratch<int32_t>(S_TC_CAND, (size_t)nq * n_lists * (TOPK * 2 + 1), &st);
+    float* qn = ctx->scratch<float>(S_TC_QN, (size_t)nq + 8, &st);
     int32_t* list = ctx->scratch<int32_t>(S_TC_LIST, (size_t)nq + 8, &st);
     int32_t* misc = ctx->scratch<int32_t>(S_TC_MISC, 8, &st);     // [0] re-scan count, [1] max |t|^2 bits, [2] max deviation bits
     ERP_TRY(st);
     float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_lists * TOPK);
+    float* cand_thr = cand_s + (size_t)nq * n_lists * TOPK;
+    ERP_CUDA(cudaMemsetAsync(cand_thr, 0x7f, (size_t)nq * n_lists * sizeof(float), ctx->stream));              // ~3.4e38: "unbounded"
     ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
     ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * TOPK * sizeof(int32_t), ctx->stream));   // index -1: empty slot
 
-    split_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, dim, dpad, -2.0f, qs, nullptr, nq, nullptr);
+    split_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3));
     ERP_LAUNCH(ctx, "split_kernel(q)");
     split_kernel<<<cdiv(n_ttiles * BN, 8), 256, 0, ctx->stream>>>(d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * BN,
                                                                  reinterpret_cast<unsigned*>(misc + 1));
@@ -525,7 +490,8 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     ERP_TRY(make_map(&mt, ts, nt, 2 * dpad, BN));
     TcParams p;
     p.nq = nq; p.nt = nt; p.n_qtiles = n_qtiles; p.n_ttiles = n_ttiles; p.units_per_cta = upc; p.n_seg = n_seg;
-    p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s;
+    p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s; p.cand_thr = cand_thr; p.qn = qn;
+    p.tn_max_bits = reinterpret_cast<const unsigned*>(misc + 1);
 
     ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
     switch (kch) {
@@ -536,9 +502,8 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     }
     ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
 
-    refine_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_lists, cand, cand_s,
-                                                        reinterpret_cast<unsigned*>(misc), d_idx2, d_dist2, d_d2, list);
-    ERP_LAUNCH(ctx, "refine_kernel");
+    ERP_TRY(refine_launch(ctx, d_q, nq, d_t, nt, dim, n_lists, TOPK, KAPPA, cand, cand_s, cand_thr, reinterpret_cast<unsigned*>(misc),
+                          d_idx2, d_dist2, d_d2, list));
     ERP_TRY(knn2_exact_rescan(ctx, d_q, nq, d_t, nt, dim, list, misc, nq, d_idx2, d_dist2, d_d2));
 
     ctx->knn_stats[0] = ERP_ENGINE_TCGEN05;

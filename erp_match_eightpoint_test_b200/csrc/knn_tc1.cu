@@ -1,0 +1,358 @@
+// knn_tc1.cu -- the fast tcgen05 distance engine: ONE TF32 product per tile, a wider candidate list
+// and the same exact certificate.
+//
+// knn_tc.cu reproduces fp32 ranking by arithmetic (3xTF32).  The certificate of refine_kernel makes
+// that unnecessary: any approximate score with a known error bound yields the exact 2-NN as long as
+//     d2_exact(second) < min_lists(s_kth) + |q|^2 - eps        (otherwise the query is re-scanned)
+// holds, and a single TF32 product has a worst-case error of 2^-11 (|q|^2 + |t|^2) (inputs rounded
+// to 11 significant bits, products exact, fp32 accumulation).  The gap between the second and the
+// fourth neighbour absorbs that error for SURF-like data (the re-scan list stays short), so the
+// kernel issues a third of the tensor work:
+//     8 UMMA instructions per 128 x 256 tile instead of 24.
+// At that rate the L2 -> shared-memory feed becomes the limiter, so every 64 KB train tile that TMA
+// brings in is multiplied against TWO resident query tiles (256 queries), alternating between the
+// two TMEM accumulators.  Results are identical to the exact engine by construction.
+#include "tc_common.cuh"
+
+namespace erp {
+
+constexpr int F_BM = 128;                 // queries per sub-tile (UMMA M)
+constexpr int F_SUB_MAX = 2;              // resident query sub-tiles sharing every train tile (1 when D > 96: smem)
+constexpr int F_BN = 256;                 // train rows per tile (UMMA N)
+constexpr int F_KC = 32;                  // floats per k chunk (one 128-byte swizzle row)
+constexpr int F_QCH = F_BM * F_KC * 4;    // 16 KB
+constexpr int F_TCH = F_BN * F_KC * 4;    // 32 KB
+constexpr int F_EPI_GROUPS = 2;
+constexpr int F_EPI_THREADS = F_EPI_GROUPS * 128;
+constexpr int F_THREADS = 128 + F_EPI_THREADS;
+constexpr int F_EPI_COLS = F_BN / F_EPI_GROUPS;
+constexpr int F_TOPK = 4;
+constexpr int F_MAX_SEG = 64 / (F_TOPK * F_EPI_GROUPS);     // 8 segments per query pair
+constexpr int F_TAIL = 2 * F_BN * 4 + 256;                  // |t|^2 of two train tiles + mbarriers
+// |s_tc - s_exact| <= 2^-11 (|q|^2 + max|t|^2) in the worst case; 2^-10 leaves a factor 2 and
+// refine_kernel reports the deviation it observes (1e-4 of that on the synthetic sets)
+constexpr double F_KAPPA = 1.0 / 1024.0;
+constexpr uint32_t F_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F_BN >> 3) << 17) | ((uint32_t)(F_BM >> 4) << 24);
+
+__host__ __device__ constexpr int f_sub(int kch) { return kch <= 3 ? F_SUB_MAX : 1; }
+__host__ __device__ constexpr int f_slots(int kch) { return (TC_SMEM_LIMIT - f_sub(kch) * kch * F_QCH - F_TAIL) / F_TCH; }
+
+// rows -> tf32-rounded rows (dpad floats), optional norms (+inf padding) and their maximum
+__global__ void __launch_bounds__(256)
+round_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
+             float* __restrict__ out, float* __restrict__ norm, int n_pad, unsigned* __restrict__ max_bits)
+{
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    if (row >= n) {
+        if (norm && lane == 0) norm[row] = INFINITY;
+        return;
+    }
+    double acc = 0.0;
+    for (int k = lane * 4; k < dpad; k += 128) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < dim) v = *reinterpret_cast<const float4*>(x + (size_t)row * dim + k);
+        acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        float4 hi = make_float4(tf32_rna(__fmul_rn(v.x, scale)), tf32_rna(__fmul_rn(v.y, scale)),
+                                tf32_rna(__fmul_rn(v.z, scale)), tf32_rna(__fmul_rn(v.w, scale)));
+        *reinterpret_cast<float4*>(out + (size_t)row * dpad + k) = hi;
+    }
+    if (norm) {
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            float f = (float)acc;
+            norm[row] = f;
+            atomicMax(max_bits, __float_as_uint(f));
+        }
+    }
+}
+
+struct Tc1Params {
+    int nq, nt;
+    int n_qpairs, n_ttiles;   // n_qpairs counts groups of f_sub(kch) query sub-tiles
+    int units_per_cta;        // CTA b owns units [b*L, (b+1)*L) of the n_qpairs x n_ttiles grid
+    int n_seg;                // candidate lists per query = n_seg x F_EPI_GROUPS
+    const float* tn;
+    const float* qn;          // nq query norms |q|^2
+    const unsigned* tn_max_bits;
+    int32_t* cand_idx;        // nq x lists x F_TOPK, pre-set to -1
+    float* cand_s;
+    float* cand_thr;          // nq x lists: lower bound of the approximate score of every non-candidate
+};
+
+template <int KCH>   // k chunks of 32 floats: dpad = 32 * KCH
+__global__ void __launch_bounds__(F_THREADS, 1)
+knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const Tc1Params p)
+{
+    constexpr int NS = f_slots(KCH), F_SUB = f_sub(KCH);
+    static_assert(NS >= KCH + 1, "T ring must hold one tile plus a chunk of look-ahead");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* q_smem = smem;                                   // [F_SUB][KCH] chunks
+    uint8_t* t_smem = smem + F_SUB * KCH * F_QCH;             // NS slots
+    float* tn_smem = reinterpret_cast<float*>(t_smem + NS * F_TCH);   // [2][F_BN], by train-tile parity
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tn_smem + 2 * F_BN);
+    uint64_t* full = bars;              // [NS]  TMA -> MMA
+    uint64_t* empty = bars + NS;        // [NS]  MMA -> TMA
+    uint64_t* qfull = bars + 2 * NS;    // query pair landed
+    uint64_t* qempty = qfull + 1;       // query pair no longer read
+    uint64_t* tfull = qfull + 2;        // [2] accumulator ready
+    uint64_t* tempty = qfull + 4;       // [2] accumulator drained
+    uint64_t* nfull = qfull + 6;        // [2] |t|^2 of a train tile landed
+    uint64_t* nempty = qfull + 8;       // [2] ... and consumed by both sub-tiles
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_ALLOC = F_EPI_THREADS / 32, W_NORM = W_ALLOC + 1, W_TMA = W_ALLOC + 2, W_MMA = W_ALLOC + 3;
+
+    if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_t); }
+    if (warp == W_MMA && lane == 0) {
+        for (int i = 0; i < NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(qfull, 1); mbar_init(qempty, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&tfull[i], 1); mbar_init(&tempty[i], F_EPI_THREADS / 32);
+            mbar_init(&nfull[i], 1); mbar_init(&nempty[i], F_EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_ALLOC) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == W_TMA) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, seg_n = 0;
+            SegIter it(p.n_qpairs, p.n_ttiles, p.units_per_cta, blockIdx.x);
+            int qp, t0, t1, seg;
+            for (; it.next(qp, t0, t1, seg); seg_n++) {
+                mbar_wait(qempty, (seg_n & 1) ^ 1);
+                mbar_expect_tx(qfull, F_SUB * KCH * F_QCH);
+#pragma unroll
+                for (int sub = 0; sub < F_SUB; sub++)
+#pragma unroll
+                    for (int c = 0; c < KCH; c++)
+                        tma_load_2d(&map_q, qfull, q_smem + (sub * KCH + c) * F_QCH, c * F_KC, (qp * F_SUB + sub) * F_BM);
+                for (int tt = t0; tt < t1; tt++) {
+#pragma unroll
+                    for (int c = 0; c < KCH; c++) {
+                        mbar_wait(&empty[slot], ph ^ 1);
+                        mbar_expect_tx(&full[slot], F_TCH);
+                        tma_load_2d(&map_t, &full[slot], t_smem + slot * F_TCH, c * F_KC, tt * F_BN);
+                        if (++slot == NS) { slot = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, seg_n = 0, tile_n = 0;
+            const uint32_t q_base = smem_u32(q_smem), t_base = smem_u32(t_smem);
+            SegIter it(p.n_qpairs, p.n_ttiles, p.units_per_cta, blockIdx.x);
+            int qp, t0, t1, seg;
+            for (; it.next(qp, t0, t1, seg); seg_n++) {
+                mbar_wait(qfull, seg_n & 1);
+                for (int tt = t0; tt < t1; tt++) {
+                    // the KCH chunks of this train tile occupy KCH consecutive ring slots
+                    uint32_t s0 = slot, p0 = ph;
+#pragma unroll
+                    for (int sub = 0; sub < F_SUB; sub++, tile_n++) {
+                        const uint32_t acc = tile_n & 1;
+                        mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
+                        const uint32_t d_tmem = tmem_base + acc * F_BN;
+                        uint32_t sl = s0, pp = p0;
+#pragma unroll
+                        for (int c = 0; c < KCH; c++) {
+                            if (sub == 0) mbar_wait(&full[sl], pp);
+                            tc_fence_after();
+                            const uint32_t a = q_base + (sub * KCH + c) * F_QCH, b = t_base + sl * F_TCH;
+#pragma unroll
+                            for (int k = 0; k < F_KC / 8; k++)
+                                tc_mma_tf32(d_tmem, smem_desc_sw128(a + k * 32), smem_desc_sw128(b + k * 32), F_IDESC, (c | k) != 0);
+                            if (sub == F_SUB - 1) tc_commit(&empty[sl]);
+                            if (++sl == NS) { sl = 0; pp ^= 1; }
+                        }
+                        tc_commit(&tfull[acc]);
+                        if (sub == F_SUB - 1) { slot = sl; ph = pp; }
+                    }
+                }
+                tc_commit(qempty);
+            }
+        }
+    } else if (warp == W_NORM) {
+        // ================================================================ |t|^2 producer (one bulk copy per train tile)
+        if (lane == 0) {
+            uint32_t tt_n = 0;
+            SegIter it(p.n_qpairs, p.n_ttiles, p.units_per_cta, blockIdx.x);
+            int qp, t0, t1, seg;
+            while (it.next(qp, t0, t1, seg)) {
+                for (int tt = t0; tt < t1; tt++, tt_n++) {
+                    const uint32_t nb = tt_n & 1;
+                    mbar_wait(&nempty[nb], ((tt_n >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&nfull[nb], F_BN * 4);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(tn_smem + nb * F_BN)), "l"(p.tn + (size_t)tt * F_BN), "r"(F_BN * 4), "r"(smem_u32(&nfull[nb]))
+                                 : "memory");
+                }
+            }
+        }
+    } else if (warp < W_ALLOC) {
+        // ================================================================ epilogue (2 column groups x 4 lane quarters)
+        const int ew = warp & 3, cg = warp >> 2;
+        const int row = ew * 32 + lane;
+        uint32_t tile_n = 0, tt_n = 0;
+        SegIter it(p.n_qpairs, p.n_ttiles, p.units_per_cta, blockIdx.x);
+        int qp, t0, t1, seg;
+        while (it.next(qp, t0, t1, seg)) {
+            float bs[F_SUB][F_TOPK];
+            int bi[F_SUB][F_TOPK];
+#pragma unroll
+            for (int sub = 0; sub < F_SUB; sub++)
+#pragma unroll
+                for (int j = 0; j < F_TOPK; j++) { bs[sub][j] = INFINITY; bi[sub][j] = -1; }
+            float slack[F_SUB];
+#pragma unroll
+            for (int sub = 0; sub < F_SUB; sub++) {
+                const int qrow = (qp * F_SUB + sub) * F_BM + row;
+                slack[sub] = slack_of(qrow < p.nq ? p.qn[qrow] : 0.f, __uint_as_float(*p.tn_max_bits), (float)F_KAPPA);
+            }
+            for (int tt = t0; tt < t1; tt++, tt_n++) {
+                const uint32_t nb = tt_n & 1;
+                mbar_wait(&nfull[nb], (tt_n >> 1) & 1);
+                const float4* tn4 = reinterpret_cast<const float4*>(tn_smem + nb * F_BN + cg * F_EPI_COLS);
+                const int colbase = tt * F_BN + cg * F_EPI_COLS;
+#pragma unroll
+                for (int sub = 0; sub < F_SUB; sub++, tile_n++) {
+                    const uint32_t acc = tile_n & 1;
+                    mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * F_BN + cg * F_EPI_COLS;
+                    uint32_t va[32], vb[32];
+                    tc_ld32(taddr, va);
+#pragma unroll 1
+                    for (int cc = 0; cc < F_EPI_COLS / 32; cc += 2) {
+                        tc_wait_ld32(va);
+                        tc_ld32(taddr + (cc + 1) * 32, vb);
+                        scan_chunk(va, taddr + cc * 32, tn4 + cc * 8, colbase + cc * 32, slack[sub], bs[sub], bi[sub]);
+                        tc_wait_ld32(vb);
+                        if (cc + 2 < F_EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
+                        scan_chunk(vb, taddr + (cc + 1) * 32, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, slack[sub], bs[sub], bi[sub]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&nempty[nb]);
+            }
+#pragma unroll
+            for (int sub = 0; sub < F_SUB; sub++) {
+                const int qg = (qp * F_SUB + sub) * F_BM + row;
+                if (qg < p.nq) {
+                    const size_t l = ((size_t)qg * p.n_seg + seg) * F_EPI_GROUPS + cg;
+                    *reinterpret_cast<int4*>(p.cand_idx + l * F_TOPK) = make_int4(bi[sub][0], bi[sub][1], bi[sub][2], bi[sub][3]);
+                    *reinterpret_cast<float4*>(p.cand_s + l * F_TOPK) = make_float4(bs[sub][0], bs[sub][1], bs[sub][2], bs[sub][3]);
+                    p.cand_thr[l] = fminf(bs[sub][3], __fadd_rn(bs[sub][1], slack[sub]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ALLOC) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <int KCH>
+static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt, const Tc1Params& p, int grid)
+{
+    constexpr int smem = f_sub(KCH) * KCH * F_QCH + f_slots(KCH) * F_TCH + F_TAIL;
+    static_assert(smem <= TC_SMEM_LIMIT, "shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        ERP_CUDA(cudaFuncSetAttribute(knn2_tc1_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    knn2_tc1_kernel<KCH><<<grid, F_THREADS, smem, ctx->stream>>>(mq, mt, p);
+    ERP_LAUNCH(ctx, "knn2_tc1_kernel");
+    return ERP_OK;
+}
+
+int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
+             int32_t* d_idx2, float* d_dist2, double* d_d2)
+{
+    if (!knn2_tc_supported(nq, nt, dim)) { set_error("tcgen05 engine: unsupported shape nq=%d nt=%d dim=%d", nq, nt, dim); return ERP_E_DIM; }
+    const int kch = (dim + F_KC - 1) / F_KC, dpad = kch * F_KC;
+    const int n_qpairs = cdiv(nq, F_BM * f_sub(kch)), n_ttiles = cdiv(nt, F_BN);
+    // stream-K plan: equal contiguous unit ranges, a query pair cut in at most F_MAX_SEG segments
+    long total = (long)n_qpairs * n_ttiles;
+    long L = (total + ctx->sm_count - 1) / ctx->sm_count;
+    long lmin = (n_ttiles + (F_MAX_SEG - 2) - 1) / (F_MAX_SEG - 2);
+    if (L < lmin) L = lmin;
+    if (L < 1) L = 1;
+    const int grid = (int)((total + L - 1) / L);
+    long segs = (n_ttiles + L - 1) / L + 1;
+    const int n_seg = (int)(segs > F_MAX_SEG ? F_MAX_SEG : segs);
+    const int n_lists = n_seg * F_EPI_GROUPS;
+
+    int st = ERP_OK;
+    float* qs = ctx->scratch<float>(S_TC_Q, (size_t)nq * dpad, &st);
+    float* ts = ctx->scratch<float>(S_TC_T, (size_t)nt * dpad, &st);
+    float* tn = ctx->scratch<float>(S_TC_TN, (size_t)n_ttiles * F_BN, &st);
+    int32_t* cand = ctx->scratch<int32_t>(S_TC_CAND, (size_t)nq * n_lists * (F_TOPK * 2 + 1), &st);
+    float* qn = ctx->scratch<float>(S_TC_QN, (size_t)nq + 8, &st);
+    int32_t* list = ctx->scratch<int32_t>(S_TC_LIST, (size_t)nq + 8, &st);
+    int32_t* misc = ctx->scratch<int32_t>(S_TC_MISC, 8, &st);
+    ERP_TRY(st);
+    float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_lists * F_TOPK);
+    float* cand_thr = cand_s + (size_t)nq * n_lists * F_TOPK;
+    ERP_CUDA(cudaMemsetAsync(cand_thr, 0x7f, (size_t)nq * n_lists * sizeof(float), ctx->stream));              // ~3.4e38: "unbounded"
+    ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
+    ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * F_TOPK * sizeof(int32_t), ctx->stream));
+
+    round_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3));
+    ERP_LAUNCH(ctx, "round_kernel(q)");
+    round_kernel<<<cdiv(n_ttiles * F_BN, 8), 256, 0, ctx->stream>>>(d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * F_BN,
+                                                                  reinterpret_cast<unsigned*>(misc + 1));
+    ERP_LAUNCH(ctx, "round_kernel(t)");
+
+    CUtensorMap mq, mt;
+    ERP_TRY(make_map(&mq, qs, nq, dpad, F_BM));
+    ERP_TRY(make_map(&mt, ts, nt, dpad, F_BN));
+    Tc1Params p;
+    p.nq = nq; p.nt = nt; p.n_qpairs = n_qpairs; p.n_ttiles = n_ttiles; p.units_per_cta = (int)L; p.n_seg = n_seg;
+    p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s; p.cand_thr = cand_thr; p.qn = qn;
+    p.tn_max_bits = reinterpret_cast<const unsigned*>(misc + 1);
+
+    ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    switch (kch) {
+    case 1: ERP_TRY(launch_tc1<1>(ctx, mq, mt, p, grid)); break;
+    case 2: ERP_TRY(launch_tc1<2>(ctx, mq, mt, p, grid)); break;
+    case 3: ERP_TRY(launch_tc1<3>(ctx, mq, mt, p, grid)); break;
+    default: ERP_TRY(launch_tc1<4>(ctx, mq, mt, p, grid)); break;
+    }
+    ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+
+    ERP_TRY(refine_launch(ctx, d_q, nq, d_t, nt, dim, n_lists, F_TOPK, F_KAPPA, cand, cand_s, cand_thr, reinterpret_cast<unsigned*>(misc),
+                          d_idx2, d_dist2, d_d2, list));
+    ERP_TRY(knn2_exact_rescan(ctx, d_q, nq, d_t, nt, dim, list, misc, nq, d_idx2, d_dist2, d_d2));
+
+    ctx->knn_stats[0] = ERP_ENGINE_TCGEN05_1X;
+    ctx->knn_stats[1] = -1;
+    ctx->knn_stats[2] = n_seg;
+    ctx->knn_stats[3] = (int)L;
+    ctx->knn_stats[4] = grid;
+    ctx->tc_misc_dev = misc;
+    return ERP_OK;
+}
+
+} // namespace erp

@@ -251,7 +251,8 @@ ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double*
             ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
         }
         if (metric == ERP_METRIC_ALGEBRAIC &&
-            (ctx->engine == ERP_ENGINE_TCGEN05 || (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m))))
+            (ctx->engine == ERP_ENGINE_TCGEN05 || ctx->engine == ERP_ENGINE_TCGEN05_1X ||
+             (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m))))
             ERP_TRY(score_tc_best(ctx, E, n, d_l4, d_r4, m, tau, hyp_offset + h0, counts, d_packed));
         else {
             cudaEvent_t e0, e1;

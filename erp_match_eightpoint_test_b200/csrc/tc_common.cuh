@@ -181,6 +181,78 @@ inline int make_map(CUtensorMap* map, const float* base, int rows, int row_float
     return ERP_OK;
 }
 
+
+// ---- running top-4 of one query row, shared by the two distance kernels -----------------------
+// A column is a candidate iff its approximate score is below
+//     min( 4th best so far,  2nd best so far + slack ),      slack = 2 * kappa * (|q|^2 + max|t|^2).
+// Columns above "2nd best + 2 eps" can never be one of the exact two nearest neighbours (their exact
+// distance exceeds the exact distance of the approximate runner-up), so they need not be kept: the
+// rare insert path then runs ~2 ln(n) times per row instead of 4 ln(n) or 8 ln(n), and the list's
+// certificate bound is that same minimum (both terms only decrease while the scan proceeds).
+__device__ __forceinline__ float slack_of(float qn, float tn_max, float kappa)
+{
+    return __fmul_rn(__fmul_rn(2.0002f * kappa, __fadd_rn(qn, tn_max)), 1.0f);
+}
+__device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[4], int (&bi)[4])
+{
+    // strict <: equal scores keep the earlier (lower) train index
+    if (s < bs[2]) {
+        bs[3] = bs[2]; bi[3] = bi[2];
+        if (s < bs[1]) {
+            bs[2] = bs[1]; bi[2] = bi[1];
+            if (s < bs[0]) { bs[1] = bs[0]; bi[1] = bi[0]; bs[0] = s; bi[0] = idx; }
+            else { bs[1] = s; bi[1] = idx; }
+        } else { bs[2] = s; bi[2] = idx; }
+    } else { bs[3] = s; bi[3] = idx; }
+}
+
+// 32 accumulator columns of one query row.  Common case: s = acc + |t|^2 (32 independent adds), a min
+// tree and ONE warp-uniform threshold test.  Rare case: only the groups of 8 columns that some lane
+// needs are re-read from TMEM in a rolled loop, and only the columns below the threshold are visited
+// -- the insert cascade exists once per call site, which keeps the loop inside the instruction cache
+// (fully unrolled it was 60 KB and 3x slower).  Re-computed scores are bit-identical to the first pass.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t taddr, const float4* __restrict__ tn4, int col0,
+                                           float slack, float (&bs)[4], int (&bi)[4])
+{
+    float gm[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
+        float s0 = __fadd_rn(__uint_as_float(v[g * 8 + 0]), na.x), s1 = __fadd_rn(__uint_as_float(v[g * 8 + 1]), na.y);
+        float s2 = __fadd_rn(__uint_as_float(v[g * 8 + 2]), na.z), s3 = __fadd_rn(__uint_as_float(v[g * 8 + 3]), na.w);
+        float s4 = __fadd_rn(__uint_as_float(v[g * 8 + 4]), nb.x), s5 = __fadd_rn(__uint_as_float(v[g * 8 + 5]), nb.y);
+        float s6 = __fadd_rn(__uint_as_float(v[g * 8 + 6]), nb.z), s7 = __fadd_rn(__uint_as_float(v[g * 8 + 7]), nb.w);
+        gm[g] = fminf(fminf(fminf(s0, s1), fminf(s2, s3)), fminf(fminf(s4, s5), fminf(s6, s7)));
+    }
+    const float thr = fminf(bs[3], __fadd_rn(bs[1], slack));
+    const unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
+    unsigned need = __reduce_or_sync(0xffffffffu, mine);
+    while (need) {                                  // warp-uniform
+        const int g = __ffs(need) - 1;
+        need &= need - 1;
+        uint32_t w[8];
+        tc_ld8(taddr + g * 8, w);
+        tc_wait_ld8(w);
+        const float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
+        if ((mine >> g) & 1u) {
+            float e[8];
+            e[0] = __fadd_rn(__uint_as_float(w[0]), na.x); e[1] = __fadd_rn(__uint_as_float(w[1]), na.y);
+            e[2] = __fadd_rn(__uint_as_float(w[2]), na.z); e[3] = __fadd_rn(__uint_as_float(w[3]), na.w);
+            e[4] = __fadd_rn(__uint_as_float(w[4]), nb.x); e[5] = __fadd_rn(__uint_as_float(w[5]), nb.y);
+            e[6] = __fadd_rn(__uint_as_float(w[6]), nb.z); e[7] = __fadd_rn(__uint_as_float(w[7]), nb.w);
+            unsigned m = (e[0] < thr ? 1u : 0u) | (e[1] < thr ? 2u : 0u) | (e[2] < thr ? 4u : 0u) | (e[3] < thr ? 8u : 0u) |
+                         (e[4] < thr ? 16u : 0u) | (e[5] < thr ? 32u : 0u) | (e[6] < thr ? 64u : 0u) | (e[7] < thr ? 128u : 0u);
+            while (m) {                             // usually a single column
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const float x = j == 0 ? e[0] : j == 1 ? e[1] : j == 2 ? e[2] : j == 3 ? e[3] : j == 4 ? e[4] : j == 5 ? e[5] : j == 6 ? e[6] : e[7];
+                if (x < fminf(bs[3], __fadd_rn(bs[1], slack))) top4_insert(x, col0 + g * 8 + j, bs, bi);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // A CTA's unit range cut into segments: consecutive train tiles of one query tile.
 struct SegIter {
     long u, end;

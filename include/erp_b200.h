@@ -60,9 +60,10 @@ typedef enum {
 
 /* which distance engine erp_knn2* uses */
 typedef enum {
-    ERP_ENGINE_AUTO = 0,       /* tcgen05 when the shape allows, else exact SIMT */
+    ERP_ENGINE_AUTO = 0,       /* the fastest exact engine for the shape: TCGEN05_1X for large problems, else SIMT */
     ERP_ENGINE_EXACT_SIMT = 1, /* fp64 direct-form brute force (also the rescan path)            */
-    ERP_ENGINE_TCGEN05 = 2     /* 3xTF32 GEMM-form tiles + fused top-k, exact fp64 refine         */
+    ERP_ENGINE_TCGEN05 = 2,    /* 3xTF32 GEMM-form tiles + fused top-4, exact fp64 refine + certificate  */
+    ERP_ENGINE_TCGEN05_1X = 3  /* one TF32 product, top-8, same certificate: a third of the tensor work */
 } erp_engine;
 
 /* pose record per hypothesis: XYZ-euler of R1, of R2 (rad), t, validity flags (1.0/0.0), 1 pad */

@@ -1,4 +1,4 @@
-"""One tcgen05-engine call on synthetic descriptors (the ncu target).  usage: tc_profile.py NQ NT DIM [REPS]"""
+"""One tcgen05-engine call on synthetic descriptors (the ncu target).  usage: tc_profile.py NQ NT DIM [REPS] [ENGINE 2=3xTF32 | 3=1xTF32]"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -7,8 +7,9 @@ from erp_match_eightpoint_test_b200 import binding, synth
 
 nq, nt, dim = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+engine = int(sys.argv[5]) if len(sys.argv) > 5 else binding.ENGINE_TCGEN05_1X
 ctx = erp.Context(0)
-ctx.set_engine(binding.ENGINE_TCGEN05)
+ctx.set_engine(engine)
 q, t, _ = synth.descriptor_pair(nq, nt, dim, seed=11)
 for _ in range(reps):
     idx, dist = ctx.knn2_raw(q, t)

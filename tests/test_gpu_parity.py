@@ -35,7 +35,7 @@ def scene():
 
 
 def engines():
-    return [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_AUTO]
+    return [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X, binding.ENGINE_AUTO]
 
 
 # ------------------------------------------------------------------ matching
@@ -82,27 +82,29 @@ def test_match_two_image_records(ctx, engine, ratio, cross):
     ctx.set_engine(binding.ENGINE_AUTO)
 
 
+@pytest.mark.parametrize("tc_engine,kappa", [(binding.ENGINE_TCGEN05, 2.0 ** -14), (binding.ENGINE_TCGEN05_1X, 2.0 ** -10)])
 @pytest.mark.parametrize("nq,nt,dim", [(5000, 7000, 64), (3000, 4000, 128), (2000, 2500, 32), (1500, 1500, 96),
-                                        (700, 900, 100), (129, 257, 64), (128, 256, 64), (4000, 300, 64)])
-def test_tcgen05_engine_certifies_and_matches_exact(ctx, nq, nt, dim):
+                                        (700, 900, 100), (129, 257, 64), (128, 256, 64), (4000, 300, 64), (257, 5000, 64)])
+def test_tcgen05_engine_certifies_and_matches_exact(ctx, nq, nt, dim, tc_engine, kappa):
     """The tensor-core engine must (1) return exactly what the fp64 SIMT engine returns, (2) certify
     nearly every query itself (a broken tile layout would push everything through the re-scan and
     still pass (1)), (3) stay far inside the certificate's error budget KAPPA = 2^-14."""
     q, t, _ = synth.descriptor_pair(nq, nt, dim, seed=3 * nq + nt)
     ctx.set_engine(binding.ENGINE_EXACT_SIMT)
     eidx, edist = ctx.knn2_raw(q, t)
-    ctx.set_engine(binding.ENGINE_TCGEN05)
+    ctx.set_engine(tc_engine)
     idx, dist = ctx.knn2_raw(q, t)
     st = ctx.last_knn_stats()
     ctx.set_engine(binding.ENGINE_AUTO)
-    assert st["engine"] == binding.ENGINE_TCGEN05
+    assert st["engine"] == tc_engine
     assert np.array_equal(idx, eidx)
     assert np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
     assert st["rescanned"] <= max(2, nq // 100), st
-    assert 0 < st["deviation"] < 2.0 ** -14 / 4, st
+    assert 0 < st["deviation"] < kappa / 2, st
 
 
-def test_tcgen05_engine_adversarial_inputs(ctx):
+@pytest.mark.parametrize("tc_engine", [binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X])
+def test_tcgen05_engine_adversarial_inputs(ctx, tc_engine):
     """Duplicated rows (more duplicates than the candidate list holds), un-normalised and widely
     scaled descriptors, zero rows: everything the certificate cannot prove must be re-scanned."""
     rng = np.random.default_rng(5)
@@ -115,7 +117,7 @@ def test_tcgen05_engine_adversarial_inputs(ctx):
     t[51] = 0
     ctx.set_engine(binding.ENGINE_EXACT_SIMT)
     eidx, edist = ctx.knn2_raw(q, t)
-    ctx.set_engine(binding.ENGINE_TCGEN05)
+    ctx.set_engine(tc_engine)
     idx, dist = ctx.knn2_raw(q, t)
     ctx.set_engine(binding.ENGINE_AUTO)
     assert np.array_equal(idx, eidx)
@@ -363,15 +365,16 @@ def test_cfg3_full_size_tensor_core_equals_exact_engine(ctx):
     of them itself, and the 1M-hypothesis RANSAC must find the planted geometry; a 1/64 sub-sample of
     the queries is also checked against the CPU oracle."""
     q, t, planted = synth.descriptor_pair(100000, 100000, 64, seed=synth.SEED_BASE + 3)
-    ctx.set_engine(binding.ENGINE_TCGEN05)
-    idx, dist = ctx.knn2_raw(q, t)
-    st = ctx.last_knn_stats()
-    m = ctx.knn2_match(q, t, ratio=0.3)
     ctx.set_engine(binding.ENGINE_EXACT_SIMT)
     eidx, edist = ctx.knn2_raw(q, t)
+    for eng, kappa in ((binding.ENGINE_TCGEN05, 2.0 ** -14), (binding.ENGINE_TCGEN05_1X, 2.0 ** -10)):
+        ctx.set_engine(eng)
+        idx, dist = ctx.knn2_raw(q, t)
+        st = ctx.last_knn_stats()
+        m = ctx.knn2_match(q, t, ratio=0.3)
+        assert np.array_equal(idx, eidx) and np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
+        assert st["rescanned"] <= 100 and st["deviation"] < kappa / 2, st
     ctx.set_engine(binding.ENGINE_AUTO)
-    assert np.array_equal(idx, eidx) and np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
-    assert st["rescanned"] <= 100 and st["deviation"] < 2.0 ** -14 / 4
     assert len(m) == (planted >= 0).sum() and (planted[m["queryIdx"]] == m["trainIdx"]).all()
     assert (np.diff(m["queryIdx"]) > 0).all()
     sub = np.arange(0, 100000, 64)
@@ -390,7 +393,7 @@ def test_cfg3_full_size_tensor_core_equals_exact_engine(ctx):
     assert max(a["packed"], b["packed"]) == res["packed"]
 
 
-@pytest.mark.parametrize("engine", [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05])
+@pytest.mark.parametrize("engine", [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X])
 def test_cfg4_style_surf128_cross_check(ctx, engine):
     """configs[3] reduced: extended 128-D descriptors with cross-check matching, both engines."""
     q, t, _ = synth.descriptor_pair(6000, 7000, 128, seed=41)
