@@ -135,6 +135,7 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
             int32_t* d_idx2, float* d_dist2, double* d_d2);
 bool knn2_tc_supported(int nq, int nt, int dim);
 bool knn2_tc_preferred(int nq, int nt, int dim);
+bool knn2_tc1_preferred(int nq, int nt, int dim);
 int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
              int32_t* d_idx2, float* d_dist2, double* d_d2);
 int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, int n_lists, int topk, double kappa,

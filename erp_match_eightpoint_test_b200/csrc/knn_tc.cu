@@ -411,10 +411,15 @@ int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int 
 
 bool knn2_tc_supported(int nq, int nt, int dim) { return nq >= 1 && nt >= 2 && dim >= 4 && dim % 4 == 0 && dim <= 128; }
 
-// AUTO policy: tensor cores once the problem is large enough to amortise the extra passes
+// AUTO policy: tensor cores once the problem is large enough to amortise the extra passes; the
+// one-product engine (knn_tc1.cu) from 2e9 dist-evals (below that its paired tiles leave SMs idle)
 bool knn2_tc_preferred(int nq, int nt, int dim)
 {
     return knn2_tc_supported(nq, nt, dim) && (double)nq * (double)nt >= 4.0e6;
+}
+bool knn2_tc1_preferred(int nq, int nt, int dim)
+{
+    return knn2_tc_supported(nq, nt, dim) && (double)nq * (double)nt >= 2.0e9;
 }
 
 // Stream-K style plan: the n_qtiles x n_ttiles unit grid (query tile major) is cut into equal
