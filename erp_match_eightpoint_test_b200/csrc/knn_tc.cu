@@ -57,38 +57,54 @@ constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >
 // ------------------------------------------------------------------------------------------
 
 // one warp per row.  out: n x (2*dpad).  norm (optional): n_pad floats, rows >= n get +inf.
+// LPR lanes own one row (4 floats per lane and pass); a warp covers 32 / LPR rows
+template <int LPR>
 __global__ void __launch_bounds__(256)
 split_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
              float* __restrict__ out, float* __restrict__ norm, int n_pad, unsigned* __restrict__ max_bits)
 {
-    int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= n_pad) return;
-    if (row >= n) {
-        if (norm && lane == 0) norm[row] = INFINITY;
-        return;
-    }
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+    const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + sub;
     double acc = 0.0;
-    for (int k = lane * 4; k < dpad; k += 128) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < dim) v = *reinterpret_cast<const float4*>(x + (size_t)row * dim + k);
-        acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-        float4 s = make_float4(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale));
-        float4 hi = make_float4(tf32_rna(s.x), tf32_rna(s.y), tf32_rna(s.z), tf32_rna(s.w));
-        float4 lo = make_float4(tf32_rna(__fsub_rn(s.x, hi.x)), tf32_rna(__fsub_rn(s.y, hi.y)),
-                                tf32_rna(__fsub_rn(s.z, hi.z)), tf32_rna(__fsub_rn(s.w, hi.w)));
-        float* o = out + (size_t)row * 2 * dpad + k;
-        *reinterpret_cast<float4*>(o) = hi;
-        *reinterpret_cast<float4*>(o + dpad) = lo;
-    }
-    if (norm) {
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-            float f = (float)acc;
-            norm[row] = f;
-            // non-negative floats (and +inf, NaN) order like their bit patterns
-            atomicMax(max_bits, __float_as_uint(f));
+    if (row < n) {
+        for (int k = l * 4; k < dpad; k += LPR * 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < dim) v = *reinterpret_cast<const float4*>(x + (size_t)row * dim + k);
+            acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+            float4 s = make_float4(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale));
+            float4 hi = make_float4(tf32_rna(s.x), tf32_rna(s.y), tf32_rna(s.z), tf32_rna(s.w));
+            float4 lo = make_float4(tf32_rna(__fsub_rn(s.x, hi.x)), tf32_rna(__fsub_rn(s.y, hi.y)),
+                                    tf32_rna(__fsub_rn(s.z, hi.z)), tf32_rna(__fsub_rn(s.w, hi.w)));
+            float* o = out + (size_t)row * 2 * dpad + k;
+            *reinterpret_cast<float4*>(o) = hi;
+            *reinterpret_cast<float4*>(o + dpad) = lo;
         }
     }
+    if (norm) {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (l == 0 && row < n_pad) {
+            float f = row < n ? (float)acc : INFINITY;
+            norm[row] = f;
+            // non-negative floats (and +inf, NaN) order like their bit patterns
+            if (row < n) atomicMax(max_bits, __float_as_uint(f));
+        }
+    }
+}
+
+static int launch_prep(erp_ctx* ctx, const float* x, int n, int dim, int dpad, float scale, float* out, float* norm, int n_pad,
+                       unsigned* max_bits)
+{
+    // 8 / 16 / 32 lanes per row for dpad = 32 / 64 / (96, 128)
+    const int lpr = dpad <= 32 ? 8 : dpad <= 64 ? 16 : 32;
+    const int rows_per_block = 8 * (32 / lpr);
+    const int grid = cdiv(n_pad, rows_per_block);
+    if (lpr == 8) split_kernel<8><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits);
+    else if (lpr == 16) split_kernel<16><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits);
+    else split_kernel<32><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits);
+    ERP_LAUNCH(ctx, "split_kernel");
+    return ERP_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -484,11 +500,8 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
     ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * TOPK * sizeof(int32_t), ctx->stream));   // index -1: empty slot
 
-    split_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3));
-    ERP_LAUNCH(ctx, "split_kernel(q)");
-    split_kernel<<<cdiv(n_ttiles * BN, 8), 256, 0, ctx->stream>>>(d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * BN,
-                                                                 reinterpret_cast<unsigned*>(misc + 1));
-    ERP_LAUNCH(ctx, "split_kernel(t)");
+    ERP_TRY(launch_prep(ctx, d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3)));
+    ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * BN, reinterpret_cast<unsigned*>(misc + 1)));
 
     CUtensorMap mq, mt;
     ERP_TRY(make_map(&mq, qs, nq, 2 * dpad, BM));

@@ -193,6 +193,20 @@ __device__ __forceinline__ float slack_of(float qn, float tn_max, float kappa)
 {
     return __fmul_rn(__fmul_rn(2.0002f * kappa, __fadd_rn(qn, tn_max)), 1.0f);
 }
+// sorted insert for any K (ascending; strict <: equal scores keep the earlier index); all stages are independent
+template <int K>
+__device__ __forceinline__ void topk_insert(float s, int idx, float (&bs)[K], int (&bi)[K])
+{
+#pragma unroll
+    for (int j = K - 1; j > 0; j--) {
+        const bool up = s < bs[j - 1], here = s < bs[j];
+        bs[j] = up ? bs[j - 1] : (here ? s : bs[j]);
+        bi[j] = up ? bi[j - 1] : (here ? idx : bi[j]);
+    }
+    const bool first = s < bs[0];
+    bs[0] = first ? s : bs[0];
+    bi[0] = first ? idx : bi[0];
+}
 __device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[4], int (&bi)[4])
 {
     // strict <: equal scores keep the earlier (lower) train index
@@ -211,8 +225,9 @@ __device__ __forceinline__ void top4_insert(float s, int idx, float (&bs)[4], in
 // needs are re-read from TMEM in a rolled loop, and only the columns below the threshold are visited
 // -- the insert cascade exists once per call site, which keeps the loop inside the instruction cache
 // (fully unrolled it was 60 KB and 3x slower).  Re-computed scores are bit-identical to the first pass.
+template <int K>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t taddr, const float4* __restrict__ tn4, int col0,
-                                           float slack, float (&bs)[4], int (&bi)[4])
+                                           float slack, float (&bs)[K], int (&bi)[K])
 {
     float gm[4];
 #pragma unroll
@@ -224,7 +239,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t tad
         float s6 = __fadd_rn(__uint_as_float(v[g * 8 + 6]), nb.z), s7 = __fadd_rn(__uint_as_float(v[g * 8 + 7]), nb.w);
         gm[g] = fminf(fminf(fminf(s0, s1), fminf(s2, s3)), fminf(fminf(s4, s5), fminf(s6, s7)));
     }
-    const float thr = fminf(bs[3], __fadd_rn(bs[1], slack));
+    const float thr = fminf(bs[K - 1], __fadd_rn(bs[1], slack));
     const unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
     unsigned need = __reduce_or_sync(0xffffffffu, mine);
     while (need) {                                  // warp-uniform
@@ -246,7 +261,10 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t tad
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
                 const float x = j == 0 ? e[0] : j == 1 ? e[1] : j == 2 ? e[2] : j == 3 ? e[3] : j == 4 ? e[4] : j == 5 ? e[5] : j == 6 ? e[6] : e[7];
-                if (x < fminf(bs[3], __fadd_rn(bs[1], slack))) top4_insert(x, col0 + g * 8 + j, bs, bi);
+                if (x < fminf(bs[K - 1], __fadd_rn(bs[1], slack))) {
+                    if (K == 4) top4_insert(x, col0 + g * 8 + j, reinterpret_cast<float (&)[4]>(bs), reinterpret_cast<int (&)[4]>(bi));
+                    else topk_insert<K>(x, col0 + g * 8 + j, bs, bi);
+                }
             }
         }
         __syncwarp();
