@@ -39,7 +39,7 @@ void Buf::release()
 
 int gram_batch(erp_ctx*, const double*, const double*, int, const int32_t*, int, int, uint64_t, uint64_t, double*);
 int gram_masked(erp_ctx*, const double*, const double*, int, const uint8_t*, double*);
-int solve_batch(erp_ctx*, const double*, int, double*, float*);
+int solve_batch(erp_ctx*, const double*, int, double*, float*, int max_sweeps = 30);
 int consensus(erp_ctx*, const float*, int, float*, float*, int32_t*);
 int mask_launch(erp_ctx*, const double*, const float*, const float*, int, int, float, uint8_t*, int32_t*);
 

@@ -650,9 +650,12 @@ int gram_masked(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, con
     return ERP_OK;
 }
 
-int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose)
+// max_sweeps: OpenCV's Jacobi allows 30; on a Gram matrix the relative off-diagonal test rarely fires once
+// the rotations only churn rounding noise, so callers that solve ONE matrix on one thread (the RANSAC
+// refit: a serial chain of ~36 rotations per sweep) cap it -- cyclic Jacobi converges quadratically and
+// is at machine precision after 6-8 sweeps.
+int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose, int max_sweeps = 30)
 {
-    const int max_sweeps = 30;
     if (d_pose) solve_kernel<true><<<cdiv(H, SOLVE_THREADS), SOLVE_THREADS, 0, ctx->stream>>>(d_G, H, max_sweeps, d_E, d_pose);
     else solve_kernel<false><<<cdiv(H, SOLVE_THREADS), SOLVE_THREADS, 0, ctx->stream>>>(d_G, H, max_sweeps, d_E, nullptr);
     ERP_LAUNCH(ctx, "solve_kernel");

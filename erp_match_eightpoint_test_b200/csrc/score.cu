@@ -31,8 +31,9 @@ score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
     __shared__ __align__(16) float Es[TH][12];
     __shared__ int cs[TH];
     if (hlist) H = min(H, *hlist_len);
-    const int h0 = blockIdx.x * TH;
-    if (h0 >= H) return;
+    // hypothesis tiles are walked with a grid stride: list launches are sized for a plausible length,
+    // not for the worst case (thousands of blocks that would only read the length and exit)
+    for (int h0 = blockIdx.x * TH; h0 < H; h0 += gridDim.x * TH) {
     for (int t = threadIdx.x; t < TH; t += SC_THREADS) {
         int h = h0 + t;
         float e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -76,6 +77,8 @@ score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
     for (int t = threadIdx.x; t < nh; t += SC_THREADS) {
         if (gridDim.y == 1) counts[h0 + t] = cs[t];
         else if (cs[t]) atomicAdd(&counts[h0 + t], cs[t]);
+    }
+    __syncthreads();
     }
 }
 
@@ -125,7 +128,7 @@ __global__ void mask_kernel(const double* __restrict__ E9, const float4* __restr
 int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples,
                int H, int S, uint64_t seed, uint64_t hyp0, double* d_G);
 int gram_masked(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const uint8_t* d_mask, double* d_G);
-int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose);
+int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose, int max_sweeps = 30);
 int solve_min8(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples, int H,
                uint64_t seed, uint64_t hyp0, double* d_E, float* d_pose);
 
@@ -170,7 +173,7 @@ int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d
     ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H_max, ctx->stream));
     // the list is usually short: always split the correspondences so that it still fills the machine
     int msplit = max(1, min(cdiv(m, SC_THREADS * 8), 16));
-    dim3 grid(cdiv(H_max, TH), msplit);
+    dim3 grid(min(cdiv(H_max, TH), 64), msplit);
     score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m,
                                                                               tau, tau2, sin2, d_counts, d_list, d_len);
     ERP_LAUNCH(ctx, "score_kernel(list)");
@@ -289,7 +292,7 @@ ERP_API int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double
     }
     ERP_TRY(mask_launch(ctx, Eb, d_l4, d_r4, m, metric, tau, d_mask, n_in));
     ERP_TRY(gram_masked(ctx, d_l3, d_r3, m, d_mask, Gr));                   // refit on the inliers
-    ERP_TRY(solve_batch(ctx, Gr, 1, Er, pose));
+    ERP_TRY(solve_batch(ctx, Gr, 1, Er, pose, 12));
     struct { double Eb[9]; } hb;
     struct { double Er[9]; float pose[12]; int32_t n; } hr;
     ERP_CUDA(cudaMemcpyAsync(&hb, Eb, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
