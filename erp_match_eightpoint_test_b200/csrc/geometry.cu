@@ -424,6 +424,16 @@ solve_kernel(const double* __restrict__ Gin, int H, int max_sweeps,
             }
         }
         if (!changed) break;
+        // a Gram matrix cannot resolve off-diagonals below ~eps * trace: once they are all there, further
+        // sweeps only churn rounding noise (the pairwise relative test above then never fires)
+        double off = 0.0, trc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            trc += fabs(G[tri(i, i)]);
+#pragma unroll
+            for (int j = i + 1; j < 9; j++) off = __fma_rn(G[tri(i, j)], G[tri(i, j)], off);
+        }
+        if (off <= (64.0 * DBL_EPSILON * trc) * (64.0 * DBL_EPSILON * trc)) break;
     }
     // singular values = sqrt of the diagonal; OpenCV's descending selection sort decides which
     // row ends up last (vt.row(vt.rows-1), eight_point.cpp:42)
@@ -515,6 +525,78 @@ min8_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m,
 #pragma unroll
     for (int k = 0; k < 9; k++) E.v[k] = q[k] * inv;
     finish_hypothesis<WANT_POSE>(E, Eout + (size_t)h * 9, pose ? pose + (size_t)h * ERP_POSE_FLOATS : nullptr);
+}
+
+// ------------------------------------------------------------------ one 9x9 solve on one warp
+// solve_kernel keeps a whole problem in one thread (right for a million hypotheses, 0.3 ms of serial
+// latency for a single refit).  Here lane k owns row/column k of G and column k of V in shared memory
+// and every rotation is applied by nine lanes at once; same pivot order and element formulas as
+// solve_kernel, so the two agree to the last bit.
+template <bool WANT_POSE>
+__global__ void __launch_bounds__(32)
+solve1_kernel(const double* __restrict__ Gin, int max_sweeps, double* __restrict__ Eout, float* __restrict__ pose)
+{
+    __shared__ double G[9][9], V[9][9];
+    __shared__ int flag[1];
+    const int k = threadIdx.x;
+    if (k < 9)
+        for (int j = 0; j < 9; j++) { G[k][j] = Gin[tri(k, j)]; V[k][j] = (k == j) ? 1.0 : 0.0; }
+    __syncwarp();
+    const double eps = DBL_EPSILON * 10;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        if (k == 0) flag[0] = 0;
+        __syncwarp();
+        for (int i = 0; i < 8; i++) {
+            for (int j = i + 1; j < 9; j++) {
+                const double a = G[i][i], b = G[j][j], p = G[i][j];
+                const double ab = fmax(a, 0.0) * fmax(b, 0.0);
+                const bool skip = fabs(p) <= eps * sqrt(ab) || fabs(p) <= DBL_EPSILON * fmax(fabs(a), fabs(b));   // warp-uniform
+                if (skip) continue;
+                double c, s;
+                cv_rotation(a, b, p, c, s);
+                __syncwarp();
+                if (k < 9) {
+                    if (k != i && k != j) {
+                        const double gi = G[k][i], gj = G[k][j];
+                        const double ni = c * gi + s * gj, nj = -s * gi + c * gj;
+                        G[k][i] = ni; G[i][k] = ni; G[k][j] = nj; G[j][k] = nj;
+                    }
+                    const double vi = V[i][k], vj = V[j][k];
+                    V[i][k] = c * vi + s * vj;
+                    V[j][k] = -s * vi + c * vj;
+                }
+                if (k == 0) {
+                    const double cc = c * c, ss = s * s, sc = c * s;
+                    G[i][i] = cc * a + 2 * sc * p + ss * b;
+                    G[j][j] = ss * a - 2 * sc * p + cc * b;
+                    const double nij = (cc - ss) * p + sc * (b - a);
+                    G[i][j] = nij; G[j][i] = nij;
+                    flag[0] = 1;
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        if (!flag[0]) break;
+        double off = 0.0, trc = 0.0;
+        for (int i = 0; i < 9; i++) {
+            trc += fabs(G[i][i]);
+            for (int j = i + 1; j < 9; j++) off = __fma_rn(G[i][j], G[i][j], off);
+        }
+        if (off <= (64.0 * DBL_EPSILON * trc) * (64.0 * DBL_EPSILON * trc)) break;
+    }
+    if (k != 0) return;
+    double W[9];
+    int perm[9];
+    for (int i = 0; i < 9; i++) { W[i] = sqrt(fmax(G[i][i], 0.0)); perm[i] = i; }
+    for (int i = 0; i < 8; i++) {
+        int j = i;
+        for (int q = i + 1; q < 9; q++) if (W[j] < W[q]) j = q;
+        if (i != j) { double t = W[i]; W[i] = W[j]; W[j] = t; int q = perm[i]; perm[i] = perm[j]; perm[j] = q; }
+    }
+    M3 E;
+    for (int q = 0; q < 9; q++) E.v[q] = V[perm[8]][q];
+    finish_hypothesis<WANT_POSE>(E, Eout, pose);
 }
 
 // ------------------------------------------------------------------ consensus pick (eight_point.cpp:117-149)
@@ -656,6 +738,12 @@ int gram_masked(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, con
 // is at machine precision after 6-8 sweeps.
 int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose, int max_sweeps = 30)
 {
+    if (H == 1) {      // a single problem: one warp instead of one thread
+        if (d_pose) solve1_kernel<true><<<1, 32, 0, ctx->stream>>>(d_G, max_sweeps, d_E, d_pose);
+        else solve1_kernel<false><<<1, 32, 0, ctx->stream>>>(d_G, max_sweeps, d_E, nullptr);
+        ERP_LAUNCH(ctx, "solve1_kernel");
+        return ERP_OK;
+    }
     if (d_pose) solve_kernel<true><<<cdiv(H, SOLVE_THREADS), SOLVE_THREADS, 0, ctx->stream>>>(d_G, H, max_sweeps, d_E, d_pose);
     else solve_kernel<false><<<cdiv(H, SOLVE_THREADS), SOLVE_THREADS, 0, ctx->stream>>>(d_G, H, max_sweeps, d_E, nullptr);
     ERP_LAUNCH(ctx, "solve_kernel");
