@@ -14,7 +14,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liberp_b200.so")
+LIB_PATH = os.environ.get("ERP_B200_LIB") or os.path.join(_HERE, "lib", "liberp_b200.so")
 
 DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 POSE_FLOATS = 12

@@ -28,7 +28,9 @@ constexpr int F_THREADS = 128 + F_EPI_THREADS;
 constexpr int F_EPI_COLS = F_BN / F_EPI_GROUPS;
 constexpr int F_TOPK = 8;
 constexpr int F_MAX_SEG = 64 / (F_TOPK * F_EPI_GROUPS);     // 4 segments per query pair
-constexpr int F_TAIL = 2 * F_BN * 4 + 256;                  // |t|^2 of two train tiles + mbarriers
+constexpr int F_AUG_T = F_BN * 32;        // 8 KB: one extra k step (8 floats) per train row, 32-byte swizzle rows
+constexpr int F_AUG_Q = F_BM * 32;        // 4 KB: the constant query side of that k step
+constexpr int F_BARS = 256;               // mbarriers + TMEM slot
 // |s_tc - s_exact| <= 2^-10 (|q|^2 + max|t|^2) in the worst case: both operands are rounded to 11
 // significant bits (relative error 2^-11 each), products are exact, and 2|q||t| <= |q|^2 + |t|^2;
 // the 1 % on top covers the fp32 accumulation.  refine_kernel reports the deviation it observes
@@ -37,14 +39,26 @@ constexpr double F_KAPPA = 1.01 / 1024.0;
 constexpr uint32_t F_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F_BN >> 3) << 17) | ((uint32_t)(F_BM >> 4) << 24);
 
 __host__ __device__ constexpr int f_sub(int kch) { return kch <= 3 ? F_SUB_MAX : 1; }
-__host__ __device__ constexpr int f_slots(int kch) { return (TC_SMEM_LIMIT - f_sub(kch) * kch * F_QCH - F_TAIL) / F_TCH; }
+// D <= 64: |t|^2 enters the accumulator through the tensor core (an extra k step whose train side is the
+// norm split in three tf32 pieces and whose query side is 1,1,1), so the epilogue neither loads nor adds it.
+// Wider descriptors keep the norm add: the 20 KB of operand staging would cost them a ring slot they need.
+__host__ __device__ constexpr bool f_fold(int kch) { return kch <= 2; }
+__host__ __device__ constexpr int f_tail(int kch, bool share)
+{
+    return (f_fold(kch) ? 2 * F_AUG_T + F_AUG_Q : 2 * F_BN * 4) + F_BARS + (share ? f_sub(kch) * F_BM * 4 : 0);
+}
+__host__ __device__ constexpr int f_slots_for(int kch, bool share) { return (TC_SMEM_LIMIT - f_sub(kch) * kch * F_QCH - f_tail(kch, share)) / F_TCH; }
+// the per-row threshold exchange between the two column groups needs 512 B per sub-tile: on unless it costs the look-ahead slot
+__host__ __device__ constexpr bool f_share(int kch) { return f_slots_for(kch, true) >= kch + 1; }
+__host__ __device__ constexpr int f_slots(int kch) { return f_slots_for(kch, f_share(kch)); }
+__host__ __device__ constexpr int f_smem(int kch) { return f_sub(kch) * kch * F_QCH + f_slots(kch) * F_TCH + f_tail(kch, f_share(kch)); }
 
 // rows -> tf32-rounded rows (dpad floats), optional norms (+inf padding) and their maximum
 // LPR lanes own one row (4 floats per lane and pass); a warp covers 32 / LPR rows
 template <int LPR>
 __global__ void __launch_bounds__(256)
 round_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
-             float* __restrict__ out, float* __restrict__ norm, int n_pad, unsigned* __restrict__ max_bits)
+             float* __restrict__ out, float* __restrict__ norm, int n_pad, unsigned* __restrict__ max_bits, float* __restrict__ aug)
 {
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
@@ -66,6 +80,13 @@ round_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
         if (l == 0 && row < n_pad) {
             float f = row < n ? (float)acc : INFINITY;
             norm[row] = f;
+            if (aug) {
+                // |t|^2 = hi + mid + lo exactly, every piece a tf32 number; rows past the end score 1e30
+                const float g = row < n ? f : 1e30f;
+                const float hi = tf32_rna(g), r1 = __fsub_rn(g, hi), mid = tf32_rna(r1), lo = __fsub_rn(r1, mid);
+                *reinterpret_cast<float4*>(aug + (size_t)row * 8) = make_float4(hi, mid, lo, 0.f);
+                *reinterpret_cast<float4*>(aug + (size_t)row * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             // non-negative floats (and +inf, NaN) order like their bit patterns
             if (row < n) atomicMax(max_bits, __float_as_uint(f));
         }
@@ -73,15 +94,15 @@ round_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
 }
 
 static int launch_prep(erp_ctx* ctx, const float* x, int n, int dim, int dpad, float scale, float* out, float* norm, int n_pad,
-                       unsigned* max_bits)
+                       unsigned* max_bits, float* aug = nullptr)
 {
     // 8 / 16 / 32 lanes per row for dpad = 32 / 64 / (96, 128)
     const int lpr = dpad <= 32 ? 8 : dpad <= 64 ? 16 : 32;
     const int rows_per_block = 8 * (32 / lpr);
     const int grid = cdiv(n_pad, rows_per_block);
-    if (lpr == 8) round_kernel<8><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits);
-    else if (lpr == 16) round_kernel<16><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits);
-    else round_kernel<32><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits);
+    if (lpr == 8) round_kernel<8><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits, aug);
+    else if (lpr == 16) round_kernel<16><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits, aug);
+    else round_kernel<32><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits, aug);
     ERP_LAUNCH(ctx, "round_kernel");
     return ERP_OK;
 }
@@ -101,16 +122,20 @@ struct Tc1Params {
 
 template <int KCH>   // k chunks of 32 floats: dpad = 32 * KCH
 __global__ void __launch_bounds__(F_THREADS, 1)
-knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const Tc1Params p)
+knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+                const __grid_constant__ CUtensorMap map_aug, const Tc1Params p)
 {
     constexpr int NS = f_slots(KCH), F_SUB = f_sub(KCH);
+    constexpr bool FOLD = f_fold(KCH), SHARE = f_share(KCH);
     static_assert(NS >= KCH + 1, "T ring must hold one tile plus a chunk of look-ahead");
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* q_smem = smem;                                   // [F_SUB][KCH] chunks
     uint8_t* t_smem = smem + F_SUB * KCH * F_QCH;             // NS slots
-    float* tn_smem = reinterpret_cast<float*>(t_smem + NS * F_TCH);   // [2][F_BN], by train-tile parity
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tn_smem + 2 * F_BN);
+    uint8_t* aug_t = t_smem + NS * F_TCH;                     // FOLD: [2][F_AUG_T] by train-tile parity, then the query side
+    uint8_t* aug_q = aug_t + 2 * F_AUG_T;
+    float* tn_smem = reinterpret_cast<float*>(t_smem + NS * F_TCH);   // !FOLD: [2][F_BN] |t|^2, by train-tile parity
+    uint64_t* bars = reinterpret_cast<uint64_t*>(t_smem + NS * F_TCH + (FOLD ? 2 * F_AUG_T + F_AUG_Q : 2 * F_BN * 4));
     uint64_t* full = bars;              // [NS]  TMA -> MMA
     uint64_t* empty = bars + NS;        // [NS]  MMA -> TMA
     uint64_t* qfull = bars + 2 * NS;    // query pair landed
@@ -118,25 +143,32 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint64_t* tfull = qfull + 2;        // [2] accumulator ready
     uint64_t* tempty = qfull + 4;       // [2] accumulator drained
     uint64_t* nfull = qfull + 6;        // [2] |t|^2 of a train tile landed
-    uint64_t* nempty = qfull + 8;       // [2] ... and consumed by both sub-tiles
+    uint64_t* nempty = qfull + 8;       // [2] ... and consumed by both sub-tiles (FOLD: by their MMAs)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 10);
+    static_assert((2 * NS + 10) * 8 + 4 <= F_BARS, "barrier block");
+    float* thr_sh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + F_BARS);   // SHARE: [F_SUB][F_BM] row thresholds
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int W_ALLOC = F_EPI_THREADS / 32, W_NORM = W_ALLOC + 1, W_TMA = W_ALLOC + 2, W_MMA = W_ALLOC + 3;
 
-    if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_t); }
+    if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_t); if (FOLD) tma_prefetch_desc(&map_aug); }
     if (warp == W_MMA && lane == 0) {
         for (int i = 0; i < NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(qfull, 1); mbar_init(qempty, 1);
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull[i], 1); mbar_init(&tempty[i], F_EPI_THREADS / 32);
-            mbar_init(&nfull[i], 1); mbar_init(&nempty[i], F_EPI_THREADS / 32);
+            mbar_init(&nfull[i], 1); mbar_init(&nempty[i], FOLD ? 1 : F_EPI_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (FOLD) {
+        // query side of the norm step: (1,1,1,0) in both 16-byte halves of every row, which the swizzle cannot change
+        for (int i = threadIdx.x; i < F_AUG_Q / 4; i += F_THREADS) reinterpret_cast<float*>(aug_q)[i] = (i & 3) != 3 ? 1.0f : 0.0f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -173,11 +205,13 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, seg_n = 0, tile_n = 0;
             const uint32_t q_base = smem_u32(q_smem), t_base = smem_u32(t_smem);
+            const uint64_t aq_desc = smem_desc_sw32(smem_u32(aug_q));
+            uint32_t tt_n = 0;
             SegIter it(p.n_qpairs, p.n_ttiles, p.units_per_cta, blockIdx.x);
             int qp, t0, t1, seg;
             for (; it.next(qp, t0, t1, seg); seg_n++) {
                 mbar_wait(qfull, seg_n & 1);
-                for (int tt = t0; tt < t1; tt++) {
+                for (int tt = t0; tt < t1; tt++, tt_n++) {
                     // the KCH chunks of this train tile occupy KCH consecutive ring slots
                     uint32_t s0 = slot, p0 = ph;
 #pragma unroll
@@ -197,6 +231,13 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                             if (sub == F_SUB - 1) tc_commit(&empty[sl]);
                             if (++sl == NS) { sl = 0; pp ^= 1; }
                         }
+                        if (FOLD) {
+                            const uint32_t nb = tt_n & 1;
+                            if (sub == 0) mbar_wait(&nfull[nb], (tt_n >> 1) & 1);
+                            tc_fence_after();
+                            tc_mma_tf32(d_tmem, aq_desc, smem_desc_sw32(smem_u32(aug_t + nb * F_AUG_T)), F_IDESC, 1);
+                            if (sub == F_SUB - 1) tc_commit(&nempty[nb]);
+                        }
                         tc_commit(&tfull[acc]);
                         if (sub == F_SUB - 1) { slot = sl; ph = pp; }
                     }
@@ -214,6 +255,11 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 for (int tt = t0; tt < t1; tt++, tt_n++) {
                     const uint32_t nb = tt_n & 1;
                     mbar_wait(&nempty[nb], ((tt_n >> 1) & 1) ^ 1);
+                    if (FOLD) {
+                        mbar_expect_tx(&nfull[nb], F_AUG_T);
+                        tma_load_2d(&map_aug, &nfull[nb], aug_t + nb * F_AUG_T, 0, tt * F_BN);
+                        continue;
+                    }
                     mbar_expect_tx(&nfull[nb], F_BN * 4);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"(smem_u32(tn_smem + nb * F_BN)), "l"(p.tn + (size_t)tt * F_BN), "r"(F_BN * 4), "r"(smem_u32(&nfull[nb]))
@@ -241,9 +287,19 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const int qrow = (qp * F_SUB + sub) * F_BM + row;
                 slack[sub] = slack_of(qrow < p.nq ? p.qn[qrow] : 0.f, __uint_as_float(*p.tn_max_bits), (float)F_KAPPA);
             }
+            float floor_thr[F_SUB];
+#pragma unroll
+            for (int sub = 0; sub < F_SUB; sub++) floor_thr[sub] = INFINITY;
+            if (SHARE) {
+                // every epilogue warp has left the previous query rows before their thresholds are replaced
+                asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+#pragma unroll
+                for (int sub = 0; sub < F_SUB; sub++) thr_sh[sub * F_BM + row] = INFINITY;
+                asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
+            }
             for (int tt = t0; tt < t1; tt++, tt_n++) {
                 const uint32_t nb = tt_n & 1;
-                mbar_wait(&nfull[nb], (tt_n >> 1) & 1);
+                if (!FOLD) mbar_wait(&nfull[nb], (tt_n >> 1) & 1);
                 const float4* tn4 = reinterpret_cast<const float4*>(tn_smem + nb * F_BN + cg * F_EPI_COLS);
                 const int colbase = tt * F_BN + cg * F_EPI_COLS;
 #pragma unroll
@@ -258,17 +314,21 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     for (int cc = 0; cc < F_EPI_COLS / 32; cc += 2) {
                         tc_wait_ld32(va);
                         tc_ld32(taddr + (cc + 1) * 32, vb);
-                        scan_chunk(va, taddr + cc * 32, tn4 + cc * 8, colbase + cc * 32, slack[sub], bs[sub], bi[sub]);
+                        scan_chunk_reg<F_TOPK, SHARE, FOLD>(va, tn4 + cc * 8, colbase + cc * 32, slack[sub], bs[sub], bi[sub],
+                                                            thr_sh + sub * F_BM + row, floor_thr[sub]);
                         tc_wait_ld32(vb);
                         if (cc + 2 < F_EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
-                        scan_chunk(vb, taddr + (cc + 1) * 32, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, slack[sub], bs[sub], bi[sub]);
+                        scan_chunk_reg<F_TOPK, SHARE, FOLD>(vb, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, slack[sub], bs[sub], bi[sub],
+                                                            thr_sh + sub * F_BM + row, floor_thr[sub]);
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&nempty[nb]);
+                if (!FOLD) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&nempty[nb]);
+                }
             }
 #pragma unroll
             for (int sub = 0; sub < F_SUB; sub++) {
@@ -280,7 +340,7 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         *reinterpret_cast<int4*>(p.cand_idx + l * F_TOPK + j) = make_int4(bi[sub][j], bi[sub][j + 1], bi[sub][j + 2], bi[sub][j + 3]);
                         *reinterpret_cast<float4*>(p.cand_s + l * F_TOPK + j) = make_float4(bs[sub][j], bs[sub][j + 1], bs[sub][j + 2], bs[sub][j + 3]);
                     }
-                    p.cand_thr[l] = fminf(bs[sub][F_TOPK - 1], __fadd_rn(bs[sub][1], slack[sub]));
+                    p.cand_thr[l] = fminf(floor_thr[sub], fminf(bs[sub][F_TOPK - 1], __fadd_rn(bs[sub][1], slack[sub])));
                 }
             }
         }
@@ -295,16 +355,16 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 }
 
 template <int KCH>
-static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt, const Tc1Params& p, int grid)
+static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt, const CUtensorMap& ma, const Tc1Params& p, int grid)
 {
-    constexpr int smem = f_sub(KCH) * KCH * F_QCH + f_slots(KCH) * F_TCH + F_TAIL;
+    constexpr int smem = f_smem(KCH);
     static_assert(smem <= TC_SMEM_LIMIT, "shared memory budget");
     static bool configured = false;
     if (!configured) {
         ERP_CUDA(cudaFuncSetAttribute(knn2_tc1_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    knn2_tc1_kernel<KCH><<<grid, F_THREADS, smem, ctx->stream>>>(mq, mt, p);
+    knn2_tc1_kernel<KCH><<<grid, F_THREADS, smem, ctx->stream>>>(mq, mt, ma, p);
     ERP_LAUNCH(ctx, "knn2_tc1_kernel");
     return ERP_OK;
 }
@@ -329,7 +389,7 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     int st = ERP_OK;
     float* qs = ctx->scratch<float>(S_TC_Q, (size_t)nq * dpad, &st);
     float* ts = ctx->scratch<float>(S_TC_T, (size_t)nt * dpad, &st);
-    float* tn = ctx->scratch<float>(S_TC_TN, (size_t)n_ttiles * F_BN, &st);
+    float* tn = ctx->scratch<float>(S_TC_TN, (size_t)n_ttiles * F_BN * 9, &st);      // norms, then the 8-float norm operand rows
     int32_t* cand = ctx->scratch<int32_t>(S_TC_CAND, (size_t)nq * n_lists * (F_TOPK * 2 + 1), &st);
     float* qn = ctx->scratch<float>(S_TC_QN, (size_t)nq + 8, &st);
     int32_t* list = ctx->scratch<int32_t>(S_TC_LIST, (size_t)nq + 8, &st);
@@ -342,11 +402,14 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * F_TOPK * sizeof(int32_t), ctx->stream));
 
     ERP_TRY(launch_prep(ctx, d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3)));
-    ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * F_BN, reinterpret_cast<unsigned*>(misc + 1)));
+    float* aug = tn + (size_t)n_ttiles * F_BN;
+    ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * F_BN, reinterpret_cast<unsigned*>(misc + 1), f_fold(kch) ? aug : nullptr));
 
     CUtensorMap mq, mt;
     ERP_TRY(make_map(&mq, qs, nq, dpad, F_BM));
     ERP_TRY(make_map(&mt, ts, nt, dpad, F_BN));
+    CUtensorMap ma = mt;
+    if (f_fold(kch)) ERP_TRY(make_map(&ma, aug, n_ttiles * F_BN, 8, F_BN, true));
     Tc1Params p;
     p.nq = nq; p.nt = nt; p.n_qpairs = n_qpairs; p.n_ttiles = n_ttiles; p.units_per_cta = (int)L; p.n_seg = n_seg;
     p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s; p.cand_thr = cand_thr; p.qn = qn;
@@ -354,10 +417,10 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
 
     ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
     switch (kch) {
-    case 1: ERP_TRY(launch_tc1<1>(ctx, mq, mt, p, grid)); break;
-    case 2: ERP_TRY(launch_tc1<2>(ctx, mq, mt, p, grid)); break;
-    case 3: ERP_TRY(launch_tc1<3>(ctx, mq, mt, p, grid)); break;
-    default: ERP_TRY(launch_tc1<4>(ctx, mq, mt, p, grid)); break;
+    case 1: ERP_TRY(launch_tc1<1>(ctx, mq, mt, ma, p, grid)); break;
+    case 2: ERP_TRY(launch_tc1<2>(ctx, mq, mt, ma, p, grid)); break;
+    case 3: ERP_TRY(launch_tc1<3>(ctx, mq, mt, ma, p, grid)); break;
+    default: ERP_TRY(launch_tc1<4>(ctx, mq, mt, ma, p, grid)); break;
     }
     ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
 

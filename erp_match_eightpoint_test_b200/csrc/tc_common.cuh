@@ -104,6 +104,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
+// K-major rows of 32 bytes (ONE tf32 k step), 32-byte swizzle: 8-row groups are 256 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                          // SWIZZLE_32B
+    return d;
+}
 // instruction descriptor: D fp32, A/B tf32, both K-major, N = 256, M = 128
 
 __device__ __forceinline__ float tf32_rna(float x)
@@ -165,17 +176,18 @@ inline EncodeTiledFn encode_fn()
     return fn;
 }
 
-// rows x row_floats fp32, row major; box = 32 floats (one 128-byte swizzle row) x box_rows, zero fill out of bounds
-inline int make_map(CUtensorMap* map, const float* base, int rows, int row_floats, int box_rows)
+// rows x row_floats fp32, row major; box = 32 floats (one 128-byte swizzle row) x box_rows, zero fill out of bounds;
+// narrow = true: box = 8 floats (one 32-byte swizzle row) x box_rows for the single-k-step operands
+inline int make_map(CUtensorMap* map, const float* base, int rows, int row_floats, int box_rows, bool narrow = false)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ERP_E_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)row_floats, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_floats * sizeof(float)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {narrow ? 8u : 32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, narrow ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ERP_E_CUDA; }
     return ERP_OK;
@@ -268,6 +280,74 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t tad
             }
         }
         __syncwarp();
+    }
+}
+
+// Register-only variant: the rare path selects the group of 8 columns out of the registers already
+// loaded (two selects per value behind an opaque group id, so the compiler cannot specialise the
+// insert cascade per group), and every lane walks only its own qualifying groups -- no TMEM re-read,
+// no warp-wide vote on the common path.  With SHARE the row's threshold is also exchanged through
+// shared memory between the threads that scan other column ranges of the same query row; any
+// published value is a valid bound (some list's "K-th best" or "2nd best + slack"), so a lost race
+// only costs pruning.  floor_thr is the smallest threshold this list ever applied.
+// With FOLD the accumulator already holds |t|^2 - 2 q.t (the norm entered the MMA as an extra k step).
+template <int K, bool SHARE, bool FOLD>
+__device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const float4* __restrict__ tn4, int col0, float slack,
+                                               float (&bs)[K], int (&bi)[K], float* row_thr, float& floor_thr)
+{
+    const float other = SHARE ? *reinterpret_cast<volatile float*>(row_thr) : INFINITY;
+    float gm[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        float s[8];
+        if (FOLD) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) s[j] = __uint_as_float(v[g * 8 + j]);
+        } else {
+            const float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
+            const float nrm[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) s[j] = __fadd_rn(__uint_as_float(v[g * 8 + j]), nrm[j]);
+        }
+        gm[g] = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(fminf(s[4], s[5]), fminf(s[6], s[7])));
+    }
+    float thr = fminf(bs[K - 1], __fadd_rn(bs[1], slack));
+    if (SHARE) { thr = fminf(thr, other); floor_thr = fminf(floor_thr, thr); }
+    if (fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])) < thr) {                                     // rare, per lane
+        unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
+        do {
+            int g = __ffs(mine) - 1;
+            mine &= mine - 1;
+            asm volatile("" : "+r"(g));
+            const bool pl = (g & 1) != 0, ph = (g & 2) != 0;
+            float nrm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (!FOLD) {
+                const float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
+                nrm[0] = na.x; nrm[1] = na.y; nrm[2] = na.z; nrm[3] = na.w; nrm[4] = nb.x; nrm[5] = nb.y; nrm[6] = nb.z; nrm[7] = nb.w;
+            }
+            float e[8];
+            unsigned m = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t lo = pl ? v[8 + j] : v[j], hi = pl ? v[24 + j] : v[16 + j];
+                const float raw = __uint_as_float(ph ? hi : lo);
+                e[j] = FOLD ? raw : __fadd_rn(raw, nrm[j]);
+                m |= e[j] < thr ? (1u << j) : 0u;
+            }
+            while (m) {                             // usually a single column
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const float x = j == 0 ? e[0] : j == 1 ? e[1] : j == 2 ? e[2] : j == 3 ? e[3] : j == 4 ? e[4] : j == 5 ? e[5] : j == 6 ? e[6] : e[7];
+                if (x < fminf(fminf(bs[K - 1], __fadd_rn(bs[1], slack)), other)) {
+                    if (K == 4) top4_insert(x, col0 + g * 8 + j, reinterpret_cast<float (&)[4]>(bs), reinterpret_cast<int (&)[4]>(bi));
+                    else topk_insert<K>(x, col0 + g * 8 + j, bs, bi);
+                }
+            }
+        } while (mine);
+        if (SHARE) {
+            const float mine_thr = fminf(bs[K - 1], __fadd_rn(bs[1], slack));
+            if (mine_thr < *reinterpret_cast<volatile float*>(row_thr)) *reinterpret_cast<volatile float*>(row_thr) = mine_thr;
+        }
     }
 }
 
