@@ -31,6 +31,15 @@ constexpr int F_MAX_SEG = 64 / (F_TOPK * F_EPI_GROUPS);     // 4 segments per qu
 constexpr int F_AUG_T = F_BN * 32;        // 8 KB: one extra k step (8 floats) per train row, 32-byte swizzle rows
 constexpr int F_AUG_Q = F_BM * 32;        // 4 KB: the constant query side of that k step
 constexpr int F_BARS = 256;               // mbarriers + TMEM slot
+#ifndef ERP_EXP
+#define ERP_EXP 0
+#endif
+#if ERP_EXP == 13
+static __device__ unsigned long long erp_clk[16];
+#define CLK_ADD(i, v) (lclk[i] += (unsigned long long)(v))
+#define CLK_DECL unsigned long long lclk[6] = {0, 0, 0, 0, 0, 0}
+#define CLK_FLUSH for (int i_ = 0; i_ < 6; i_++) if (lclk[i_]) atomicAdd(&erp_clk[i_], lclk[i_])
+#endif
 // |s_tc - s_exact| <= 2^-10 (|q|^2 + max|t|^2) in the worst case: both operands are rounded to 11
 // significant bits (relative error 2^-11 each), products are exact, and 2|q||t| <= |q|^2 + |t|^2;
 // the 1 % on top covers the fp32 accumulation.  refine_kernel reports the deviation it observes
@@ -149,6 +158,9 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     float* thr_sh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + F_BARS);   // SHARE: [F_SUB][F_BM] row thresholds
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#if ERP_EXP == 13
+    CLK_DECL;
+#endif
     constexpr int W_ALLOC = F_EPI_THREADS / 32, W_NORM = W_ALLOC + 1, W_TMA = W_ALLOC + 2, W_MMA = W_ALLOC + 3;
 
     if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_t); if (FOLD) tma_prefetch_desc(&map_aug); }
@@ -217,12 +229,24 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                     for (int sub = 0; sub < F_SUB; sub++, tile_n++) {
                         const uint32_t acc = tile_n & 1;
+#if ERP_EXP == 13
+                        long long m0 = clock64();
+#endif
                         mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
+#if ERP_EXP == 13
+                        long long m1 = clock64(); CLK_ADD(3, m1 - m0); CLK_ADD(4, 1);
+#endif
                         const uint32_t d_tmem = tmem_base + acc * F_BN;
                         uint32_t sl = s0, pp = p0;
 #pragma unroll
                         for (int c = 0; c < KCH; c++) {
+#if ERP_EXP == 13
+                            long long f0 = clock64();
+#endif
                             if (sub == 0) mbar_wait(&full[sl], pp);
+#if ERP_EXP == 13
+                            CLK_ADD(5, clock64() - f0);
+#endif
                             tc_fence_after();
                             const uint32_t a = q_base + (sub * KCH + c) * F_QCH, b = t_base + sl * F_TCH;
 #pragma unroll
@@ -305,25 +329,42 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                 for (int sub = 0; sub < F_SUB; sub++, tile_n++) {
                     const uint32_t acc = tile_n & 1;
+#if ERP_EXP == 13
+                    long long c0 = clock64();
+#endif
                     mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
+#if ERP_EXP == 13
+                    long long c1 = clock64();
+#endif
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * F_BN + cg * F_EPI_COLS;
                     uint32_t va[32], vb[32];
                     tc_ld32(taddr, va);
 #pragma unroll 1
                     for (int cc = 0; cc < F_EPI_COLS / 32; cc += 2) {
+                        const bool last = cc + 2 >= F_EPI_COLS / 32;
                         tc_wait_ld32(va);
                         tc_ld32(taddr + (cc + 1) * 32, vb);
+                        if (last) {
+                            // the scan works on registers only: hand the accumulator back before the last two chunks are examined,
+                            // so that a slow insert path in them does not hold up the next MMA
+                            tc_wait_ld32(vb);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[acc]);
+                        }
                         scan_chunk_reg<F_TOPK, SHARE, FOLD>(va, tn4 + cc * 8, colbase + cc * 32, slack[sub], bs[sub], bi[sub],
                                                             thr_sh + sub * F_BM + row, floor_thr[sub]);
-                        tc_wait_ld32(vb);
-                        if (cc + 2 < F_EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
+                        if (!last) {
+                            tc_wait_ld32(vb);
+                            tc_ld32(taddr + (cc + 2) * 32, va);
+                        }
                         scan_chunk_reg<F_TOPK, SHARE, FOLD>(vb, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, slack[sub], bs[sub], bi[sub],
                                                             thr_sh + sub * F_BM + row, floor_thr[sub]);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+#if ERP_EXP == 13
+                    if (lane == 0) { long long c2 = clock64(); CLK_ADD(0, c1 - c0); CLK_ADD(1, c2 - c1); CLK_ADD(2, 1); }
+#endif
                 }
                 if (!FOLD) {
                     __syncwarp();
@@ -346,6 +387,9 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
     }
 
+#if ERP_EXP == 13
+    if (lane == 0) { CLK_FLUSH; }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == W_ALLOC) {
@@ -354,6 +398,14 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
+#if ERP_EXP == 13
+__global__ void dbg_print_kernel()
+{
+    printf("epi: wait_tfull %.0f scan %.0f per warp-tile (%llu warp-tiles) | mma: wait_tempty %.0f wait_full(sum over chunks) %.0f per tile (%llu tiles)\n",
+           (double)erp_clk[0] / erp_clk[2], (double)erp_clk[1] / erp_clk[2], erp_clk[2], (double)erp_clk[3] / erp_clk[4], (double)erp_clk[5] / erp_clk[4], erp_clk[4]);
+    for (int i = 0; i < 16; i++) erp_clk[i] = 0;
+}
+#endif
 template <int KCH>
 static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt, const CUtensorMap& ma, const Tc1Params& p, int grid)
 {
@@ -366,6 +418,10 @@ static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt
     }
     knn2_tc1_kernel<KCH><<<grid, F_THREADS, smem, ctx->stream>>>(mq, mt, ma, p);
     ERP_LAUNCH(ctx, "knn2_tc1_kernel");
+#if ERP_EXP == 13
+    dbg_print_kernel<<<1, 1, 0, ctx->stream>>>();
+    cudaStreamSynchronize(ctx->stream);
+#endif
     return ERP_OK;
 }
 

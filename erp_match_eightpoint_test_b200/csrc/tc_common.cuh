@@ -313,7 +313,12 @@ __device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const fl
     }
     float thr = fminf(bs[K - 1], __fadd_rn(bs[1], slack));
     if (SHARE) { thr = fminf(thr, other); floor_thr = fminf(floor_thr, thr); }
+#if defined(ERP_EXP) && ERP_EXP == 2
+    bs[0] = fminf(bs[0], fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])));
+    if (false) {
+#else
     if (fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])) < thr) {                                     // rare, per lane
+#endif
         unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
         do {
             int g = __ffs(mine) - 1;
