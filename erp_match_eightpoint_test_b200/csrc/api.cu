@@ -96,9 +96,12 @@ ERP_API int erp_ctx_create(int device, erp_ctx** out)
         delete ctx;
         return ERP_E_CUDA;
     }
-    if (cudaEventCreate(&ctx->ev_k0) != cudaSuccess || cudaEventCreate(&ctx->ev_k1) != cudaSuccess) {
-        set_error("cudaEventCreate failed");
-        delete ctx;
+    bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev_k0) == cudaSuccess && cudaEventCreate(&ctx->ev_k1) == cudaSuccess;
+    for (auto& e2 : ctx->ev_copy) ok = ok && cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        set_error("cudaStreamCreate / cudaEventCreate failed");
+        erp_ctx_destroy(ctx);
         return ERP_E_CUDA;
     }
     *out = ctx;
@@ -109,13 +112,15 @@ ERP_API void erp_ctx_destroy(erp_ctx* ctx)
 {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (cudaEvent_t e : ctx->ev_copy) if (e) cudaEventDestroy(e);
     for (auto& b : ctx->dev) b.release();
     for (auto& b : ctx->pinned) b.release();
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     for (cudaEvent_t e : ctx->ev_score) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -188,10 +193,10 @@ ERP_API int erp_ctx_last_knn_stats(erp_ctx* ctx, int64_t out[5])
     if ((ctx->knn_stats[0] == ERP_ENGINE_TCGEN05 || ctx->knn_stats[0] == ERP_ENGINE_TCGEN05_1X) && ctx->tc_misc_dev) {
         // the re-scan count and the observed deviation live on the device
         DeviceGuard g(ctx->device);
-        int32_t w[4] = {0, 0, 0, 0};
+        int32_t w[5] = {0, 0, 0, 0, 0};
         ERP_CUDA(cudaMemcpyAsync(w, ctx->tc_misc_dev, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
         ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-        out[1] = w[0];
+        out[1] = w[4];                              // summed over the query chunks of a host-buffer call
         float dev;
         memcpy(&dev, &w[2], 4);
         out[4] = (int64_t)((double)dev * 1e12);     // max |s_tc - s_exact| / (|q|^2 + max|t|^2), in 1e-12 units
@@ -300,19 +305,58 @@ ERP_API int erp_knn2_match_dev(erp_ctx* ctx, const float* d_q, int nq, const flo
     return erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n_out);
 }
 
-static int stage_descriptors(erp_ctx* ctx, const float* q, int nq, size_t qs, const float* t, int nt, size_t ts,
-                             int dim, float** dq, float** dt)
+// Host-buffer 2-NN: the train set and the first query chunk are uploaded, then every further query chunk travels
+// (on its own stream) while the previous one is searched.  Rows are independent, so the result does not depend on
+// the cut; the train-side operands are prepared by the first chunk only.  Chunks: $ERP_B200_HOST_CHUNKS (1..7).
+// Measured on cfg3 (100k x 100k, pinned source): 1 chunk 3.85 ms, 2 chunks 3.90, 4 chunks 4.27, 6 chunks 6.07 -- the
+// shorter per-chunk kernels (more list segments per row, more tails) lose more than the hidden copy gains, so the
+// default is ONE chunk and the knob stays for larger query sets / slower links.
+static int host_chunks(int nq, int nt)
+{
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("ERP_B200_HOST_CHUNKS");
+        forced = e ? atoi(e) : 0;
+        if (forced < 0 || forced > 7) forced = 0;
+    }
+    if (forced) return forced;
+    (void)nq; (void)nt;
+    return 1;
+}
+static int knn2_host(erp_ctx* ctx, const float* q, int nq, size_t qs, const float* t, int nt, size_t ts, int dim,
+                     int32_t* d_idx2, float* d_dist2)
 {
     size_t row = (size_t)dim * sizeof(float);
     ERP_ARG((nq == 0 || q) && (nt == 0 || t), ERP_E_ARG, "null descriptor pointer");
     ERP_ARG(qs >= row && ts >= row, ERP_E_ARG, "row stride smaller than a descriptor row (%zu < %zu)", qs < ts ? qs : ts, row);
     int st = ERP_OK;
-    *dq = ctx->scratch<float>(S_Q, (size_t)nq * dim + 4, &st);
-    *dt = ctx->scratch<float>(S_T, (size_t)nt * dim + 4, &st);
+    float* dq = ctx->scratch<float>(S_Q, (size_t)nq * dim + 4, &st);
+    float* dt = ctx->scratch<float>(S_T, (size_t)nt * dim + 4, &st);
     ERP_TRY(st);
-    ERP_TRY(upload_rows(ctx, *dq, q, nq, row, qs));
-    ERP_TRY(upload_rows(ctx, *dt, t, nt, row, ts));
-    return ERP_OK;
+    int chunks = host_chunks(nq, nt);
+    int rows = cdiv(cdiv(nq, chunks), 256) * 256;
+    chunks = cdiv(nq, rows);
+    // fork: the copy stream starts after whatever the context stream still has queued
+    ERP_CUDA(cudaEventRecord(ctx->ev_copy[7], ctx->stream));
+    ERP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->copy_stream;                 // upload_rows enqueues on ctx->stream
+    int rc = upload_rows(ctx, dt, t, nt, row, ts);
+    for (int c = 0; c < chunks && rc == ERP_OK; c++) {
+        const int r0 = c * rows, n = nq - r0 < rows ? nq - r0 : rows;
+        rc = upload_rows(ctx, dq + (size_t)r0 * dim, reinterpret_cast<const char*>(q) + (size_t)r0 * qs, n, row, qs);
+        if (rc == ERP_OK && cudaEventRecord(ctx->ev_copy[c], ctx->copy_stream) != cudaSuccess) rc = ERP_E_CUDA;
+    }
+    ctx->stream = main_stream;
+    ERP_TRY(rc);
+    for (int c = 0; c < chunks && rc == ERP_OK; c++) {
+        const int r0 = c * rows, n = nq - r0 < rows ? nq - r0 : rows;
+        ERP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[c], 0));
+        ctx->tc_chunk = c;
+        rc = erp_knn2_dev(ctx, dq + (size_t)r0 * dim, n, dt, nt, dim, d_idx2 + 2 * (size_t)r0, d_dist2 + 2 * (size_t)r0, nullptr);
+    }
+    ctx->tc_chunk = 0;
+    return rc;
 }
 
 ERP_API int erp_knn2_match(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
@@ -325,13 +369,20 @@ ERP_API int erp_knn2_match(erp_ctx* ctx, const float* q, int nq, size_t q_stride
     if (nq == 0) return ERP_OK;
     ERP_ARG(out, ERP_E_ARG, "erp_knn2_match: out is null");
     DeviceGuard g(ctx->device);
-    float *dq, *dt;
-    ERP_TRY(stage_descriptors(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, &dq, &dt));
     int st = ERP_OK;
     erp_dmatch* d_out = ctx->scratch<erp_dmatch>(S_OUT, (size_t)nq, &st);
     int32_t* d_n = ctx->scratch<int32_t>(S_NOUT, 4, &st);
+    int32_t* idx2 = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
+    float* dist2 = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
     ERP_TRY(st);
-    ERP_TRY(erp_knn2_match_dev(ctx, dq, nq, dt, nt, dim, ratio, cross_check, d_out, d_n));
+    ERP_TRY(knn2_host(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, idx2, dist2));
+    int32_t* rev = nullptr;
+    if (cross_check) {
+        rev = ctx->scratch<int32_t>(S_REVQ, (size_t)nt, &st);
+        ERP_TRY(st);
+        ERP_TRY(erp_nn1_reverse_dev(ctx, ctx->dev[S_Q].as<float>(), nq, ctx->dev[S_T].as<float>(), nt, dim, 0, rev, nullptr));
+    }
+    ERP_TRY(erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n));
     int32_t n = 0;
     ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -350,13 +401,11 @@ ERP_API int erp_knn2_raw(erp_ctx* ctx, const float* q, int nq, size_t q_stride_b
     ERP_TRY(check_knn_args("erp_knn2_raw", ctx, nq, nt, dim));
     if (nq == 0) return ERP_OK;
     DeviceGuard g(ctx->device);
-    float *dq, *dt;
-    ERP_TRY(stage_descriptors(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, &dq, &dt));
     int st = ERP_OK;
     int32_t* d_idx = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
     float* d_dist = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
     ERP_TRY(st);
-    ERP_TRY(erp_knn2_dev(ctx, dq, nq, dt, nt, dim, d_idx, d_dist, nullptr));
+    ERP_TRY(knn2_host(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, d_idx, d_dist));
     if (idx2) ERP_CUDA(cudaMemcpyAsync(idx2, d_idx, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
     if (dist2) ERP_CUDA(cudaMemcpyAsync(dist2, d_dist, sizeof(float) * 2 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -67,6 +67,9 @@ struct erp_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;             // host-buffer calls upload query chunks here while the previous chunk computes
+    cudaEvent_t ev_copy[8] = {};                    // "chunk c is on the device" (+ one fork event)
+    int tc_chunk = 0;                               // > 0: later query chunk of one host call: train operand and statistics carry over
     int engine = ERP_ENGINE_AUTO;
     uint64_t launches = 0;
     int64_t knn_stats[5] = {0, 0, 0, 0, 0};
@@ -138,6 +141,8 @@ bool knn2_tc_preferred(int nq, int nt, int dim);
 bool knn2_tc1_preferred(int nq, int nt, int dim);
 int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
              int32_t* d_idx2, float* d_dist2, double* d_d2);
+int tc_misc_begin(erp_ctx* ctx, int32_t* misc);
+int tc_misc_end(erp_ctx* ctx, int32_t* misc);
 int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, int n_lists, int topk, double kappa,
                   const int32_t* cand, const float* cand_s, const float* cand_thr, unsigned* misc, int32_t* d_idx2, float* d_dist2,
                   double* d_d2, int32_t* rescan_list);

@@ -415,6 +415,27 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
 }
 
 // topk must be a power of two, n_lists * topk <= 64
+// misc words of a tcgen05 call: [0] re-scan count of THIS call (also the length of its re-scan list), [1] max |t|^2 bits,
+// [2] max deviation bits, [3] max |q|^2 bits, [4] re-scan count summed over the query chunks of one host call
+__global__ void misc_reset_kernel(int32_t* misc) { misc[0] = 0; misc[3] = 0; }
+__global__ void misc_accum_kernel(int32_t* misc) { misc[4] += misc[0]; }
+int tc_misc_begin(erp_ctx* ctx, int32_t* misc)
+{
+    if (ctx->tc_chunk == 0) {
+        ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
+    } else {
+        misc_reset_kernel<<<1, 1, 0, ctx->stream>>>(misc);
+        ERP_LAUNCH(ctx, "misc_reset_kernel");
+    }
+    return ERP_OK;
+}
+int tc_misc_end(erp_ctx* ctx, int32_t* misc)
+{
+    misc_accum_kernel<<<1, 1, 0, ctx->stream>>>(misc);
+    ERP_LAUNCH(ctx, "misc_accum_kernel");
+    return ERP_OK;
+}
+
 int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, int n_lists, int topk, double kappa,
                   const int32_t* cand, const float* cand_s, const float* cand_thr, unsigned* misc, int32_t* d_idx2, float* d_dist2,
                   double* d_d2, int32_t* rescan_list)
@@ -497,11 +518,11 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_lists * TOPK);
     float* cand_thr = cand_s + (size_t)nq * n_lists * TOPK;
     ERP_CUDA(cudaMemsetAsync(cand_thr, 0x7f, (size_t)nq * n_lists * sizeof(float), ctx->stream));              // ~3.4e38: "unbounded"
-    ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
+    ERP_TRY(tc_misc_begin(ctx, misc));
     ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * TOPK * sizeof(int32_t), ctx->stream));   // index -1: empty slot
 
     ERP_TRY(launch_prep(ctx, d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3)));
-    ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * BN, reinterpret_cast<unsigned*>(misc + 1)));
+    if (ctx->tc_chunk == 0) ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * BN, reinterpret_cast<unsigned*>(misc + 1)));
 
     CUtensorMap mq, mt;
     ERP_TRY(make_map(&mq, qs, nq, 2 * dpad, BM));
@@ -511,7 +532,7 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s; p.cand_thr = cand_thr; p.qn = qn;
     p.tn_max_bits = reinterpret_cast<const unsigned*>(misc + 1);
 
-    ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if (ctx->tc_chunk == 0) ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
     switch (kch) {
     case 1: ERP_TRY(launch_tc<1>(ctx, mq, mt, p, grid)); break;
     case 2: ERP_TRY(launch_tc<2>(ctx, mq, mt, p, grid)); break;
@@ -523,6 +544,7 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     ERP_TRY(refine_launch(ctx, d_q, nq, d_t, nt, dim, n_lists, TOPK, KAPPA, cand, cand_s, cand_thr, reinterpret_cast<unsigned*>(misc),
                           d_idx2, d_dist2, d_d2, list));
     ERP_TRY(knn2_exact_rescan(ctx, d_q, nq, d_t, nt, dim, list, misc, nq, d_idx2, d_dist2, d_d2));
+    ERP_TRY(tc_misc_end(ctx, misc));
 
     ctx->knn_stats[0] = ERP_ENGINE_TCGEN05;
     ctx->knn_stats[1] = -1;                       // re-scan count lives on the device: see erp_ctx_last_knn_stats

@@ -187,6 +187,9 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // the four feeder warps need few registers; the eight epilogue warps take them over (4 chunks of 32 accumulator columns in flight)
+    if (warp >= W_ALLOC) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     if (warp == W_TMA) {
         // ================================================================ TMA producer
         if (lane == 0) {
@@ -291,7 +294,9 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 }
             }
         }
-    } else if (warp < W_ALLOC) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
         // ================================================================ epilogue (2 column groups x 4 lane quarters)
         const int ew = warp & 3, cg = warp >> 2;
         const int row = ew * 32 + lane;
@@ -338,29 +343,32 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #endif
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * F_BN + cg * F_EPI_COLS;
-                    uint32_t va[32], vb[32];
+                    // all four chunks of this warp's share go to registers at once (the epilogue warps hold 224 registers, see
+                    // setmaxnreg above), the accumulator is handed back, and only then are the columns examined: a slow insert
+                    // path delays this warp's next read, not the next MMA
+                    static_assert(F_EPI_COLS == 128, "four chunks of 32 columns per warp and tile");
+                    uint32_t va[32], vb[32], vc[32], vd[32];
                     tc_ld32(taddr, va);
-#pragma unroll 1
-                    for (int cc = 0; cc < F_EPI_COLS / 32; cc += 2) {
-                        const bool last = cc + 2 >= F_EPI_COLS / 32;
-                        tc_wait_ld32(va);
-                        tc_ld32(taddr + (cc + 1) * 32, vb);
-                        if (last) {
-                            // the scan works on registers only: hand the accumulator back before the last two chunks are examined,
-                            // so that a slow insert path in them does not hold up the next MMA
-                            tc_wait_ld32(vb);
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[acc]);
-                        }
-                        scan_chunk_reg<F_TOPK, SHARE, FOLD>(va, tn4 + cc * 8, colbase + cc * 32, slack[sub], bs[sub], bi[sub],
-                                                            thr_sh + sub * F_BM + row, floor_thr[sub]);
-                        if (!last) {
-                            tc_wait_ld32(vb);
-                            tc_ld32(taddr + (cc + 2) * 32, va);
-                        }
-                        scan_chunk_reg<F_TOPK, SHARE, FOLD>(vb, tn4 + (cc + 1) * 8, colbase + (cc + 1) * 32, slack[sub], bs[sub], bi[sub],
-                                                            thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    tc_ld32(taddr + 32, vb);
+                    tc_ld32(taddr + 64, vc);
+                    tc_ld32(taddr + 96, vd);
+                    tc_wait_ld32(va);
+                    tc_wait_ld32(vb);
+                    tc_wait_ld32(vc);
+                    tc_wait_ld32(vd);
+                    if (FOLD) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(va, tn4, colbase, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(vb, tn4 + 8, colbase + 32, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(vc, tn4 + 16, colbase + 64, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(vd, tn4 + 24, colbase + 96, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    if (!FOLD) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
                     }
 #if ERP_EXP == 13
                     if (lane == 0) { long long c2 = clock64(); CLK_ADD(0, c1 - c0); CLK_ADD(1, c2 - c1); CLK_ADD(2, 1); }
@@ -398,6 +406,13 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
+#if ERP_EXP == 14
+__global__ void dbg_print_kernel()
+{
+    printf("warp-events (first lane) steady %llu, %.0f clk each; warm-up %llu, %.0f clk each\n", erp_evt[1], (double)erp_evt[0] / erp_evt[1], erp_evt[3], (double)erp_evt[2] / erp_evt[3]);
+    erp_evt[0] = erp_evt[1] = erp_evt[2] = erp_evt[3] = 0;
+}
+#endif
 #if ERP_EXP == 13
 __global__ void dbg_print_kernel()
 {
@@ -418,7 +433,7 @@ static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt
     }
     knn2_tc1_kernel<KCH><<<grid, F_THREADS, smem, ctx->stream>>>(mq, mt, ma, p);
     ERP_LAUNCH(ctx, "knn2_tc1_kernel");
-#if ERP_EXP == 13
+#if ERP_EXP == 13 || ERP_EXP == 14
     dbg_print_kernel<<<1, 1, 0, ctx->stream>>>();
     cudaStreamSynchronize(ctx->stream);
 #endif
@@ -454,12 +469,13 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_lists * F_TOPK);
     float* cand_thr = cand_s + (size_t)nq * n_lists * F_TOPK;
     ERP_CUDA(cudaMemsetAsync(cand_thr, 0x7f, (size_t)nq * n_lists * sizeof(float), ctx->stream));              // ~3.4e38: "unbounded"
-    ERP_CUDA(cudaMemsetAsync(misc, 0, 8 * sizeof(int32_t), ctx->stream));
+    ERP_TRY(tc_misc_begin(ctx, misc));
     ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * F_TOPK * sizeof(int32_t), ctx->stream));
 
     ERP_TRY(launch_prep(ctx, d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3)));
     float* aug = tn + (size_t)n_ttiles * F_BN;
-    ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * F_BN, reinterpret_cast<unsigned*>(misc + 1), f_fold(kch) ? aug : nullptr));
+    if (ctx->tc_chunk == 0)
+        ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * F_BN, reinterpret_cast<unsigned*>(misc + 1), f_fold(kch) ? aug : nullptr));
 
     CUtensorMap mq, mt;
     ERP_TRY(make_map(&mq, qs, nq, dpad, F_BM));
@@ -471,7 +487,7 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s; p.cand_thr = cand_thr; p.qn = qn;
     p.tn_max_bits = reinterpret_cast<const unsigned*>(misc + 1);
 
-    ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if (ctx->tc_chunk == 0) ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
     switch (kch) {
     case 1: ERP_TRY(launch_tc1<1>(ctx, mq, mt, ma, p, grid)); break;
     case 2: ERP_TRY(launch_tc1<2>(ctx, mq, mt, ma, p, grid)); break;
@@ -483,6 +499,7 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     ERP_TRY(refine_launch(ctx, d_q, nq, d_t, nt, dim, n_lists, F_TOPK, F_KAPPA, cand, cand_s, cand_thr, reinterpret_cast<unsigned*>(misc),
                           d_idx2, d_dist2, d_d2, list));
     ERP_TRY(knn2_exact_rescan(ctx, d_q, nq, d_t, nt, dim, list, misc, nq, d_idx2, d_dist2, d_d2));
+    ERP_TRY(tc_misc_end(ctx, misc));
 
     ctx->knn_stats[0] = ERP_ENGINE_TCGEN05_1X;
     ctx->knn_stats[1] = -1;

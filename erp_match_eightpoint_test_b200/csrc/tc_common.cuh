@@ -291,6 +291,9 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t tad
 // published value is a valid bound (some list's "K-th best" or "2nd best + slack"), so a lost race
 // only costs pruning.  floor_thr is the smallest threshold this list ever applied.
 // With FOLD the accumulator already holds |t|^2 - 2 q.t (the norm entered the MMA as an extra k step).
+#if defined(ERP_EXP) && ERP_EXP == 14
+static __device__ unsigned long long erp_evt[4];
+#endif
 template <int K, bool SHARE, bool FOLD>
 __device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const float4* __restrict__ tn4, int col0, float slack,
                                                float (&bs)[K], int (&bi)[K], float* row_thr, float& floor_thr)
@@ -320,6 +323,9 @@ __device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const fl
     if (fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])) < thr) {                                     // rare, per lane
 #endif
         unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
+#if defined(ERP_EXP) && ERP_EXP == 14
+        const long long e0 = clock64();
+#endif
         do {
             int g = __ffs(mine) - 1;
             mine &= mine - 1;
@@ -353,6 +359,17 @@ __device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const fl
             const float mine_thr = fminf(bs[K - 1], __fadd_rn(bs[1], slack));
             if (mine_thr < *reinterpret_cast<volatile float*>(row_thr)) *reinterpret_cast<volatile float*>(row_thr) = mine_thr;
         }
+#if defined(ERP_EXP) && ERP_EXP == 14
+        const long long e1 = clock64();
+        {
+            const unsigned am = __activemask();
+            const bool warm = (col0 & 0xffff) < 4096;      // rough: early columns of a list
+            if ((threadIdx.x & 31) == __ffs(am) - 1) {
+                atomicAdd(&erp_evt[warm ? 2 : 0], (unsigned long long)(e1 - e0));
+                atomicAdd(&erp_evt[warm ? 3 : 1], 1ull);
+            }
+        }
+#endif
     }
 }
 
