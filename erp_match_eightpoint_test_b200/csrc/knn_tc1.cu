@@ -361,10 +361,10 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[acc]);
                     }
-                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(va, tn4, colbase, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
-                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(vb, tn4 + 8, colbase + 32, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
-                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(vc, tn4 + 16, colbase + 64, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
-                    scan_chunk_reg<F_TOPK, SHARE, FOLD>(vd, tn4 + 24, colbase + 96, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    scan_chunk_lean<SHARE, FOLD>(va, tn4, colbase, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    scan_chunk_lean<SHARE, FOLD>(vb, tn4 + 8, colbase + 32, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    scan_chunk_lean<SHARE, FOLD>(vc, tn4 + 16, colbase + 64, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
+                    scan_chunk_lean<SHARE, FOLD>(vd, tn4 + 24, colbase + 96, slack[sub], bs[sub], bi[sub], thr_sh + sub * F_BM + row, floor_thr[sub]);
                     if (!FOLD) {
                         tc_fence_before();
                         __syncwarp();
@@ -389,7 +389,7 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         *reinterpret_cast<int4*>(p.cand_idx + l * F_TOPK + j) = make_int4(bi[sub][j], bi[sub][j + 1], bi[sub][j + 2], bi[sub][j + 3]);
                         *reinterpret_cast<float4*>(p.cand_s + l * F_TOPK + j) = make_float4(bs[sub][j], bs[sub][j + 1], bs[sub][j + 2], bs[sub][j + 3]);
                     }
-                    p.cand_thr[l] = fminf(floor_thr[sub], fminf(bs[sub][F_TOPK - 1], __fadd_rn(bs[sub][1], slack[sub])));
+                    p.cand_thr[l] = fminf(floor_thr[sub], __fadd_rn(bs[sub][1], slack[sub]));
                 }
             }
         }
@@ -410,7 +410,8 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 __global__ void dbg_print_kernel()
 {
     printf("warp-events (first lane) steady %llu, %.0f clk each; warm-up %llu, %.0f clk each\n", erp_evt[1], (double)erp_evt[0] / erp_evt[1], erp_evt[3], (double)erp_evt[2] / erp_evt[3]);
-    erp_evt[0] = erp_evt[1] = erp_evt[2] = erp_evt[3] = 0;
+    printf("lane-events %llu groups %llu inserts %llu\n", erp_evt[4], erp_evt[5], erp_evt[6]);
+    for (int i = 0; i < 8; i++) erp_evt[i] = 0;
 }
 #endif
 #if ERP_EXP == 13

@@ -283,20 +283,27 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t tad
     }
 }
 
-// Register-only variant: the rare path selects the group of 8 columns out of the registers already
-// loaded (two selects per value behind an opaque group id, so the compiler cannot specialise the
-// insert cascade per group), and every lane walks only its own qualifying groups -- no TMEM re-read,
-// no warp-wide vote on the common path.  With SHARE the row's threshold is also exchanged through
-// shared memory between the threads that scan other column ranges of the same query row; any
-// published value is a valid bound (some list's "K-th best" or "2nd best + slack"), so a lost race
-// only costs pruning.  floor_thr is the smallest threshold this list ever applied.
+// Candidate list of the 1xTF32 engine, 8 entries per (query row, list): [0], [1] = the two best scores so far in
+// order (all the threshold needs), [2..7] = a FIFO of the other columns that were within the slack of the runner-up when
+// they arrived (newest first).  An entry pushed out of the FIFO lowers floor_thr to its score (and with it the threshold),
+// every other dropped column scored >= the threshold in force, so min(floor_thr, final threshold) bounds all
+// non-candidates of the list.
+// Scores carry their column (mod 8) in the three low mantissa bits -- the minimum of the packed keys is the winning
+// score AND its position, which replaces a dynamic register index; the 2^-21 relative perturbation is part of the margin
+// in F_KAPPA.  refine_kernel takes the list in any order.
+//
+// scan_chunk_lean: 32 accumulator columns of one query row, all in registers.  Common case: a min tree and ONE compare.
+// Rare case (per lane, no TMEM access, no warp-wide vote): the groups of 8 columns whose minimum is below the threshold are
+// selected out of the registers behind an opaque group id (so the compiler cannot specialise the code per group), packed,
+// and inserted smallest first.  With SHARE the threshold is also exchanged through shared memory with the thread that scans
+// the other column range of the same row; any published value is a valid bound, so a lost race only costs pruning.
 // With FOLD the accumulator already holds |t|^2 - 2 q.t (the norm entered the MMA as an extra k step).
 #if defined(ERP_EXP) && ERP_EXP == 14
-static __device__ unsigned long long erp_evt[4];
+static __device__ unsigned long long erp_evt[8];
 #endif
-template <int K, bool SHARE, bool FOLD>
-__device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const float4* __restrict__ tn4, int col0, float slack,
-                                               float (&bs)[K], int (&bi)[K], float* row_thr, float& floor_thr)
+template <bool SHARE, bool FOLD>
+__device__ __forceinline__ void scan_chunk_lean(const uint32_t (&v)[32], const float4* __restrict__ tn4, int col0, float slack,
+                                                float (&bs)[8], int (&bi)[8], float* row_thr, float& floor_thr)
 {
     const float other = SHARE ? *reinterpret_cast<volatile float*>(row_thr) : INFINITY;
     float gm[4];
@@ -314,17 +321,15 @@ __device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const fl
         }
         gm[g] = fminf(fminf(fminf(s[0], s[1]), fminf(s[2], s[3])), fminf(fminf(s[4], s[5]), fminf(s[6], s[7])));
     }
-    float thr = fminf(bs[K - 1], __fadd_rn(bs[1], slack));
-    if (SHARE) { thr = fminf(thr, other); floor_thr = fminf(floor_thr, thr); }
-#if defined(ERP_EXP) && ERP_EXP == 2
-    bs[0] = fminf(bs[0], fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])));
-    if (false) {
-#else
+    // floor_thr in the threshold is the capacity rule: once an entry has been pushed out, columns at or above its score
+    // cannot improve the list's bound any more (all-equal scores would otherwise insert at every column)
+    float thr = fminf(fminf(__fadd_rn(bs[1], slack), other), floor_thr);
+    if (SHARE) floor_thr = thr;
     if (fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])) < thr) {                                     // rare, per lane
-#endif
         unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
 #if defined(ERP_EXP) && ERP_EXP == 14
         const long long e0 = clock64();
+        atomicAdd(&erp_evt[4], 1ull);
 #endif
         do {
             int g = __ffs(mine) - 1;
@@ -336,34 +341,53 @@ __device__ __forceinline__ void scan_chunk_reg(const uint32_t (&v)[32], const fl
                 const float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
                 nrm[0] = na.x; nrm[1] = na.y; nrm[2] = na.z; nrm[3] = na.w; nrm[4] = nb.x; nrm[5] = nb.y; nrm[6] = nb.z; nrm[7] = nb.w;
             }
-            float e[8];
-            unsigned m = 0;
+#if defined(ERP_EXP) && ERP_EXP == 14
+            atomicAdd(&erp_evt[5], 1ull);
+#endif
+            float k[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint32_t lo = pl ? v[8 + j] : v[j], hi = pl ? v[24 + j] : v[16 + j];
                 const float raw = __uint_as_float(ph ? hi : lo);
-                e[j] = FOLD ? raw : __fadd_rn(raw, nrm[j]);
-                m |= e[j] < thr ? (1u << j) : 0u;
+                const float e = FOLD ? raw : __fadd_rn(raw, nrm[j]);
+                k[j] = __uint_as_float((__float_as_uint(e) & ~7u) | (uint32_t)j);
             }
-            while (m) {                             // usually a single column
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                const float x = j == 0 ? e[0] : j == 1 ? e[1] : j == 2 ? e[2] : j == 3 ? e[3] : j == 4 ? e[4] : j == 5 ? e[5] : j == 6 ? e[6] : e[7];
-                if (x < fminf(fminf(bs[K - 1], __fadd_rn(bs[1], slack)), other)) {
-                    if (K == 4) top4_insert(x, col0 + g * 8 + j, reinterpret_cast<float (&)[4]>(bs), reinterpret_cast<int (&)[4]>(bi));
-                    else topk_insert<K>(x, col0 + g * 8 + j, bs, bi);
+            const int cbase = col0 + g * 8;
+            for (;;) {
+                const float km = fminf(fminf(fminf(k[0], k[1]), fminf(k[2], k[3])), fminf(fminf(k[4], k[5]), fminf(k[6], k[7])));
+                if (!(km < thr)) break;
+#if defined(ERP_EXP) && ERP_EXP == 14
+                atomicAdd(&erp_evt[6], 1ull);
+#endif
+                const int col = cbase + (int)(__float_as_uint(km) & 7u);
+                // strict <: equal scores keep the earlier (lower) train index
+                const bool lt0 = km < bs[0], lt1 = km < bs[1];
+                const float pv = lt1 ? bs[1] : km;            // leaves the top two (or never enters)
+                const int pi = lt1 ? bi[1] : col;
+                bs[1] = lt0 ? bs[0] : (lt1 ? km : bs[1]);
+                bi[1] = lt0 ? bi[0] : (lt1 ? col : bi[1]);
+                bs[0] = lt0 ? km : bs[0];
+                bi[0] = lt0 ? col : bi[0];
+                thr = fminf(fminf(__fadd_rn(bs[1], slack), other), floor_thr);
+                if (pv < thr) {
+                    floor_thr = fminf(floor_thr, bs[7]);     // +inf while the FIFO has room
+                    thr = fminf(thr, floor_thr);
+#pragma unroll
+                    for (int i = 7; i > 2; i--) { bs[i] = bs[i - 1]; bi[i] = bi[i - 1]; }
+                    bs[2] = pv; bi[2] = pi;
                 }
+#pragma unroll
+                for (int j = 0; j < 8; j++) k[j] = k[j] == km ? INFINITY : k[j];
             }
         } while (mine);
         if (SHARE) {
-            const float mine_thr = fminf(bs[K - 1], __fadd_rn(bs[1], slack));
-            if (mine_thr < *reinterpret_cast<volatile float*>(row_thr)) *reinterpret_cast<volatile float*>(row_thr) = mine_thr;
+            if (thr < *reinterpret_cast<volatile float*>(row_thr)) *reinterpret_cast<volatile float*>(row_thr) = thr;
         }
 #if defined(ERP_EXP) && ERP_EXP == 14
         const long long e1 = clock64();
         {
             const unsigned am = __activemask();
-            const bool warm = (col0 & 0xffff) < 4096;      // rough: early columns of a list
+            const bool warm = (col0 & 0xffff) < 4096;
             if ((threadIdx.x & 31) == __ffs(am) - 1) {
                 atomicAdd(&erp_evt[warm ? 2 : 0], (unsigned long long)(e1 - e0));
                 atomicAdd(&erp_evt[warm ? 3 : 1], 1ull);
