@@ -50,7 +50,7 @@ constexpr float S_KAPPA = 1.0f / 65536.0f;
 // ---- operand preparation ---------------------------------------------------------------
 // row i of Es = split scaled E of hypothesis list[i] (i < *list_len) or of hypothesis i
 __global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __restrict__ Es /* H x 32 */,
-                              const int32_t* __restrict__ list, const int32_t* __restrict__ list_len)
+                              const int32_t* __restrict__ list, const int32_t* __restrict__ list_len, float big)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (list) H = min(H, *list_len);
@@ -61,7 +61,7 @@ __global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __rest
     for (int i = 0; i < 9; i++) { hi[i] = tf32_rna(e[i]); lo[i] = tf32_rna(__fsub_rn(e[i], hi[i])); }
     float row[32];
 #pragma unroll
-    for (int i = 0; i < 9; i++) { row[i] = hi[i]; row[9 + i] = hi[i]; row[18 + i] = lo[i]; }
+    for (int i = 0; i < 9; i++) { row[i] = hi[i] * big; row[9 + i] = hi[i] * big; row[18 + i] = lo[i] * big; }   // exact: power of two
 #pragma unroll
     for (int i = 27; i < 32; i++) row[i] = 0.f;
     float4* o = reinterpret_cast<float4*>(Es + (size_t)h * 32);
@@ -100,6 +100,7 @@ __global__ void prep_k_kernel(const float4* __restrict__ l4, const float4* __res
 struct ScoreTcParams {
     int m;
     float tau;
+    float big;                    // 2^k applied to every A row: tau * big in [2^30, 2^31)
     const unsigned* kmax_bits;
     const int32_t* dyn;           // device: { hypotheses (rows of the A matrix), first correspondence tile, end tile }
     int32_t* upper;               // one counter per A row, zeroed by the caller: partial sums are added
@@ -119,23 +120,44 @@ struct ScoreShape {
     }
 };
 
-// 32 residuals of one hypothesis row: FSET.BF (1.0f when |res| < thr) + FADD into four independent
-// accumulators.  Counts stay exact in fp32 up to 2^24 correspondences.
-__device__ __forceinline__ float lt_one(uint32_t bits, float thr)
+// 32 residuals of one hypothesis row -> 1.0f per residual with |res| < thr, summed pairwise into two packed fp32x2
+// accumulators (FADD2).  The indicator comes from two different pipes, alternating by pair, so that neither limits:
+//   * FSET.BF.LT |res|, thr                    (ALU pipe, half rate)
+//   * FADD.SAT thr, -|res|                     (FMA pipe): residuals and threshold arrive scaled by 2^k with thr * 2^k >= 2^30,
+//     so thr - |res| is 0 or at least one ulp >= 128 and the saturation yields exactly 0 or 1 (NaN -> 0, like the compare)
+// 1.5 instructions per residual over two pipes instead of 2 with the ALU pipe saturated.  Counts stay exact in fp32 up to 2^24.
+__device__ __forceinline__ float ind_set(uint32_t bits, float thr)
 {
     float r;
     asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(fabsf(__uint_as_float(bits))), "f"(thr));
     return r;
 }
-__device__ __forceinline__ void count_chunk(const uint32_t (&v)[32], float hi, float (&acc)[4])
+__device__ __forceinline__ float ind_sat(uint32_t bits, float thr)
+{
+    float r;
+    asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(thr), "f"(-fabsf(__uint_as_float(bits))));
+    return r;
+}
+__device__ __forceinline__ void add_pair(unsigned long long& acc, float a, float b)
+{
+    unsigned long long p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(a), "f"(b));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(p));
+}
+__device__ __forceinline__ void count_chunk(const uint32_t (&v)[32], float hi, unsigned long long (&acc)[2])
 {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        acc[0] = __fadd_rn(acc[0], lt_one(v[j], hi));
-        acc[1] = __fadd_rn(acc[1], lt_one(v[j + 1], hi));
-        acc[2] = __fadd_rn(acc[2], lt_one(v[j + 2], hi));
-        acc[3] = __fadd_rn(acc[3], lt_one(v[j + 3], hi));
+        add_pair(acc[0], ind_sat(v[j], hi), ind_sat(v[j + 1], hi));
+        add_pair(acc[1], ind_set(v[j + 2], hi), ind_set(v[j + 3], hi));
     }
+}
+__device__ __forceinline__ int pair_total(const unsigned long long (&acc)[2])
+{
+    float a, b, c, d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(acc[0]));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(acc[1]));
+    return (int)((a + b) + (c + d));
 }
 
 __global__ void __launch_bounds__(S_THREADS, 1)
@@ -178,6 +200,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // the four feeder warps need few registers; the eight epilogue warps take them over (128 accumulator columns in flight)
+    if (warp >= W_ALLOC) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     if (warp == W_TMA) {
         // ================================================================ TMA producer
         if (lane == 0) {
@@ -233,26 +258,30 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
                 tc_commit(&aempty[ab]);
             }
         }
-    } else if (warp < W_ALLOC) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
         // ================================================================ epilogue
         const int ew = warp & 3, cg = warp >> 2;
         const int row = ew * 32 + lane;
         // band around tau inside which the tensor-core value cannot decide the test
         const float kmax = __uint_as_float(*p.kmax_bits);
         const float delta = S_KAPPA * 1.41421356f * kmax;
-        float hi = p.tau + delta;
+        float hi = (p.tau + delta) * p.big;                             // the A operand carries the factor p.big (a power of two)
         if (!(delta < INFINITY)) hi = INFINITY;                         // non-finite input: every finite residual may be an inlier
+        // the threshold is re-read (volatile) after every hand-back of an accumulator: the counting depends on that load, so
+        // the assembler cannot sink the TMEM loads into the counting code and delay the hand-back
+        volatile float* hi_sh = reinterpret_cast<volatile float*>(reinterpret_cast<uint8_t*>(bars) + 192);
+        *hi_sh = hi;
         uint32_t tile_n = 0;
         const ScoreShape sh(p);
         SegIter it(sh.n_htiles, sh.n_ctiles, sh.units_per_cta, blockIdx.x);
         int ht, c0, c1, seg;
         while (it.next(ht, c0, c1, seg)) {
             c0 += sh.ct_begin; c1 += sh.ct_begin;
-            float acc4[S_SUB][4];
+            unsigned long long acc4[S_SUB][2];
 #pragma unroll
-            for (int sub = 0; sub < S_SUB; sub++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) acc4[sub][i] = 0.f;
+            for (int sub = 0; sub < S_SUB; sub++) acc4[sub][0] = acc4[sub][1] = 0ull;
             int pad_total = 0;
             for (int ct = c0; ct < c1; ct++) {
                 const int colbase = ct * SN_ROWS + cg * S_EPI_COLS;
@@ -262,20 +291,26 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
                     mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * SN_ROWS + cg * S_EPI_COLS;
-                    uint32_t va[32], vb[32];
+                    // the warp's 128 columns go to registers at once and the accumulator is handed back before they are
+                    // counted: the next MMA into this accumulator overlaps the counting instead of following it
+                    static_assert(S_EPI_COLS == 128, "four chunks of 32 columns per warp and tile");
+                    uint32_t va[32], vb[32], vc[32], vd[32];
                     tc_ld32(taddr, va);
-#pragma unroll
-                    for (int cc = 0; cc < S_EPI_COLS / 32; cc += 2) {
-                        tc_wait_ld32(va);
-                        tc_ld32(taddr + (cc + 1) * 32, vb);
-                        count_chunk(va, hi, acc4[sub]);
-                        tc_wait_ld32(vb);
-                        if (cc + 2 < S_EPI_COLS / 32) tc_ld32(taddr + (cc + 2) * 32, va);
-                        count_chunk(vb, hi, acc4[sub]);
-                    }
+                    tc_ld32(taddr + 32, vb);
+                    tc_ld32(taddr + 64, vc);
+                    tc_ld32(taddr + 96, vd);
+                    tc_wait_ld32(va);
+                    tc_wait_ld32(vb);
+                    tc_wait_ld32(vc);
+                    tc_wait_ld32(vd);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
+                    const float hv = *hi_sh;
+                    count_chunk(va, hv, acc4[sub]);
+                    count_chunk(vb, hv, acc4[sub]);
+                    count_chunk(vc, hv, acc4[sub]);
+                    count_chunk(vd, hv, acc4[sub]);
                 }
                 // zero-filled columns past m have res = 0 exactly and were counted
                 pad_total += S_EPI_COLS - min(max(p.m - colbase, 0), S_EPI_COLS);
@@ -284,7 +319,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
             for (int sub = 0; sub < S_SUB; sub++) {
                 const int h = (ht * S_SUB + sub) * SM_ROWS + row;
                 if (h < sh.H) {
-                    int n = (int)((acc4[sub][0] + acc4[sub][1]) + (acc4[sub][2] + acc4[sub][3]));
+                    int n = pair_total(acc4[sub]);
                     if (0.f < hi) n -= pad_total;
                     if (n) atomicAdd(p.upper + h, n);
                 }
@@ -396,6 +431,10 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
                   uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best)
 {
     if (m >= (1 << 24)) { set_error("score_tc_best: more than 2^24 correspondences"); return ERP_E_LIMIT; }
+    // power-of-two factor on the hypothesis operand: the scaled threshold lies in [2^30, 2^31) (see count_chunk)
+    int ex = 0;
+    frexpf(tau > 1e-30f ? tau : 1e-30f, &ex);            // tau = f * 2^ex, f in [0.5, 1)
+    const float big = ldexpf(1.0f, 31 - ex);
     int st = ERP_OK;
     float* Es = ctx->scratch<float>(S_SC_E, (size_t)H * 32, &st);
     float* Es2 = ctx->scratch<float>(S_SC_E2, (size_t)H * 32, &st);
@@ -410,7 +449,7 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
     set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(w + W_DYN_A, H, 0, n0);
     ERP_LAUNCH(ctx, "set_dyn_kernel");
     ERP_CUDA(cudaMemsetAsync(upper, 0, sizeof(int32_t) * (size_t)H * 2, ctx->stream));
-    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es, nullptr, nullptr);
+    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es, nullptr, nullptr, big);
     ERP_LAUNCH(ctx, "prep_e_kernel");
     prep_k_kernel<<<cdiv(m, 256), 256, 0, ctx->stream>>>((const float4*)d_l4, (const float4*)d_r4, m, Ks, (unsigned*)(w + W_KMAX));
     ERP_LAUNCH(ctx, "prep_k_kernel");
@@ -419,7 +458,7 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
     ERP_TRY(make_map(&me2, Es2, H, 32, SM_ROWS));
     ERP_TRY(make_map(&mk, Ks, m, 32, SN_ROWS));
     ScoreTcParams p;
-    p.m = m; p.tau = tau; p.kmax_bits = (const unsigned*)(w + W_KMAX);
+    p.m = m; p.tau = tau; p.big = big; p.kmax_bits = (const unsigned*)(w + W_KMAX);
 
     // pass A: every hypothesis, the first n0 correspondence tiles
     p.dyn = w + W_DYN_A; p.upper = upper;
@@ -441,7 +480,7 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
     ERP_LAUNCH(ctx, "survivor_select_kernel");
 
     // pass C: the survivors, tiles [ct1, n_ct)
-    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es2, survivors, w + W_DYN_C);
+    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es2, survivors, w + W_DYN_C, big);
     ERP_LAUNCH(ctx, "prep_e_kernel(survivors)");
     p.dyn = w + W_DYN_C; p.upper = upper2;
     ERP_TRY(launch_score_tc(ctx, me2, mk, p));
