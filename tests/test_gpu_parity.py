@@ -236,8 +236,71 @@ def test_score_counts_bit_exact(ctx, scene, metric, tau, m):
     assert np.array_equal(mask, O.inlier_mask(kp["E"], l[:m], r[:m], metric, tau)) and n == mask.sum() == got[300]
 
 
+@pytest.mark.parametrize("tc_engine", [binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X])
+def test_tcgen05_engine_ties_beyond_list_capacity(ctx, tc_engine):
+    """Several train tiles with far more exact ties than a candidate list holds (40 copies of one row, 30 of a zero
+    row), queries on and next to them, one all-zero query (every score equal): the list floor must bound what was
+    pushed out and everything it cannot prove must come back through the exact re-scan."""
+    rng = np.random.default_rng(11)
+    t = synth.surf_like(3000, 64, rng)
+    q = synth.surf_like(700, 64, rng)
+    copies = rng.permutation(3000)[:40]
+    t[copies] = t[copies[0]]
+    zeros = rng.permutation(np.setdiff1d(np.arange(3000), copies))[:30]
+    t[zeros] = 0
+    q[0] = t[copies[0]]
+    q[1] = t[copies[0]] + np.float32(1e-4) * rng.standard_normal(64).astype(np.float32)
+    q[2] = 0
+    q[3:40] = t[copies[0]] * rng.uniform(0.5, 1.5, (37, 1)).astype(np.float32)
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    eidx, edist = ctx.knn2_raw(q, t)
+    ctx.set_engine(tc_engine)
+    idx, dist = ctx.knn2_raw(q, t)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert np.array_equal(idx, eidx)
+    assert np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
+
+
+def test_host_call_with_query_chunks_equals_single_call(tmp_path):
+    """$ERP_B200_HOST_CHUNKS pipelines the upload of a host-buffer call over query chunks (read once per process):
+    results and statistics must not depend on the cut."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, ".")
+        import erp_match_eightpoint_test_b200 as erp
+        from erp_match_eightpoint_test_b200 import binding, synth
+        q, t, _ = synth.descriptor_pair(3001, 2500, 64, seed=9)
+        ctx = erp.Context(0)
+        for eng in (binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X):
+            ctx.set_engine(eng)
+            idx, dist = ctx.knn2_raw(q, t)
+            m = ctx.knn2_match(q, t, 0.3, True)
+            st = ctx.last_knn_stats()
+            np.save(sys.argv[1] + f"_idx{eng}.npy", idx); np.save(sys.argv[1] + f"_dist{eng}.npy", dist)
+            np.save(sys.argv[1] + f"_m{eng}.npy", m)
+            print(eng, st["rescanned"])
+        ctx.close()
+    """)
+    import os
+    outs = {}
+    for chunks in ("1", "3"):
+        env = dict(os.environ, ERP_B200_HOST_CHUNKS=chunks)
+        base = str(tmp_path / f"c{chunks}")
+        r = subprocess.run([sys.executable, "-c", code, base], env=env, capture_output=True, text=True, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[chunks] = base
+    for eng in (binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X):
+        for what in ("idx", "dist", "m"):
+            a, b = np.load(outs["1"] + f"_{what}{eng}.npy"), np.load(outs["3"] + f"_{what}{eng}.npy")
+            assert a.tobytes() == b.tobytes(), (eng, what)
+
+
 @pytest.mark.parametrize("H,m,tau", [(5000, 3000, 0.002), (129, 257, 0.002), (20000, 777, 0.01), (3000, 3000, 1e-5),
-                                      (1500, 100, 0.002), (40000, 2500, 0.0005)])
+                                      (1500, 100, 0.002), (40000, 2500, 0.0005),
+                                      # the power-of-two scaling of the counting epilogue at both ends of its range
+                                      (3000, 3000, 0.5), (2000, 1000, 4.0), (3000, 3000, 1e-9)])
 def test_tensor_core_best_search_is_exact(ctx, scene, H, m, tau):
     """score_tc.cu bounds every hypothesis' inlier count with a 3xTF32 residual GEMM and re-scores the
     contenders exactly: winner, count (the packed word) and inlier mask must equal the all-SIMT path
