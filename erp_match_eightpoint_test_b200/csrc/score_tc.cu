@@ -283,34 +283,51 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
 #pragma unroll
             for (int sub = 0; sub < S_SUB; sub++) acc4[sub][0] = acc4[sub][1] = 0ull;
             int pad_total = 0;
+            // Software pipeline over the tiles of the segment: while a tile is counted out of registers, the next tile's
+            // accumulator is read into the buffers that have just been consumed (first two chunks after the first half of
+            // the counting, the other two after the second half) and handed back -- the TMEM read latency and the wait
+            // for the MMA hide behind the counting instead of adding to it.
+            static_assert(S_EPI_COLS == 128 && S_SUB == 2, "four chunks of 32 columns per warp and tile, two tiles per round");
+            uint32_t va[32], vb[32], vc[32], vd[32];
+            const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + cg * S_EPI_COLS;
+            if (c0 < c1) {
+                const uint32_t acc = tile_n & 1;
+                mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = lane_base + acc * SN_ROWS;
+                tc_ld32(taddr, va); tc_ld32(taddr + 32, vb); tc_ld32(taddr + 64, vc); tc_ld32(taddr + 96, vd);
+                tc_wait_ld32(va); tc_wait_ld32(vb); tc_wait_ld32(vc); tc_wait_ld32(vd);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                tile_n++;
+            }
             for (int ct = c0; ct < c1; ct++) {
                 const int colbase = ct * SN_ROWS + cg * S_EPI_COLS;
 #pragma unroll
-                for (int sub = 0; sub < S_SUB; sub++, tile_n++) {
+                for (int sub = 0; sub < S_SUB; sub++) {
+                    // registers hold tile (ct, sub); tile_n already names the next one
+                    const bool has_next = sub + 1 < S_SUB || ct + 1 < c1;
                     const uint32_t acc = tile_n & 1;
-                    mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * SN_ROWS + cg * S_EPI_COLS;
-                    // the warp's 128 columns go to registers at once and the accumulator is handed back before they are
-                    // counted: the next MMA into this accumulator overlaps the counting instead of following it
-                    static_assert(S_EPI_COLS == 128, "four chunks of 32 columns per warp and tile");
-                    uint32_t va[32], vb[32], vc[32], vd[32];
-                    tc_ld32(taddr, va);
-                    tc_ld32(taddr + 32, vb);
-                    tc_ld32(taddr + 64, vc);
-                    tc_ld32(taddr + 96, vd);
-                    tc_wait_ld32(va);
-                    tc_wait_ld32(vb);
-                    tc_wait_ld32(vc);
-                    tc_wait_ld32(vd);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    const uint32_t taddr = lane_base + acc * SN_ROWS;
                     const float hv = *hi_sh;
                     count_chunk(va, hv, acc4[sub]);
                     count_chunk(vb, hv, acc4[sub]);
+                    if (has_next) {
+                        mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
+                        tc_fence_after();
+                        tc_ld32(taddr, va); tc_ld32(taddr + 32, vb);
+                    }
                     count_chunk(vc, hv, acc4[sub]);
                     count_chunk(vd, hv, acc4[sub]);
+                    if (has_next) {
+                        tc_ld32(taddr + 64, vc); tc_ld32(taddr + 96, vd);
+                        tc_wait_ld32(va); tc_wait_ld32(vb); tc_wait_ld32(vc); tc_wait_ld32(vd);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                        tile_n++;
+                    }
                 }
                 // zero-filled columns past m have res = 0 exactly and were counted
                 pad_total += S_EPI_COLS - min(max(p.m - colbase, 0), S_EPI_COLS);
