@@ -9,14 +9,22 @@ using namespace cv;
 void feature_matcher::init()
 {
 #ifndef ERP_OPENCV_COMPAT
-    // SURF with OpenCV's defaults, as src/feature_matcher.cpp:13-15 (extended = false: 64-D)
-    detector = xfeatures2d::SURF::create();
-    descriptor_extractor = xfeatures2d::SURF::create();
+    // SURF with OpenCV's defaults, as src/feature_matcher.cpp:13-15 (extended = false: 64-D);
+    // extended_ = true is the 128-D variant (same defaults otherwise: hessianThreshold 100, 4 octaves, 3 layers)
+    detector = xfeatures2d::SURF::create(100, 4, 3, extended_);
+    descriptor_extractor = xfeatures2d::SURF::create(100, 4, 3, extended_);
 #endif
     // no matcher object: the CUDA context is per thread and created on first use
 }
 
 void feature_matcher::deinit() {}
+
+void feature_matcher::set_extended(bool extended_descriptors)
+{
+    if (extended_descriptors == extended_) return;
+    extended_ = extended_descriptors;
+    init();
+}
 
 vector<KeyPoint> feature_matcher::detect_key_point(const Mat &image)
 {

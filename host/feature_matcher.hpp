@@ -38,11 +38,16 @@ public:
     // extensions: Lowe ratio (reference: 0.3f) and mutual-nearest cross-check
     float ratio_thresh = 0.3f;
     bool cross_check = false;
+    // SURF-128: re-creates the detector / extractor with extended descriptors (SURF::create(100, 4, 3, true));
+    // match_two_image itself takes any descriptor width that is a multiple of 4 (64 and 128 run on the tensor cores)
+    void set_extended(bool extended_descriptors);
+    bool extended() const { return extended_; }
 
 private:
 #ifndef ERP_OPENCV_COMPAT
     cv::Ptr<cv::Feature2D> detector;
     cv::Ptr<cv::Feature2D> descriptor_extractor;
 #endif
+    bool extended_ = false;
     std::vector<cv::DMatch> matches;     // last result (draw_match reads it, as in the reference)
 };

@@ -2,14 +2,17 @@
 // (src/automatic.cpp:117-136: match, then eight_point::find), on inputs read from a binary file so
 // that the Python parity test can compare the outputs with the CPU oracle.
 //
-//   dropin_main <in.bin> <out.bin>
+//   dropin_main <in.bin> <out.bin> [estimated_extrinsic.txt]
 // in : int32 nq, nt, dim, W, H | float q[nq*dim] | float t[nt*dim] | float lxy[nq*2] | float rxy[nt*2]
 // out: int32 n_matches | DMatch[n] | float R[3] | float T[3] | int32 v1,v2 | float R1[3],R2[3],Tn[3]
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <vector>
 
 #include "eight_point.hpp"
+#include "extrinsic_log.hpp"
 #include "feature_matcher.hpp"
 
 static void rd(FILE* f, void* p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
@@ -65,6 +68,18 @@ int main(int argc, char** argv)
         fwrite(vv, 4, 2, o);
         fwrite(R1.val, 4, 3, o); fwrite(R2.val, 4, 3, o); fwrite(Tn.val, 4, 3, o);
         fclose(o);
+        if (argc > 3) {
+            // estimated_extrinsic.txt as src/automatic.cpp:128-136 writes it, and back through the parser
+            std::ofstream log(argv[3]);
+            const cv::Vec3d rv(R[0], R[1], R[2]), tv(T[0], T[1], T[2]);
+            erp_host::write_initial_pose(log, rv, tv);
+            log.close();
+            std::ifstream in(argv[3]);
+            cv::Vec3d r2, t2;
+            if (!erp_host::read_initial_pose(in, r2, t2)) { fprintf(stderr, "dropin_main: log does not parse\n"); return 1; }
+            for (int i = 0; i < 3; i++)
+                if (std::fabs(r2[i] - rv[i]) > 1e-5 * (1 + std::fabs(rv[i])) || std::fabs(t2[i] - tv[i]) > 1e-5) { fprintf(stderr, "dropin_main: log round trip\n"); return 1; }
+        }
         DEBUG_PRINT_OUT("matches " << n << "  R " << R[0] << " " << R[1] << " " << R[2] << "  T " << T[0] << " " << T[1] << " " << T[2]);
     } catch (const std::exception& e) {
         fprintf(stderr, "dropin_main: %s\n", e.what());

@@ -51,7 +51,8 @@ def test_host_classes_build_and_refuse_to_run_without_a_gpu(tmp_path):
                  "eight_point::find(int, int, std::vector<cv::KeyPoint", "eight_point::eight_point_estimation(int, int,",
                  "eight_point::initial_guess(int, int,", "random_array::random_array(int)", "erp_rotation::rot2eular(cv::Mat)",
                  "erp_rotation::rotate_image(cv::Mat const&, cv::Mat&)", "erp_rotation::rotate_pixel(",
-                 "epipolar_tool::epipolar_tool(std::vector<cv::KeyPoint", "epipolar_tool::draw_epipole(cv::Mat&)"]:
+                 "epipolar_tool::epipolar_tool(std::vector<cv::KeyPoint", "epipolar_tool::draw_epipole(cv::Mat&)",
+                 "feature_matcher::set_extended(bool)", "erp_host::write_initial_pose(", "erp_host::read_initial_pose("]:
         assert name in syms, name
     import torch
     if torch.cuda.is_available():
@@ -63,13 +64,31 @@ def test_host_classes_build_and_refuse_to_run_without_a_gpu(tmp_path):
     assert r.returncode == 1 and "no CPU fallback" in r.stderr and not out.exists()
 
 
+def test_extrinsic_log_format_and_round_trip(tmp_path):
+    """estimated_extrinsic.txt (src/automatic.cpp:135-136): Euler angles in degrees and the unit translation, each as
+    "[a, b, c]" with six significant digits; the reader skips the other lines and returns radians."""
+    _build()
+    exe = os.path.join(HOST, "_build", "log_main")
+    r = [0.0872664626, -0.1745329252, 0.2617993878]
+    t = [0.3128689, -0.9386067, 0.1042896]
+    log = tmp_path / "estimated_extrinsic.txt"
+    p = subprocess.run([exe, str(log)] + ["%.10g" % x for x in r + t], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    lines = open(log).read().splitlines()
+    assert lines[0] == "match result"
+    assert lines[1] == "initial_R_vector: [%g, %g, %g]" % tuple(180.0 * x / np.pi for x in r)
+    assert lines[2] == "initial_T_vector: [%g, %g, %g]" % tuple(t)
+    back = [float(x) for x in p.stdout.split()]
+    assert np.allclose(back[:3], r, rtol=1e-5) and np.allclose(back[3:], t, rtol=1e-5)      # six significant digits
+
+
 @pytest.mark.gpu
 def test_dropin_driver_matches_oracle(tmp_path):
     _build()
     q, t, lxy, rxy, W, H = _scene()
-    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    inp, out, log = tmp_path / "in.bin", tmp_path / "out.bin", tmp_path / "estimated_extrinsic.txt"
     _write_input(inp, q, t, lxy, rxy, W, H)
-    r = subprocess.run([EXE, str(inp), str(out)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([EXE, str(inp), str(out), str(log)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     raw = open(out, "rb").read()
     n = struct.unpack_from("<i", raw, 0)[0]
@@ -90,3 +109,8 @@ def test_dropin_driver_matches_oracle(tmp_path):
     b = np.abs(R1 - e["R2"]).max() + np.abs(R2 - e["R1"]).max()
     assert min(a, b) < 2e-5 and np.abs(np.abs(Tn) - np.abs(e["T"])).max() < 1e-5
     assert set(v.tolist()) <= {0, 1}
+    # estimated_extrinsic.txt: the two lines of src/automatic.cpp:135-136, degrees then unit translation, "%g" numbers
+    deg = [180.0 * float(x) / np.pi for x in R]
+    want_log = ("initial_R_vector: [%g, %g, %g]\ninitial_T_vector: [%g, %g, %g]\n"
+                % (deg[0], deg[1], deg[2], float(T[0]), float(T[1]), float(T[2])))
+    assert open(log).read() == want_log
