@@ -75,6 +75,22 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with A read from tensor memory (lane = row, one tf32 per column): only B is fetched from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory -> tensor memory, 128 rows x 32 bytes (8 columns) of the matrix a K-major descriptor names; asynchronous,
+// ordered with the MMAs the same thread issues afterwards
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t s_desc)
+{
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
+}
 // 32 lanes x 32 consecutive columns: thread i of the warp receives lane (base + i)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
