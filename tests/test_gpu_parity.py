@@ -456,6 +456,34 @@ def test_cfg3_full_size_tensor_core_equals_exact_engine(ctx):
     assert max(a["packed"], b["packed"]) == res["packed"]
 
 
+def test_cfg4_full_size_surf128_cross_check_properties(ctx):
+    """configs[3] at full size: 200k x 200k SURF-128 with cross-check (4e10 dist-evals each way) through the host-buffer
+    call.  Size-independent properties: every planted pair is found and nothing else passes ratio + cross-check;
+    records ascend; matching t -> q gives the mirrored pairs; a sub-sample of the rows equals the fp64 SIMT engine
+    bit for bit and a smaller one equals the oracle."""
+    n = 200000
+    q, t, planted = synth.descriptor_pair(n, n, 128, seed=synth.SEED_BASE + 5)
+    m = ctx.knn2_match(q, t, ratio=0.3, cross_check=True)
+    st = ctx.last_knn_stats()
+    assert st["engine"] == binding.ENGINE_TCGEN05_1X and st["rescanned"] <= n // 100, st
+    assert len(m) == (planted >= 0).sum() and (planted[m["queryIdx"]] == m["trainIdx"]).all()
+    assert (np.diff(m["queryIdx"]) > 0).all() and (m["imgIdx"] == 0).all()
+    a = ctx.knn2_match(q, t, ratio=-1.0, cross_check=True)
+    b = ctx.knn2_match(t, q, ratio=-1.0, cross_check=True)
+    assert len(a) == len(b)
+    order = np.lexsort((b["queryIdx"], b["trainIdx"]))
+    assert np.array_equal(a["queryIdx"], b["trainIdx"][order]) and np.array_equal(a["trainIdx"], b["queryIdx"][order])
+    idx, dist = ctx.knn2_raw(q, t)
+    sub = np.arange(0, n, 97)
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    eidx, edist = ctx.knn2_raw(q[sub], t)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert np.array_equal(idx[sub], eidx) and np.array_equal(dist[sub].view(np.uint32), edist.view(np.uint32))
+    tiny = sub[::32]
+    oidx, odist, _ = O.knn2(q[tiny], t)
+    assert np.array_equal(idx[tiny], oidx) and np.array_equal(dist[tiny], odist)
+
+
 @pytest.mark.parametrize("engine", [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X])
 def test_cfg4_style_surf128_cross_check(ctx, engine):
     """configs[3] reduced: extended 128-D descriptors with cross-check matching, both engines."""
