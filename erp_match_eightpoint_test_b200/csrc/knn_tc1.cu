@@ -31,14 +31,22 @@ constexpr int F_MAX_SEG = 64 / (F_TOPK * F_EPI_GROUPS);     // 4 segments per qu
 constexpr int F_AUG_T = F_BN * 32;        // 8 KB: one extra k step (8 floats) per train row, 32-byte swizzle rows
 constexpr int F_AUG_Q = F_BM * 32;        // 4 KB: the constant query side of that k step
 constexpr int F_BARS = 256;               // mbarriers + TMEM slot
-#ifndef ERP_EXP
-#define ERP_EXP 0
+// Instrumented builds (scripts/build_variant.sh N): -DERP_TC_COUNTERS=1 adds clock64 phase timers to the MMA issuer and the
+// epilogue warps, =2 counts and times the insert path (tc_common.cuh); both print after every launch.  Off by default.
+#ifndef ERP_TC_COUNTERS
+#define ERP_TC_COUNTERS 0
 #endif
-#if ERP_EXP == 13
-static __device__ unsigned long long erp_clk[16];
-#define CLK_ADD(i, v) (lclk[i] += (unsigned long long)(v))
-#define CLK_DECL unsigned long long lclk[6] = {0, 0, 0, 0, 0, 0}
-#define CLK_FLUSH for (int i_ = 0; i_ < 6; i_++) if (lclk[i_]) atomicAdd(&erp_clk[i_], lclk[i_])
+#if ERP_TC_COUNTERS == 1
+static __device__ unsigned long long erp_clk[8];
+#define TCC_DECL unsigned long long lclk[6] = {0, 0, 0, 0, 0, 0}
+#define TCC_CLOCK(name) const long long name = clock64()
+#define TCC_ADD(i, v) (lclk[i] += (unsigned long long)(v))
+#define TCC_FLUSH() do { if ((threadIdx.x & 31) == 0) for (int i_ = 0; i_ < 6; i_++) if (lclk[i_]) atomicAdd(&erp_clk[i_], lclk[i_]); } while (0)
+#else
+#define TCC_DECL
+#define TCC_CLOCK(name)
+#define TCC_ADD(i, v)
+#define TCC_FLUSH()
 #endif
 // |s_tc - s_exact| <= 2^-10 (|q|^2 + max|t|^2) in the worst case: both operands are rounded to 11
 // significant bits (relative error 2^-11 each), products are exact, and 2|q||t| <= |q|^2 + |t|^2;
@@ -158,9 +166,7 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     float* thr_sh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + F_BARS);   // SHARE: [F_SUB][F_BM] row thresholds
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#if ERP_EXP == 13
-    CLK_DECL;
-#endif
+    TCC_DECL;
     constexpr int W_ALLOC = F_EPI_THREADS / 32, W_NORM = W_ALLOC + 1, W_TMA = W_ALLOC + 2, W_MMA = W_ALLOC + 3;
 
     if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_t); if (FOLD) tma_prefetch_desc(&map_aug); }
@@ -232,24 +238,16 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                     for (int sub = 0; sub < F_SUB; sub++, tile_n++) {
                         const uint32_t acc = tile_n & 1;
-#if ERP_EXP == 13
-                        long long m0 = clock64();
-#endif
+                        TCC_CLOCK(m0);
                         mbar_wait(&tempty[acc], ((tile_n >> 1) & 1) ^ 1);
-#if ERP_EXP == 13
-                        long long m1 = clock64(); CLK_ADD(3, m1 - m0); CLK_ADD(4, 1);
-#endif
+                        TCC_ADD(3, clock64() - m0); TCC_ADD(4, 1);
                         const uint32_t d_tmem = tmem_base + acc * F_BN;
                         uint32_t sl = s0, pp = p0;
 #pragma unroll
                         for (int c = 0; c < KCH; c++) {
-#if ERP_EXP == 13
-                            long long f0 = clock64();
-#endif
+                            TCC_CLOCK(f0);
                             if (sub == 0) mbar_wait(&full[sl], pp);
-#if ERP_EXP == 13
-                            CLK_ADD(5, clock64() - f0);
-#endif
+                            TCC_ADD(5, clock64() - f0);
                             tc_fence_after();
                             const uint32_t a = q_base + (sub * KCH + c) * F_QCH, b = t_base + sl * F_TCH;
 #pragma unroll
@@ -334,13 +332,9 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
                 for (int sub = 0; sub < F_SUB; sub++, tile_n++) {
                     const uint32_t acc = tile_n & 1;
-#if ERP_EXP == 13
-                    long long c0 = clock64();
-#endif
+                    TCC_CLOCK(c0);
                     mbar_wait(&tfull[acc], (tile_n >> 1) & 1);
-#if ERP_EXP == 13
-                    long long c1 = clock64();
-#endif
+                    TCC_CLOCK(c1);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * F_BN + cg * F_EPI_COLS;
                     // all four chunks of this warp's share go to registers at once (the epilogue warps hold 224 registers, see
@@ -370,9 +364,7 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[acc]);
                     }
-#if ERP_EXP == 13
-                    if (lane == 0) { long long c2 = clock64(); CLK_ADD(0, c1 - c0); CLK_ADD(1, c2 - c1); CLK_ADD(2, 1); }
-#endif
+                    TCC_ADD(0, c1 - c0); TCC_ADD(1, clock64() - c1); TCC_ADD(2, 1);
                 }
                 if (!FOLD) {
                     __syncwarp();
@@ -395,9 +387,7 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
     }
 
-#if ERP_EXP == 13
-    if (lane == 0) { CLK_FLUSH; }
-#endif
+    TCC_FLUSH();
     tc_fence_before();
     __syncthreads();
     if (warp == W_ALLOC) {
@@ -406,7 +396,7 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
-#if ERP_EXP == 14
+#if ERP_TC_COUNTERS == 2
 __global__ void dbg_print_kernel()
 {
     printf("warp-events (first lane) steady %llu, %.0f clk each; warm-up %llu, %.0f clk each\n", erp_evt[1], (double)erp_evt[0] / erp_evt[1], erp_evt[3], (double)erp_evt[2] / erp_evt[3]);
@@ -414,12 +404,12 @@ __global__ void dbg_print_kernel()
     for (int i = 0; i < 8; i++) erp_evt[i] = 0;
 }
 #endif
-#if ERP_EXP == 13
+#if ERP_TC_COUNTERS == 1
 __global__ void dbg_print_kernel()
 {
     printf("epi: wait_tfull %.0f scan %.0f per warp-tile (%llu warp-tiles) | mma: wait_tempty %.0f wait_full(sum over chunks) %.0f per tile (%llu tiles)\n",
            (double)erp_clk[0] / erp_clk[2], (double)erp_clk[1] / erp_clk[2], erp_clk[2], (double)erp_clk[3] / erp_clk[4], (double)erp_clk[5] / erp_clk[4], erp_clk[4]);
-    for (int i = 0; i < 16; i++) erp_clk[i] = 0;
+    for (int i = 0; i < 8; i++) erp_clk[i] = 0;
 }
 #endif
 template <int KCH>
@@ -434,7 +424,7 @@ static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt
     }
     knn2_tc1_kernel<KCH><<<grid, F_THREADS, smem, ctx->stream>>>(mq, mt, ma, p);
     ERP_LAUNCH(ctx, "knn2_tc1_kernel");
-#if ERP_EXP == 13 || ERP_EXP == 14
+#if ERP_TC_COUNTERS
     dbg_print_kernel<<<1, 1, 0, ctx->stream>>>();
     cudaStreamSynchronize(ctx->stream);
 #endif

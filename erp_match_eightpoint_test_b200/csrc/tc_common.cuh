@@ -314,7 +314,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t tad
 // and inserted smallest first.  With SHARE the threshold is also exchanged through shared memory with the thread that scans
 // the other column range of the same row; any published value is a valid bound, so a lost race only costs pruning.
 // With FOLD the accumulator already holds |t|^2 - 2 q.t (the norm entered the MMA as an extra k step).
-#if defined(ERP_EXP) && ERP_EXP == 14
+#if defined(ERP_TC_COUNTERS) && ERP_TC_COUNTERS == 2
 static __device__ unsigned long long erp_evt[8];
 #endif
 template <bool SHARE, bool FOLD>
@@ -343,7 +343,7 @@ __device__ __forceinline__ void scan_chunk_lean(const uint32_t (&v)[32], const f
     if (SHARE) floor_thr = thr;
     if (fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])) < thr) {                                     // rare, per lane
         unsigned mine = (gm[0] < thr ? 1u : 0u) | (gm[1] < thr ? 2u : 0u) | (gm[2] < thr ? 4u : 0u) | (gm[3] < thr ? 8u : 0u);
-#if defined(ERP_EXP) && ERP_EXP == 14
+#if defined(ERP_TC_COUNTERS) && ERP_TC_COUNTERS == 2
         const long long e0 = clock64();
         atomicAdd(&erp_evt[4], 1ull);
 #endif
@@ -357,7 +357,7 @@ __device__ __forceinline__ void scan_chunk_lean(const uint32_t (&v)[32], const f
                 const float4 na = tn4[g * 2], nb = tn4[g * 2 + 1];
                 nrm[0] = na.x; nrm[1] = na.y; nrm[2] = na.z; nrm[3] = na.w; nrm[4] = nb.x; nrm[5] = nb.y; nrm[6] = nb.z; nrm[7] = nb.w;
             }
-#if defined(ERP_EXP) && ERP_EXP == 14
+#if defined(ERP_TC_COUNTERS) && ERP_TC_COUNTERS == 2
             atomicAdd(&erp_evt[5], 1ull);
 #endif
             float k[8];
@@ -372,7 +372,7 @@ __device__ __forceinline__ void scan_chunk_lean(const uint32_t (&v)[32], const f
             for (;;) {
                 const float km = fminf(fminf(fminf(k[0], k[1]), fminf(k[2], k[3])), fminf(fminf(k[4], k[5]), fminf(k[6], k[7])));
                 if (!(km < thr)) break;
-#if defined(ERP_EXP) && ERP_EXP == 14
+#if defined(ERP_TC_COUNTERS) && ERP_TC_COUNTERS == 2
                 atomicAdd(&erp_evt[6], 1ull);
 #endif
                 const int col = cbase + (int)(__float_as_uint(km) & 7u);
@@ -399,7 +399,7 @@ __device__ __forceinline__ void scan_chunk_lean(const uint32_t (&v)[32], const f
         if (SHARE) {
             if (thr < *reinterpret_cast<volatile float*>(row_thr)) *reinterpret_cast<volatile float*>(row_thr) = thr;
         }
-#if defined(ERP_EXP) && ERP_EXP == 14
+#if defined(ERP_TC_COUNTERS) && ERP_TC_COUNTERS == 2
         const long long e1 = clock64();
         {
             const unsigned am = __activemask();
