@@ -330,9 +330,7 @@ def run_gpu(args, cfg):
         # the caller's gather of the matched keypoints (automatic.cpp's loop): 8-byte rows, one take() each
         lxy = np.take(left8, np.ascontiguousarray(mt["queryIdx"]).astype(np.int64) + qlo).view(np.float32).reshape(-1, 2)
         rxy = np.take(right8, np.ascontiguousarray(mt["trainIdx"]).astype(np.int64)).view(np.float32).reshape(-1, 2)
-        l3 = ctx.bearings(lxy, cfg["W"], cfg["H"])
-        r3 = ctx.bearings(rxy, cfg["W"], cfg["H"])
-        r_e2e = ctx.ransac(l3, r3, 1, hlo, hhi - hlo, SAMPLE, METRIC, TAU)            # H2D bearings; D2H result + mask
+        r_e2e = ctx.ransac_pixels(lxy, rxy, cfg["W"], cfg["H"], 1, hlo, hhi - hlo, SAMPLE, METRIC, TAU)   # H2D keypoints; D2H result + mask
         c = time.perf_counter()
         if it > 0:
             t_e2e_match += b - a
@@ -341,8 +339,8 @@ def run_gpu(args, cfg):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e_match, t_e2e_ransac = [float(x) for x in te.tolist()]
-    h2d = pq.nbytes + pt.nbytes + 2 * len(mt) * 8 + 2 * len(mt) * 24
-    d2h = len(mt) * 16 + 2 * len(mt) * 24 + len(mt) + 256
+    h2d = pq.nbytes + pt.nbytes + 2 * len(mt) * 8
+    d2h = len(mt) * 16 + len(mt) + 256
 
     stats = ctx.last_knn_stats()
     # the spec's arithmetic (3xTF32 tiles, knn_tc.cu) timed beside the default engine: same inputs, same results
@@ -450,7 +448,7 @@ def run_gpu(args, cfg):
                 "unit": "dist-evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "match_ms": 1e3 * t_e2e_match / e2e_steps, "ransac_ms": 1e3 * t_e2e_ransac / e2e_steps,
                 "ransac_hyps_per_s": hyps_total * e2e_steps / t_e2e_ransac, "steps": e2e_steps,
-                "api": "erp_knn2_match + erp_bearings_from_pixels + erp_ransac (host buffers)"},
+                "api": "erp_knn2_match + erp_ransac_pixels (host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
         "check": {"matches": m, "planted": n_pl, "E_refit_err": e_err, "inliers": res["count"], "rescanned": stats["rescanned"]},
         "wall_s_timed_region": wall,

@@ -84,6 +84,8 @@ _SIGNATURES = {
     "erp_refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "erp_ransac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                              C.c_float, C.POINTER(RansacResult), C.c_void_p]),
+    "erp_ransac_pixels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64,
+                                    C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(RansacResult), C.c_void_p]),
     "erp_ransac_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                        C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "erp_ransac_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
@@ -344,6 +346,17 @@ class Context:
         mask = np.empty(l3.shape[0], np.uint8)
         _check(lib().erp_ransac(self._h, _ptr(l3), _ptr(r3), l3.shape[0], seed, hyp_offset, H, S, metric, tau,
                                 C.byref(res), _ptr(mask)))
+        out = self._result(res)
+        out["mask"] = mask
+        return out
+
+    def ransac_pixels(self, left_xy, right_xy, W, H_img, seed, hyp_offset, H, S=8, metric=METRIC_ALGEBRAIC, tau=0.002):
+        """erp_ransac_pixels: matched keypoints (n x 2 float32 pixel pairs) -> pose; the bearings stay on the device."""
+        left_xy, right_xy = _f32(left_xy), _f32(right_xy)
+        res = RansacResult()
+        mask = np.empty(left_xy.shape[0], np.uint8)
+        _check(lib().erp_ransac_pixels(self._h, W, H_img, _ptr(left_xy), _ptr(right_xy), left_xy.strides[0], left_xy.shape[0],
+                                       seed, hyp_offset, H, S, metric, tau, C.byref(res), _ptr(mask)))
         out = self._result(res)
         out["mask"] = mask
         return out

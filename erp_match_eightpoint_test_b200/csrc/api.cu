@@ -603,6 +603,40 @@ ERP_API int erp_ransac(erp_ctx* ctx, const double* l3, const double* r3, int m, 
     return ERP_OK;
 }
 
+ERP_API int erp_ransac_pixels(erp_ctx* ctx, int width, int height, const void* left_xy, const void* right_xy,
+                              size_t stride_bytes, int m, uint64_t seed, uint64_t hyp_offset, int H, int S, int metric,
+                              float tau, erp_ransac_result* result, uint8_t* mask)
+{
+    ERP_ARG(ctx && result && H >= 1 && width > 0 && height > 0, ERP_E_ARG, "erp_ransac_pixels: bad argument");
+    ERP_ARG(stride_bytes >= 8 && stride_bytes % 4 == 0, ERP_E_ARG, "erp_ransac_pixels: bad stride %zu", stride_bytes);
+    ERP_ARG(m >= S && S >= 8, ERP_E_TOO_FEW_POINTS, "erp_ransac_pixels: %d correspondences for sample size %d", m, S);
+    ERP_ARG(left_xy && right_xy, ERP_E_ARG, "erp_ransac_pixels: null keypoints");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    float* d_xy = ctx->scratch<float>(S_XY, (size_t)m * 4, &st);                 // left pairs, then right pairs
+    double* dl = ctx->scratch<double>(S_L3, (size_t)m * 3 + 4, &st);
+    double* dr = ctx->scratch<double>(S_R3, (size_t)m * 3 + 4, &st);
+    float* dl4 = ctx->scratch<float>(S_L4, (size_t)m * 4 + 4, &st);
+    float* dr4 = ctx->scratch<float>(S_R4, (size_t)m * 4 + 4, &st);
+    uint64_t* d_packed = ctx->scratch<uint64_t>(S_PACKED, 2, &st);
+    uint8_t* d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m + 4, &st);
+    ERP_TRY(st);
+    ERP_TRY(upload_rows(ctx, d_xy, left_xy, m, 8, stride_bytes));
+    ERP_TRY(upload_rows(ctx, d_xy + (size_t)m * 2, right_xy, m, 8, stride_bytes));
+    ERP_TRY(erp_bearings_dev(ctx, d_xy, 8, m, width, height, dl, dl4));
+    ERP_TRY(erp_bearings_dev(ctx, d_xy + (size_t)m * 2, 8, m, width, height, dr, dr4));
+    ERP_TRY(erp_ransac_local_dev(ctx, dl, dr, dl4, dr4, m, seed, hyp_offset, H, S, metric, tau, d_packed));
+    uint64_t packed = 0;
+    ERP_CUDA(cudaMemcpyAsync(&packed, d_packed, sizeof packed, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ERP_TRY(erp_ransac_finish_dev(ctx, dl, dr, dl4, dr4, m, seed, packed, S, metric, tau, d_mask, result));
+    if (mask) {
+        ERP_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return ERP_OK;
+}
+
 // ======================================================================================
 // reference mode: initial_guess / find
 // ======================================================================================

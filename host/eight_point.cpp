@@ -65,6 +65,20 @@ int eight_point::ransac(vector<Point3d>& l, vector<Point3d>& r, int match_size, 
     return res.count;
 }
 
+int eight_point::ransac(int im_width, int im_height, vector<KeyPoint>& kl, vector<KeyPoint>& kr, int match_size, int hypotheses,
+                        unsigned long long seed, double E_out[9], Vec3f& R1_vec, Vec3f& R2_vec, Vec3f& T_vec,
+                        vector<unsigned char>* inlier_mask)
+{
+    erp_ransac_result res;
+    if (inlier_mask) inlier_mask->resize(match_size);
+    erp_host::check(erp_ransac_pixels(erp_host::context(), im_width, im_height, &kl[0].pt, &kr[0].pt, sizeof(KeyPoint), match_size,
+                                      seed, 0, hypotheses, 8, ERP_METRIC_ALGEBRAIC, 0.002f, &res,
+                                      inlier_mask ? inlier_mask->data() : nullptr), "eight_point::ransac");
+    for (int i = 0; i < 9; i++) E_out[i] = res.E_refit[i];
+    for (int i = 0; i < 3; i++) { R1_vec[i] = res.pose[i]; R2_vec[i] = res.pose[3 + i]; T_vec[i] = res.pose[6 + i]; }
+    return res.count;
+}
+
 random_array::random_array(int size) : size_(size), rand_arr(size > 0 ? size : 0), count_(0)
 {
     if (size > 0) erp_host::check(erp_libstdcxx_sample_table(size, 1, size, 1, rand_arr.data()), "random_array");

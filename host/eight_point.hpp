@@ -32,6 +32,12 @@ public:
                int match_size, int hypotheses, unsigned long long seed, double E_out[9],
                cv::Vec3f& R1_vec, cv::Vec3f& R2_vec, cv::Vec3f& T_vec, std::vector<unsigned char>* inlier_mask = nullptr);
 
+    // ... and on the matched keypoints, with find's argument list: pixels -> bearings -> RANSAC in one device round trip
+    int ransac(int im_width, int im_height
+               , std::vector<cv::KeyPoint>& key_point_left, std::vector<cv::KeyPoint>& key_point_right
+               , int match_size, int hypotheses, unsigned long long seed, double E_out[9]
+               , cv::Vec3f& R1_vec, cv::Vec3f& R2_vec, cv::Vec3f& T_vec, std::vector<unsigned char>* inlier_mask = nullptr);
+
 private:
     erp_rotation erp_rot;
     double max_vec(cv::Vec3f& vec);

@@ -190,6 +190,13 @@ int erp_refit(erp_ctx* ctx, const double* l3, const double* r3, int m, const uin
 int erp_ransac(erp_ctx* ctx, const double* l3, const double* r3, int m, uint64_t seed,
                uint64_t hyp_offset, int H, int S, int metric, float tau,
                erp_ransac_result* result, uint8_t* mask /* m or NULL */);
+/* the same on the matched KEYPOINTS (the argument list of eight_point::find, src/eight_point.cpp:152-192, with the
+ * RANSAC parameters instead of the 80-round schedule): pixels -> bearings (src/eight_point.cpp:163-186) -> RANSAC on the
+ * device; the bearings never travel.  left_xy / right_xy: first two floats of every stride_bytes record (8 = packed
+ * xy pairs, 28 = cv::KeyPoint). */
+int erp_ransac_pixels(erp_ctx* ctx, int width, int height, const void* left_xy, const void* right_xy,
+                      size_t stride_bytes, int m, uint64_t seed, uint64_t hyp_offset, int H, int S, int metric,
+                      float tau, erp_ransac_result* result, uint8_t* mask /* m or NULL */);
 /* sharded form: every rank scores its hypothesis range and leaves its packed best in
  * d_packed (one uint64 on the device); the caller max-reduces it across ranks (one 8-byte
  * NCCL allreduce) and calls erp_ransac_finish_dev with the winning packed value. */

@@ -337,6 +337,22 @@ def test_tensor_core_best_search_with_pruning(ctx, m, outliers, H):
         assert e_dist(tc["E_refit"], kp["E"]) < 2e-2
 
 
+def test_ransac_on_keypoints_equals_ransac_on_bearings(ctx):
+    """erp_ransac_pixels = erp_bearings_from_pixels (both views) + erp_ransac without the round trip of the bearings."""
+    kp = synth.keypoint_pair(5000, 8192, 4096, seed=77)
+    l, r = ctx.bearings(kp["left_xy"], 8192, 4096), ctx.bearings(kp["right_xy"], 8192, 4096)
+    a = ctx.ransac(l, r, seed=3, hyp_offset=5, H=20000, S=8, metric=0, tau=0.002)
+    b = ctx.ransac_pixels(kp["left_xy"], kp["right_xy"], 8192, 4096, seed=3, hyp_offset=5, H=20000, S=8, metric=0, tau=0.002)
+    assert a["packed"] == b["packed"] and a["count"] == b["count"] and np.array_equal(a["mask"], b["mask"])
+    assert np.array_equal(a["E_refit"], b["E_refit"]) and np.array_equal(a["pose"], b["pose"])
+    # cv::KeyPoint records (28 bytes, pt first)
+    rec = np.zeros((5000, 7), np.float32)
+    rec[:, :2] = kp["left_xy"]
+    c = ctx.ransac_pixels(rec, np.concatenate([kp["right_xy"], np.zeros((5000, 5), np.float32)], axis=1), 8192, 4096,
+                          seed=3, hyp_offset=5, H=20000)
+    assert c["packed"] == a["packed"]
+
+
 def test_refit_on_inliers(ctx, scene):
     kp, l, r = scene
     mask = O.inlier_mask(kp["E"], l, r)
