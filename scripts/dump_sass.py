@@ -21,7 +21,8 @@ for line in txt.splitlines():
         continue
     if cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
         kernels[cur].append(re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", line).rstrip())
-FULL = {"knn2_tc_kernelILi2": "knn2_tc_kernel_D64.sass", "score_tc_kernel": "score_tc_kernel.sass"}
+FULL = {"knn2_tc_kernelILi2": "knn2_tc_kernel_D64.sass", "knn2_tc1_kernelILi2": "knn2_tc1_kernel_D64.sass", "knn2_tc1_kernelILi4": "knn2_tc1_kernel_D128.sass",
+        "score_tc_kernel": "score_tc_kernel.sass", "min8_kernelILb0": "min8_kernel.sass", "refine_kernel": "refine_kernel.sass"}
 with open(os.path.join(OUT, "opcode_histogram.txt"), "w") as f:
     f.write("# per kernel: instruction count and the opcodes that prove the Blackwell path\n"
             "# (UTC*MMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA tensor load, UBLKCP = bulk copy, SYNCS = mbarrier)\n")
