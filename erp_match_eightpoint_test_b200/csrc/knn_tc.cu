@@ -88,7 +88,8 @@ split_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
             float f = row < n ? (float)acc : INFINITY;
             norm[row] = f;
             // non-negative floats (and +inf, NaN) order like their bit patterns
-            if (row < n) atomicMax(max_bits, __float_as_uint(f));
+            // one hot word for the whole array: read it first, the atomic only fires while the maximum still grows
+            if (row < n && __float_as_uint(f) > *reinterpret_cast<volatile unsigned*>(max_bits)) atomicMax(max_bits, __float_as_uint(f));
         }
     }
 }
@@ -346,33 +347,61 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
     for (int o = 16; o > 0; o >>= 1) thr = fminf(thr, __shfl_xor_sync(0xffffffffu, thr, o));
 
     // exact distances of the candidates that matter: a listed column whose approximate score is not below that bound
-    // is covered by the certificate like any unlisted column, so its exact distance is not needed
+    // is covered by the certificate like any unlisted column, so its exact distance is not needed.  The ones that are left
+    // (usually two to six of the 64 slots) are compacted through shared memory so that one pass of the warp evaluates
+    // them, and the query row is converted to fp64 ONCE per warp (the fp32 -> fp64 conversions, not the FMAs, were the
+    // limiter: 128 per candidate).  Each candidate still gets the oracle's fma chain in the oracle's order.
+    __shared__ double q_sh[8][128];
+    __shared__ int c_idx[8][64];
+    __shared__ float c_sc[8][64];
+    const int wq = threadIdx.x >> 5;
+    for (int k = lane; k < dim; k += 32) q_sh[wq][k] = (double)qr[k];
+    int n_act;
+    {
+        int ti[2];
+        float s2[2];
+        bool act[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int c = lane + 32 * s;
+            ti[s] = c < ncand ? cand_idx[(size_t)qi * ncand + c] : -1;
+            s2[s] = (c < ncand && ti[s] >= 0) ? cand_s[(size_t)qi * ncand + c] : INFINITY;   // unused list slots are -1 / unset
+            act[s] = ti[s] >= 0 && ti[s] < nt && (s2[s] < thr || !(thr < INFINITY));
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, act[0]), m1 = __ballot_sync(0xffffffffu, act[1]);
+        const unsigned lt = (1u << lane) - 1u;
+        if (act[0]) { const int pos = __popc(m0 & lt); c_idx[wq][pos] = ti[0]; c_sc[wq][pos] = s2[0]; }
+        if (act[1]) { const int pos = __popc(m0) + __popc(m1 & lt); c_idx[wq][pos] = ti[1]; c_sc[wq][pos] = s2[1]; }
+        n_act = __popc(m0) + __popc(m1);
+    }
+    __syncwarp();
     double d[2];
     int id[2];
     float sc[2];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        int c = lane + 32 * s;
-        int ti = c < ncand ? cand_idx[(size_t)qi * ncand + c] : -1;
-        sc[s] = (c < ncand && ti >= 0) ? cand_s[(size_t)qi * ncand + c] : INFINITY;   // unused list slots are -1 / unset
-        d[s] = INFINITY; id[s] = 0x7fffffff;
-        if (ti >= 0 && ti < nt && (sc[s] < thr || !(thr < INFINITY))) {
-            const float* tr = t + (size_t)ti * dim;
-            double a = 0.0;
-            for (int k = 0; k < dim; k += 4) {
-                float4 x = *reinterpret_cast<const float4*>(qr + k);
-                float4 y = *reinterpret_cast<const float4*>(tr + k);
-                double e;
-                e = __dsub_rn((double)x.x, (double)y.x); a = __fma_rn(e, e, a);
-                e = __dsub_rn((double)x.y, (double)y.y); a = __fma_rn(e, e, a);
-                e = __dsub_rn((double)x.z, (double)y.z); a = __fma_rn(e, e, a);
-                e = __dsub_rn((double)x.w, (double)y.w); a = __fma_rn(e, e, a);
+        const int c = lane + 32 * s;
+        d[s] = INFINITY; id[s] = 0x7fffffff; sc[s] = INFINITY;
+        if (32 * s < n_act) {                                  // warp-uniform: the second pass rarely runs
+            if (c < n_act) {
+                const int ti = c_idx[wq][c];
+                sc[s] = c_sc[wq][c];
+                const float* tr = t + (size_t)ti * dim;
+                double a = 0.0;
+                for (int k = 0; k < dim; k += 4) {
+                    float4 y = *reinterpret_cast<const float4*>(tr + k);
+                    double e;
+                    e = __dsub_rn(q_sh[wq][k], (double)y.x); a = __fma_rn(e, e, a);
+                    e = __dsub_rn(q_sh[wq][k + 1], (double)y.y); a = __fma_rn(e, e, a);
+                    e = __dsub_rn(q_sh[wq][k + 2], (double)y.z); a = __fma_rn(e, e, a);
+                    e = __dsub_rn(q_sh[wq][k + 3], (double)y.w); a = __fma_rn(e, e, a);
+                }
+                d[s] = a; id[s] = ti;
             }
-            d[s] = a; id[s] = ti;
         }
     }
     double qn = 0.0;
-    for (int k = lane; k < dim; k += 32) { double x = (double)qr[k]; qn += x * x; }
+    for (int k = lane; k < dim; k += 32) { double x = q_sh[wq][k]; qn += x * x; }
     for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
     const double tn_max = (double)__uint_as_float(misc[1]);
     const double scale = qn + tn_max;
@@ -400,7 +429,8 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
     }
 
     if (lane == 0) {
-        if (dev > 0.f) atomicMax(misc + 2, __float_as_uint(dev));
+        // (same-address atomics from every warp were the whole cost of this kernel: 135 us for 100k queries)
+        if (dev > 0.f && __float_as_uint(dev) > *reinterpret_cast<volatile unsigned*>(misc + 2)) atomicMax(misc + 2, __float_as_uint(dev));
         const double eps = kappa * scale;
         // non-finite input anywhere (NaN compares false, inf norms) -> exact re-scan
         bool finite_in = scale < (double)INFINITY && scale == scale;

@@ -105,7 +105,8 @@ round_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
                 *reinterpret_cast<float4*>(aug + (size_t)row * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             // non-negative floats (and +inf, NaN) order like their bit patterns
-            if (row < n) atomicMax(max_bits, __float_as_uint(f));
+            // one hot word for the whole array: read it first, the atomic only fires while the maximum still grows
+            if (row < n && __float_as_uint(f) > *reinterpret_cast<volatile unsigned*>(max_bits)) atomicMax(max_bits, __float_as_uint(f));
         }
     }
 }

@@ -93,7 +93,7 @@ __global__ void prep_k_kernel(const float4* __restrict__ l4, const float4* __res
     // non-negative floats (inf, NaN included) order like their bit patterns
     unsigned b = __float_as_uint(nrm);
     b = __reduce_max_sync(0xffffffffu, b);
-    if ((threadIdx.x & 31) == 0 && b) atomicMax(kmax_bits, b);
+    if ((threadIdx.x & 31) == 0 && b > *reinterpret_cast<volatile unsigned*>(kmax_bits)) atomicMax(kmax_bits, b);
 }
 
 // ---- the scoring kernel ------------------------------------------------------------------
