@@ -388,7 +388,23 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
                 sc[s] = c_sc[wq][c];
                 const float* tr = t + (size_t)ti * dim;
                 double a = 0.0;
-                for (int k = 0; k < dim; k += 4) {
+                // 16 floats of the train row in flight at a time (the loads, not the chain, set the pace otherwise: one
+                // L2 round trip per 4 terms); the chain itself stays in index order
+                int k = 0;
+                for (; k + 16 <= dim; k += 16) {
+                    float4 y[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) y[u] = *reinterpret_cast<const float4*>(tr + k + 4 * u);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        double e;
+                        e = __dsub_rn(q_sh[wq][k + 4 * u], (double)y[u].x); a = __fma_rn(e, e, a);
+                        e = __dsub_rn(q_sh[wq][k + 4 * u + 1], (double)y[u].y); a = __fma_rn(e, e, a);
+                        e = __dsub_rn(q_sh[wq][k + 4 * u + 2], (double)y[u].z); a = __fma_rn(e, e, a);
+                        e = __dsub_rn(q_sh[wq][k + 4 * u + 3], (double)y[u].w); a = __fma_rn(e, e, a);
+                    }
+                }
+                for (; k < dim; k += 4) {
                     float4 y = *reinterpret_cast<const float4*>(tr + k);
                     double e;
                     e = __dsub_rn(q_sh[wq][k], (double)y.x); a = __fma_rn(e, e, a);
