@@ -171,10 +171,11 @@ int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d
     float tau2, sin2;
     thresholds(tau, tau2, sin2);
     ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H_max, ctx->stream));
-    // the list is usually short: always split the correspondences so that it still fills the machine
-    int msplit = max(1, min(cdiv(m, SC_THREADS * 8), 16));
+    // the list is usually short (cfg3: ~900 contenders = 14 hypothesis tiles): split the correspondences finely so that
+    // it still fills the machine (14 x 16 blocks of 8 correspondences per thread took 100 us, 14 x 48 of 4: see profiles/)
+    int msplit = max(1, min(cdiv(m, SC_THREADS * 4), 48));
     dim3 grid(min(cdiv(H_max, TH), 64), msplit);
-    score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m,
+    score_kernel<ERP_METRIC_ALGEBRAIC, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m,
                                                                               tau, tau2, sin2, d_counts, d_list, d_len);
     ERP_LAUNCH(ctx, "score_kernel(list)");
     best_kernel<<<min(cdiv(H_max, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(d_counts, H_max, hyp0,

@@ -397,17 +397,25 @@ __global__ void plan_passes_kernel(int32_t* __restrict__ w, const int32_t* __res
     w[W_REMAIN] = seen >= m ? 0 : (int)(m - seen);
 }
 
-// survivors of pass B: bound so far + correspondences not yet seen >= L*
-__global__ void survivor_select_kernel(const int32_t* __restrict__ upper, int H, int32_t* __restrict__ w, int32_t* __restrict__ list)
+// survivors of pass B: bound so far + correspondences not yet seen >= L*.  One atomic per block (the per-warp version
+// spent its 24 us on ~27k atomics to one word); launched with 256 threads.
+__global__ void __launch_bounds__(256)
+survivor_select_kernel(const int32_t* __restrict__ upper, int H, int32_t* __restrict__ w, int32_t* __restrict__ list)
 {
-    int h = blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = h < H && upper[h] + w[W_REMAIN] >= w[W_LSTAR];
-    unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (!bal) return;
-    int lane = threadIdx.x & 31, base = 0;
-    if (lane == 0) base = atomicAdd(&w[W_DYN_C], __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep) list[base + __popc(bal & ((1u << lane) - 1))] = h;
+    __shared__ int wcount[8], wbase[8];
+    const int h = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool keep = h < H && upper[h] + w[W_REMAIN] >= w[W_LSTAR];
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wcount[wid] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int i = 0; i < 8; i++) { wbase[i] = total; total += wcount[i]; }
+        const int base = total ? atomicAdd(&w[W_DYN_C], total) : 0;
+        for (int i = 0; i < 8; i++) wbase[i] += base;
+    }
+    __syncthreads();
+    if (keep) list[wbase[wid] + __popc(bal & ((1u << lane) - 1))] = h;
 }
 
 // contenders: survivors whose completed bound still reaches L*
