@@ -1,6 +1,6 @@
 """Host-side timing of the e2e (host-buffer C-ABI) calls of one cfg3 step.  usage: e2e_breakdown.py [REPS]"""
 import sys, time, faulthandler
-faulthandler.dump_traceback_later(40, exit=True)
+faulthandler.dump_traceback_later(120, exit=True)
 import numpy as np
 sys.path.insert(0, ".")
 import erp_match_eightpoint_test_b200 as erp
