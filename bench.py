@@ -335,6 +335,17 @@ def run_gpu(args, cfg):
         if it > 0:
             t_e2e_match += b - a
             t_e2e_ransac += c - b
+    # the same pair through ONE call (erp_pair_pose): matches, gather, bearings and hypotheses stay on the device
+    t_pair = 0.0
+    if not strong:
+        for it in range(e2e_steps + 1):
+            torch.cuda.synchronize()
+            a = time.perf_counter()
+            pm, pr = ctx.pair_pose(pq, pt, pair["left"], pair["right"], cfg["W"], cfg["H"], ratio=RATIO, cross_check=False,
+                                   seed=1, H=hhi - hlo, S=SAMPLE, metric=METRIC, tau=TAU)
+            if it > 0:
+                t_pair += time.perf_counter() - a
+        assert len(pm) == len(mt) and pr["packed"] == r_e2e["packed"], "erp_pair_pose disagrees with the separate calls"
     te = torch.tensor([t_e2e_match, t_e2e_ransac], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -448,6 +459,7 @@ def run_gpu(args, cfg):
                 "unit": "dist-evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "match_ms": 1e3 * t_e2e_match / e2e_steps, "ransac_ms": 1e3 * t_e2e_ransac / e2e_steps,
                 "ransac_hyps_per_s": hyps_total * e2e_steps / t_e2e_ransac, "steps": e2e_steps,
+                "pair_ms_one_call": (1e3 * t_pair / e2e_steps) if t_pair > 0 else None,
                 "api": "erp_knn2_match + erp_ransac_pixels (host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
         "check": {"matches": m, "planted": n_pl, "E_refit_err": e_err, "inliers": res["count"], "rescanned": stats["rescanned"]},

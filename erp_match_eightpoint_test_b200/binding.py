@@ -86,6 +86,9 @@ _SIGNATURES = {
                              C.c_float, C.POINTER(RansacResult), C.c_void_p]),
     "erp_ransac_pixels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64,
                                     C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(RansacResult), C.c_void_p]),
+    "erp_pair_pose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                C.c_void_p, C.POINTER(C.c_int), C.POINTER(RansacResult), C.c_void_p]),
     "erp_ransac_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                        C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "erp_ransac_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
@@ -360,6 +363,21 @@ class Context:
         out = self._result(res)
         out["mask"] = mask
         return out
+
+    def pair_pose(self, q, t, left_xy, right_xy, W, H_img, ratio=0.3, cross_check=False, seed=1, H=10000, S=8,
+                  metric=METRIC_ALGEBRAIC, tau=0.002):
+        """erp_pair_pose: descriptors + all keypoints of both views -> (match records, RANSAC result with mask)."""
+        q, t, left_xy, right_xy = _f32(q), _f32(t), _f32(left_xy), _f32(right_xy)
+        out = np.empty(q.shape[0], DMATCH)
+        n = C.c_int(0)
+        res = RansacResult()
+        mask = np.empty(q.shape[0], np.uint8)
+        _check(lib().erp_pair_pose(self._h, _ptr(q), q.shape[0], q.strides[0], _ptr(t), t.shape[0], t.strides[0], q.shape[1],
+                                   ratio, int(cross_check), _ptr(left_xy), _ptr(right_xy), left_xy.strides[0], W, H_img,
+                                   seed, H, S, metric, tau, _ptr(out), C.byref(n), C.byref(res), _ptr(mask)))
+        r = self._result(res)
+        r["mask"] = mask[:n.value]
+        return out[:n.value], r
 
     def ransac_local_dev(self, d_l3, d_r3, d_l4, d_r4, m, seed, hyp_offset, H, S, metric, tau, d_packed):
         _check(lib().erp_ransac_local_dev(self._h, _ptr(d_l3), _ptr(d_r3), _ptr(d_l4), _ptr(d_r4), m, seed, hyp_offset, H, S,

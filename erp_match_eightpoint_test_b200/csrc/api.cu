@@ -637,6 +637,64 @@ ERP_API int erp_ransac_pixels(erp_ctx* ctx, int width, int height, const void* l
     return ERP_OK;
 }
 
+ERP_API int erp_pair_pose(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                          int dim, float ratio, int cross_check,
+                          const void* left_xy, const void* right_xy, size_t kp_stride_bytes, int width, int height,
+                          uint64_t seed, int H, int S, int metric, float tau,
+                          erp_dmatch* matches_out, int* n_matches, erp_ransac_result* result, uint8_t* mask)
+{
+    ERP_TRY(check_knn_args("erp_pair_pose", ctx, nq, nt, dim));
+    ERP_ARG(n_matches && result && matches_out && H >= 1 && S >= 8 && width > 0 && height > 0, ERP_E_ARG, "erp_pair_pose: bad argument");
+    ERP_ARG(left_xy && right_xy && kp_stride_bytes >= 8 && kp_stride_bytes % 4 == 0, ERP_E_ARG, "erp_pair_pose: bad keypoints");
+    *n_matches = 0;
+    ERP_ARG(nq >= 1, ERP_E_TOO_FEW_POINTS, "erp_pair_pose: no query descriptors");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    erp_dmatch* d_out = ctx->scratch<erp_dmatch>(S_OUT, (size_t)nq, &st);
+    int32_t* d_n = ctx->scratch<int32_t>(S_NOUT, 4, &st);
+    int32_t* idx2 = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
+    float* dist2 = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
+    float* d_xy = ctx->scratch<float>(S_XY, ((size_t)nq + nt) * 2, &st);           // left pairs, then right pairs
+    ERP_TRY(st);
+    // keypoints first (small), so that the gather can follow the filter without another upload
+    ERP_TRY(upload_rows(ctx, d_xy, left_xy, nq, 8, kp_stride_bytes));
+    ERP_TRY(upload_rows(ctx, d_xy + (size_t)nq * 2, right_xy, nt, 8, kp_stride_bytes));
+    ERP_TRY(knn2_host(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, idx2, dist2));
+    int32_t* rev = nullptr;
+    if (cross_check) {
+        rev = ctx->scratch<int32_t>(S_REVQ, (size_t)nt, &st);
+        ERP_TRY(st);
+        ERP_TRY(erp_nn1_reverse_dev(ctx, ctx->dev[S_Q].as<float>(), nq, ctx->dev[S_T].as<float>(), nt, dim, 0, rev, nullptr));
+    }
+    ERP_TRY(erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n));
+    int32_t n = 0;
+    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));           // the launch shapes of the RANSAC depend on the match count
+    *n_matches = n;
+    if (n > 0) ERP_CUDA(cudaMemcpyAsync(matches_out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n < S) {
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        set_error("erp_pair_pose: %d matches for sample size %d", n, S);
+        return ERP_E_TOO_FEW_POINTS;
+    }
+    double* dl = ctx->scratch<double>(S_L3, (size_t)n * 3 + 4, &st);
+    double* dr = ctx->scratch<double>(S_R3, (size_t)n * 3 + 4, &st);
+    float* dl4 = ctx->scratch<float>(S_L4, (size_t)n * 4 + 4, &st);
+    float* dr4 = ctx->scratch<float>(S_R4, (size_t)n * 4 + 4, &st);
+    uint64_t* d_packed = ctx->scratch<uint64_t>(S_PACKED, 2, &st);
+    uint8_t* d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)n + 4, &st);
+    ERP_TRY(st);
+    ERP_TRY(erp_gather_bearings_dev(ctx, d_out, n, d_xy, d_xy + (size_t)nq * 2, 8, 0, width, height, dl, dr, dl4, dr4));
+    ERP_TRY(erp_ransac_local_dev(ctx, dl, dr, dl4, dr4, n, seed, 0, H, S, metric, tau, d_packed));
+    uint64_t packed = 0;
+    ERP_CUDA(cudaMemcpyAsync(&packed, d_packed, sizeof packed, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ERP_TRY(erp_ransac_finish_dev(ctx, dl, dr, dl4, dr4, n, seed, packed, S, metric, tau, d_mask, result));
+    if (mask) ERP_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
 // ======================================================================================
 // reference mode: initial_guess / find
 // ======================================================================================

@@ -197,6 +197,16 @@ int erp_ransac(erp_ctx* ctx, const double* l3, const double* r3, int m, uint64_t
 int erp_ransac_pixels(erp_ctx* ctx, int width, int height, const void* left_xy, const void* right_xy,
                       size_t stride_bytes, int m, uint64_t seed, uint64_t hyp_offset, int H, int S, int metric,
                       float tau, erp_ransac_result* result, uint8_t* mask /* m or NULL */);
+/* One call per ERP pair -- the sequence of src/automatic.cpp:117-126 (match_two_image, gather of the matched keypoints,
+ * eight_point::find) with the RANSAC schedule: descriptors and ALL keypoints of both views go up once, matches, their
+ * gather, the bearings and the hypotheses stay on the device, the match records, the pose and the inlier mask come back.
+ * left_xy has nq records, right_xy nt records (first two floats of every kp_stride_bytes bytes).  With fewer matches than
+ * S the matches are still returned and the status is ERP_E_TOO_FEW_POINTS. */
+int erp_pair_pose(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                  int dim, float ratio, int cross_check,
+                  const void* left_xy, const void* right_xy, size_t kp_stride_bytes, int width, int height,
+                  uint64_t seed, int H, int S, int metric, float tau,
+                  erp_dmatch* matches_out /* nq */, int* n_matches, erp_ransac_result* result, uint8_t* mask /* nq or NULL */);
 /* sharded form: every rank scores its hypothesis range and leaves its packed best in
  * d_packed (one uint64 on the device); the caller max-reduces it across ranks (one 8-byte
  * NCCL allreduce) and calls erp_ransac_finish_dev with the winning packed value. */

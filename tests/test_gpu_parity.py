@@ -353,6 +353,30 @@ def test_ransac_on_keypoints_equals_ransac_on_bearings(ctx):
     assert c["packed"] == a["packed"]
 
 
+def test_pair_pose_equals_the_separate_calls(ctx):
+    """erp_pair_pose = erp_knn2_match + the caller's gather of the matched keypoints + erp_ransac_pixels."""
+    q, t, planted = synth.descriptor_pair(4000, 5000, 64, seed=21)
+    n_pl = int((planted >= 0).sum())
+    kp = synth.keypoint_pair(n_pl, 4096, 2048, seed=22)
+    rng = np.random.default_rng(23)
+    left = (rng.uniform(0, 1, (4000, 2)) * [4096, 2047]).astype(np.float32)
+    right = (rng.uniform(0, 1, (5000, 2)) * [4096, 2047]).astype(np.float32)
+    qi = np.nonzero(planted >= 0)[0]
+    left[qi] = kp["left_xy"]
+    right[planted[qi]] = kp["right_xy"]
+    for cross in (False, True):
+        m = ctx.knn2_match(q, t, 0.3, cross)
+        want = ctx.ransac_pixels(left[m["queryIdx"]], right[m["trainIdx"]], 4096, 2048, seed=5, hyp_offset=0, H=8192)
+        got_m, got = ctx.pair_pose(q, t, left, right, 4096, 2048, ratio=0.3, cross_check=cross, seed=5, H=8192)
+        assert got_m.tobytes() == m.tobytes()
+        assert got["packed"] == want["packed"] and np.array_equal(got["mask"], want["mask"])
+        assert np.array_equal(got["E_refit"], want["E_refit"]) and np.array_equal(got["pose"], want["pose"])
+    # too few matches: the records still come back, the status says why there is no pose
+    with pytest.raises(erp.ErpError) as ei:
+        ctx.pair_pose(q[:50], t, left[:50], right, 4096, 2048, ratio=1e-9, H=64)      # nothing passes such a ratio test
+    assert ei.value.status == binding.E_TOO_FEW_POINTS
+
+
 def test_refit_on_inliers(ctx, scene):
     kp, l, r = scene
     mask = O.inlier_mask(kp["E"], l, r)
