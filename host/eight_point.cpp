@@ -79,7 +79,7 @@ int eight_point::ransac(int im_width, int im_height, vector<KeyPoint>& kl, vecto
     return res.count;
 }
 
-random_array::random_array(int size) : size_(size), rand_arr(size > 0 ? size : 0), count_(0)
+random_array::random_array(int size) : length_(size), order_(size > 0 ? size : 0), next_(0)
 {
-    if (size > 0) erp_host::check(erp_libstdcxx_sample_table(size, 1, size, 1, rand_arr.data()), "random_array");
+    if (size > 0) erp_host::check(erp_libstdcxx_sample_table(size, 1, size, 1, order_.data()), "random_array");
 }

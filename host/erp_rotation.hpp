@@ -1,6 +1,9 @@
-// erp_rotation.hpp -- drop-in for the reference's src/erp_rotation.hpp:9-19.  eular2rot / rot2eular
-// are host arithmetic (src/erp_rotation.cpp:14-63); rotate_pixel / rotate_image run on the B200
-// through the C ABI (erp_rotate_pixels, erp_rotate_image; src/erp_rotation.cpp:66-122).
+// erp_rotation.hpp -- drop-in for the reference's src/erp_rotation.hpp:9-19 (same class, same four members).
+//
+//   eular2rot, rot2eular    host arithmetic, src/erp_rotation.cpp:14-63
+//   rotate_pixel            src/erp_rotation.cpp:66-92   -> erp_rotate_pixels (one pixel per call = one device round
+//                           trip: loops over pixels should use the batched C entry point instead)
+//   rotate_image            src/erp_rotation.cpp:94-122  -> erp_rotate_image (inverse-mapped nearest-neighbour warp)
 #pragma once
 #include <cmath>
 
@@ -10,15 +13,26 @@
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif
+// degrees <-> radians, as the callers spell them (src/erp_rotation.hpp:6-7)
 #define RAD(x) M_PI*(x)/180.0
 #define DEGREE(x) 180.0*(x)/M_PI
 
 class erp_rotation
 {
 public:
-    cv::Mat eular2rot(cv::Vec3d theta);      // R = Rx * Ry * Rz, XYZ Euler
+    // XYZ Euler angles (radians) -> 3x3 CV_64F rotation, R = Rx * Ry * Rz
+    cv::Mat eular2rot(cv::Vec3d theta);
+
+    // the inverse; x = 0 in the singular case sqrt(R22^2 + R12^2) < 1e-6
     cv::Vec3d rot2eular(cv::Mat R);
-    // in_vec = (row, col).  One pixel per call costs a device round trip: batch through erp_rotate_pixels.
-    cv::Vec2i rotate_pixel(const cv::Vec2i& in_vec, cv::Mat& rot_mat, int width, int height);
-    cv::Mat rotate_image(const cv::Mat& im, cv::Mat& rot_mat);
+
+    // (row, col) of an ERP pixel after rotating its bearing by rot_mat
+    cv::Vec2i rotate_pixel(const cv::Vec2i& in_vec,
+                           cv::Mat& rot_mat,
+                           int width,
+                           int height);
+
+    // the whole image: every output pixel fetches its source through rot_mat^-1
+    cv::Mat rotate_image(const cv::Mat& im,
+                         cv::Mat& rot_mat);
 };

@@ -11,8 +11,8 @@ void feature_matcher::init()
 #ifndef ERP_OPENCV_COMPAT
     // SURF with OpenCV's defaults, as src/feature_matcher.cpp:13-15 (extended = false: 64-D);
     // extended_ = true is the 128-D variant (same defaults otherwise: hessianThreshold 100, 4 octaves, 3 layers)
-    detector = xfeatures2d::SURF::create(100, 4, 3, extended_);
-    descriptor_extractor = xfeatures2d::SURF::create(100, 4, 3, extended_);
+    surf_detect_ = xfeatures2d::SURF::create(100, 4, 3, extended_);
+    surf_describe_ = xfeatures2d::SURF::create(100, 4, 3, extended_);
 #endif
     // no matcher object: the CUDA context is per thread and created on first use
 }
@@ -30,7 +30,7 @@ vector<KeyPoint> feature_matcher::detect_key_point(const Mat &image)
 {
 #ifndef ERP_OPENCV_COMPAT
     vector<KeyPoint> key_point;
-    detector->detect(image, key_point);
+    surf_detect_->detect(image, key_point);
     return key_point;
 #else
     (void)image;
@@ -42,7 +42,7 @@ Mat feature_matcher::comput_descriptor(const Mat &image, vector<KeyPoint> &key_p
 {
 #ifndef ERP_OPENCV_COMPAT
     Mat d;
-    descriptor_extractor->compute(image, key_point, d);
+    surf_describe_->compute(image, key_point, d);
     return d;
 #else
     (void)image; (void)key_point;
@@ -69,7 +69,7 @@ vector<DMatch> feature_matcher::match_two_image(const Mat &descriptor1, const Ma
     // the reference throws cv::Exception out of knnMatch on malformed input (e.g. < 2 train rows)
     if (st != ERP_OK) throw cv::Exception(string("match_two_image: ") + erp_last_error());
     good.resize(n);
-    matches = good;
+    last_matches_ = good;
     return good;
 }
 
@@ -77,7 +77,7 @@ Mat feature_matcher::draw_match(const Mat& im_left, const Mat& im_right, const v
 {
 #ifndef ERP_OPENCV_COMPAT
     Mat out;
-    drawMatches(im_left, key_left, im_right, key_right, matches, out, Scalar::all(-1), Scalar::all(-1), vector<char>(),
+    drawMatches(im_left, key_left, im_right, key_right, last_matches_, out, Scalar::all(-1), Scalar::all(-1), vector<char>(),
                 DrawMatchesFlags::NOT_DRAW_SINGLE_POINTS);
     return out;
 #else
