@@ -377,6 +377,45 @@ def test_pair_pose_equals_the_separate_calls(ctx):
     assert ei.value.status == binding.E_TOO_FEW_POINTS
 
 
+def test_two_contexts_on_two_host_threads(ctx):
+    """One context per host thread: two threads with a context each, interleaving pairs on the same
+    GPU, return exactly what a single context returns (cfg5: frame pairs of a video are sharded this way)."""
+    import threading
+    pairs = []
+    for i in range(3):
+        q, t, planted = synth.descriptor_pair(3000 + 64 * i, 3500, 64, seed=31 + i)
+        rng = np.random.default_rng(100 + i)
+        left = (rng.uniform(0, 1, (len(q), 2)) * [4096, 2047]).astype(np.float32)
+        right = (rng.uniform(0, 1, (len(t), 2)) * [4096, 2047]).astype(np.float32)
+        kp = synth.keypoint_pair(int((planted >= 0).sum()), 4096, 2048, seed=200 + i)
+        qi = np.nonzero(planted >= 0)[0]
+        left[qi] = kp["left_xy"]
+        right[planted[qi]] = kp["right_xy"]
+        pairs.append((q, t, left, right))
+    want = [ctx.pair_pose(q, t, l, r, 4096, 2048, seed=2, H=4096) for q, t, l, r in pairs]
+    got = [None] * 12
+    errs = []
+
+    def work(tid):
+        try:
+            c = erp.Context(0)
+            for i in range(tid, 12, 2):
+                q, t, l, r = pairs[i % 3]
+                got[i] = c.pair_pose(q, t, l, r, 4096, 2048, seed=2, H=4096)
+            c.close()
+        except Exception as e:          # surfaced below: an exception in a thread would otherwise pass silently
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for i in range(12):
+        m, r = got[i]
+        wm, wr = want[i % 3]
+        assert m.tobytes() == wm.tobytes() and r["packed"] == wr["packed"] and np.array_equal(r["mask"], wr["mask"])
+
+
 def test_refit_on_inliers(ctx, scene):
     kp, l, r = scene
     mask = O.inlier_mask(kp["E"], l, r)
