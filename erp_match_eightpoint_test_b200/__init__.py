@@ -6,7 +6,7 @@ tests and ``bench.py``; the C++ drop-in classes live under ``host/``.
 """
 from .binding import (  # noqa: F401
     DMATCH, ENGINE_AUTO, ENGINE_EXACT_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_1X, METRIC_ALGEBRAIC, METRIC_ANGULAR,
-    METRIC_SAMPSON, POSE_FLOATS, Context, ErpError, LIB_PATH, lib, libstdcxx_sample_table,
+    METRIC_SAMPSON, POSE_FLOATS, Context, ErpError, Group, LIB_PATH, comm_unique_id, lib, libstdcxx_sample_table, shard_range,
 )
 
-__all__ = ["Context", "ErpError", "DMATCH", "lib", "LIB_PATH", "libstdcxx_sample_table"]
+__all__ = ["Context", "Group", "ErpError", "DMATCH", "lib", "LIB_PATH", "libstdcxx_sample_table", "comm_unique_id", "shard_range"]

@@ -24,7 +24,8 @@ ENGINE_AUTO, ENGINE_EXACT_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_1X = 0, 1, 2, 3
 
 OK = 0
 E_ARG, E_DIM, E_TOO_FEW_TRAIN, E_TOO_FEW_POINTS, E_NO_CANDIDATE, E_LIMIT = 1, 2, 3, 4, 5, 6
-E_CUDA, E_NO_DEVICE, E_ARCH = -1, -2, -3
+E_CUDA, E_NO_DEVICE, E_ARCH, E_NCCL = -1, -2, -3, -4
+COMM_ID_BYTES = 128
 
 
 class RansacResult(C.Structure):
@@ -56,6 +57,7 @@ _SIGNATURES = {
     "erp_ctx_last_knn_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "erp_ctx_last_score_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "erp_ctx_last_score_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "erp_ctx_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "erp_gather_bearings_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "erp_knn2_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
@@ -89,6 +91,35 @@ _SIGNATURES = {
     "erp_pair_pose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
                                 C.c_void_p, C.POINTER(C.c_int), C.POINTER(RansacResult), C.c_void_p]),
+    "erp_pair_pose_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "erp_shard_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "erp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "erp_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "erp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "erp_comm_size": (C.c_int, [C.c_void_p]),
+    "erp_comm_rank": (C.c_int, [C.c_void_p]),
+    "erp_comm_allreduce_best_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "erp_comm_cross_check_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "erp_pair_pose_dist_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "erp_pair_pose_dist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                C.c_void_p, C.POINTER(C.c_int), C.POINTER(RansacResult), C.c_void_p]),
+    "erp_knn2_match_dist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
+                                 C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "erp_knn2_match_dist_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "erp_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "erp_group_destroy": (None, [C.c_void_p]),
+    "erp_group_size": (C.c_int, [C.c_void_p]),
+    "erp_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "erp_group_pair_pose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                C.c_void_p, C.POINTER(C.c_int), C.POINTER(RansacResult), C.c_void_p]),
+    "erp_group_knn2_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
+                                 C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "erp_ransac_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                        C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "erp_ransac_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
@@ -224,6 +255,12 @@ class Context:
         ms, n = C.c_float(0), C.c_int(0)
         _check(lib().erp_ctx_last_score_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    def last_stage_ms(self):
+        """Device time of the stages of the last pair_pose* call: (match, exchange + gather, RANSAC) in ms."""
+        out = (C.c_float * 3)()
+        _check(lib().erp_ctx_last_stage_ms(self._h, out))
+        return float(out[0]), float(out[1]), float(out[2])
 
     def last_score_stats(self):
         out = (C.c_int64 * 6)()
@@ -367,15 +404,69 @@ class Context:
     def pair_pose(self, q, t, left_xy, right_xy, W, H_img, ratio=0.3, cross_check=False, seed=1, H=10000, S=8,
                   metric=METRIC_ALGEBRAIC, tau=0.002):
         """erp_pair_pose: descriptors + all keypoints of both views -> (match records, RANSAC result with mask)."""
+        return self._pair_pose(lib().erp_pair_pose, self._h, q, t, left_xy, right_xy, W, H_img, ratio, cross_check, seed, H, S,
+                               metric, tau)
+
+    def pair_pose_dev(self, d_q, nq, d_t, nt, dim, ratio, cross_check, d_left_xy, d_right_xy, kp_stride, W, H_img, seed, H, S,
+                      metric, tau, d_matches, d_n, d_mask, d_result, dist=False):
+        """erp_pair_pose_dev / erp_pair_pose_dist_dev (dist=True: d_q is this rank's shard, nq the TOTAL): enqueue only."""
+        fn = lib().erp_pair_pose_dist_dev if dist else lib().erp_pair_pose_dev
+        _check(fn(self._h, _ptr(d_q), nq, _ptr(d_t), nt, dim, ratio, int(cross_check), _ptr(d_left_xy), _ptr(d_right_xy), kp_stride,
+                  W, H_img, seed, H, S, metric, tau, _ptr(d_matches), _ptr(d_n), _ptr(d_mask), _ptr(d_result)))
+
+    # ---- multi-GPU: one process per GPU (the caller distributes the id, e.g. with torch.distributed)
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        _check(lib().erp_comm_init(self._h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        _check(lib().erp_comm_destroy(self._h))
+
+    @property
+    def comm_size(self) -> int:
+        return int(lib().erp_comm_size(self._h))
+
+    @property
+    def comm_rank(self) -> int:
+        return int(lib().erp_comm_rank(self._h))
+
+    def comm_allreduce_best_dev(self, d_packed):
+        _check(lib().erp_comm_allreduce_best_dev(self._h, _ptr(d_packed)))
+
+    def comm_cross_check_dev(self, d_best_q, d_best_d2, nt):
+        _check(lib().erp_comm_cross_check_dev(self._h, _ptr(d_best_q), _ptr(d_best_d2), nt))
+
+    def pair_pose_dist(self, q, t, left_xy, right_xy, W, H_img, ratio=0.3, cross_check=False, seed=1, H=10000, S=8,
+                       metric=METRIC_ALGEBRAIC, tau=0.002):
+        """erp_pair_pose_dist: collective over the context's clique, host buffers (every rank passes the same arrays)."""
+        return self._pair_pose(lib().erp_pair_pose_dist, self._h, q, t, left_xy, right_xy, W, H_img, ratio, cross_check, seed, H, S,
+                               metric, tau)
+
+    def knn2_match_dist(self, q, t, ratio: float = 0.3, cross_check: bool = False) -> np.ndarray:
+        """This rank's part of the query-sharded match list (global query ids)."""
+        q, t = _f32(q), _f32(t)
+        out = np.empty(max(q.shape[0], 1), DMATCH)
+        n = C.c_int(0)
+        _check(lib().erp_knn2_match_dist(self._h, _ptr(q), q.shape[0], q.strides[0] if q.shape[0] else 4 * q.shape[1],
+                                         _ptr(t), t.shape[0], t.strides[0] if t.shape[0] else 4 * t.shape[1], q.shape[1],
+                                         ratio, int(cross_check), _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def knn2_match_dist_dev(self, d_q_shard, nq_total, d_t, nt, dim, ratio, cross_check, d_out, d_n_out):
+        _check(lib().erp_knn2_match_dist_dev(self._h, _ptr(d_q_shard), nq_total, _ptr(d_t), nt, dim, ratio, int(cross_check),
+                                             _ptr(d_out), _ptr(d_n_out)))
+
+    @classmethod
+    def _pair_pose(cls, fn, handle, q, t, left_xy, right_xy, W, H_img, ratio, cross_check, seed, H, S, metric, tau):
         q, t, left_xy, right_xy = _f32(q), _f32(t), _f32(left_xy), _f32(right_xy)
         out = np.empty(q.shape[0], DMATCH)
         n = C.c_int(0)
         res = RansacResult()
         mask = np.empty(q.shape[0], np.uint8)
-        _check(lib().erp_pair_pose(self._h, _ptr(q), q.shape[0], q.strides[0], _ptr(t), t.shape[0], t.strides[0], q.shape[1],
-                                   ratio, int(cross_check), _ptr(left_xy), _ptr(right_xy), left_xy.strides[0], W, H_img,
-                                   seed, H, S, metric, tau, _ptr(out), C.byref(n), C.byref(res), _ptr(mask)))
-        r = self._result(res)
+        _check(fn(handle, _ptr(q), q.shape[0], q.strides[0], _ptr(t), t.shape[0], t.strides[0], q.shape[1],
+                  ratio, int(cross_check), _ptr(left_xy), _ptr(right_xy), left_xy.strides[0], W, H_img,
+                  seed, H, S, metric, tau, _ptr(out), C.byref(n), C.byref(res), _ptr(mask)))
+        r = cls._result(res)
         r["mask"] = mask[:n.value]
         return out[:n.value], r
 
@@ -457,3 +548,71 @@ class Context:
         _check(lib().erp_find(self._h, W, H, _ptr(left_xy), _ptr(right_xy), 8, match_size, _ptr(samples), n_hyp, S,
                               _ptr(R), _ptr(T)))
         return R, T
+
+
+def shard_range(n: int, rank: int, nranks: int) -> tuple[int, int]:
+    lo, hi = C.c_int(0), C.c_int(0)
+    _check(lib().erp_shard_range(n, rank, nranks, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def comm_unique_id() -> bytes:
+    """ncclUniqueId of a new clique (rank 0 calls this and broadcasts the bytes)."""
+    buf = (C.c_char * COMM_ID_BYTES)()
+    _check(lib().erp_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Group:
+    """One process, several GPUs (include/erp_b200.h: erp_group): the calls fan out inside the library."""
+
+    def __init__(self, devices):
+        devices = list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        _check(lib().erp_group_create(arr, len(devices), C.byref(self._h)))
+        self.devices = devices
+        _live.add(self)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().erp_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __len__(self):
+        return int(lib().erp_group_size(self._h))
+
+    def set_engine(self, engine: int):
+        for r in range(len(self)):
+            _check(lib().erp_ctx_set_engine(lib().erp_group_ctx(self._h, r), engine))
+
+    def stage_ms(self, rank: int = 0):
+        out = (C.c_float * 3)()
+        _check(lib().erp_ctx_last_stage_ms(lib().erp_group_ctx(self._h, rank), out))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def pair_pose(self, q, t, left_xy, right_xy, W, H_img, ratio=0.3, cross_check=False, seed=1, H=10000, S=8,
+                  metric=METRIC_ALGEBRAIC, tau=0.002):
+        return Context._pair_pose(lib().erp_group_pair_pose, self._h, q, t, left_xy, right_xy, W, H_img, ratio, cross_check,
+                                  seed, H, S, metric, tau)
+
+    def knn2_match(self, q, t, ratio: float = 0.3, cross_check: bool = False) -> np.ndarray:
+        q, t = _f32(q), _f32(t)
+        out = np.empty(max(q.shape[0], 1), DMATCH)
+        n = C.c_int(0)
+        _check(lib().erp_group_knn2_match(self._h, _ptr(q), q.shape[0], q.strides[0] if q.shape[0] else 4 * q.shape[1],
+                                          _ptr(t), t.shape[0], t.strides[0] if t.shape[0] else 4 * t.shape[1], q.shape[1],
+                                          ratio, int(cross_check), _ptr(out), C.byref(n)))
+        return out[: n.value].copy()

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "liberp_b200.so")
-SOURCES = ["api.cu", "knn_exact.cu", "knn_tc.cu", "knn_tc1.cu", "geometry.cu", "score.cu", "score_tc.cu", "erp_image.cu"]
+SOURCES = ["api.cu", "knn_exact.cu", "knn_tc.cu", "knn_tc1.cu", "geometry.cu", "score.cu", "score_tc.cu", "erp_image.cu", "dist.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl", "-lpthread",
                                                     "-ccbin", "/usr/bin/g++"]
         subprocess.run(cmd, check=True)
     return LIB

@@ -1,6 +1,6 @@
 // api.cu -- context management, error reporting, host-pointer entry points (staging + copies)
 // and the pieces of the reference's host logic that stay on the host (random_array replay).
-#include "common.cuh"
+#include "score_common.cuh"
 
 #include <stdarg.h>
 
@@ -37,7 +37,6 @@ void Buf::release()
     p = nullptr; cap = 0;
 }
 
-int gram_batch(erp_ctx*, const double*, const double*, int, const int32_t*, int, int, uint64_t, uint64_t, double*);
 int gram_masked(erp_ctx*, const double*, const double*, int, const uint8_t*, double*);
 int solve_batch(erp_ctx*, const double*, int, double*, float*, int max_sweeps = 30);
 int consensus(erp_ctx*, const float*, int, float*, float*, int32_t*);
@@ -98,6 +97,7 @@ ERP_API int erp_ctx_create(int device, erp_ctx** out)
     }
     bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_k0) == cudaSuccess && cudaEventCreate(&ctx->ev_k1) == cudaSuccess;
+    for (auto& e2 : ctx->ev_stage) ok = ok && cudaEventCreate(&e2) == cudaSuccess;
     for (auto& e2 : ctx->ev_copy) ok = ok && cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         set_error("cudaStreamCreate / cudaEventCreate failed");
@@ -119,6 +119,8 @@ ERP_API void erp_ctx_destroy(erp_ctx* ctx)
     for (auto& b : ctx->pinned) b.release();
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    for (cudaEvent_t e : ctx->ev_stage) if (e) cudaEventDestroy(e);
+    comm_release(ctx);
     for (cudaEvent_t e : ctx->ev_score) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -168,6 +170,15 @@ ERP_API int erp_ctx_last_score_kernel_ms(erp_ctx* ctx, float* ms, int* launches)
     return ERP_OK;
 }
 
+ERP_API int erp_ctx_last_stage_ms(erp_ctx* ctx, float out[3])
+{
+    ERP_ARG(ctx && out, ERP_E_ARG, "erp_ctx_last_stage_ms: bad argument");
+    DeviceGuard g(ctx->device);
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; i++) ERP_CUDA(cudaEventElapsedTime(&out[i], ctx->ev_stage[i], ctx->ev_stage[i + 1]));
+    return ERP_OK;
+}
+
 ERP_API int erp_ctx_last_score_stats(erp_ctx* ctx, int64_t out[6])
 {
     ERP_ARG(ctx && out, ERP_E_ARG, "erp_ctx_last_score_stats: bad argument");
@@ -177,12 +188,12 @@ ERP_API int erp_ctx_last_score_stats(erp_ctx* ctx, int64_t out[6])
     int32_t w[24];
     ERP_CUDA(cudaMemcpyAsync(w, ctx->sc_misc_dev, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    out[0] = w[12];            // hypotheses of the chunk
-    out[1] = w[14];            // correspondence tiles (of 256) every hypothesis was bounded on
-    out[2] = w[18];            // correspondence tiles in total
-    out[3] = w[16];            // survivors that were bounded on the rest
-    out[4] = w[3];             // contenders scored exactly
-    out[5] = w[20];            // L*: exact count of the first contender
+    out[0] = w[W_DYN_A];       // hypotheses of the chunk
+    out[1] = w[W_DYN_B + 2];   // correspondence tiles (of 256) every hypothesis was bounded on
+    out[2] = w[W_NCT];         // correspondence tiles in total
+    out[3] = w[W_DYN_C];       // survivors that were bounded on the rest
+    out[4] = w[W_LENF];        // contenders scored exactly
+    out[5] = w[W_LSTAR];       // L*: exact count of the first contender
     return ERP_OK;
 }
 
@@ -349,13 +360,15 @@ static int knn2_host(erp_ctx* ctx, const float* q, int nq, size_t qs, const floa
     }
     ctx->stream = main_stream;
     ERP_TRY(rc);
+    // tc_chunk > 0 tells the tensor engines that the train operand of this call is already prepared: it must not
+    // survive this function on ANY exit path (a stale value would make the next call reuse old train data)
+    struct ChunkReset { erp_ctx* c; ~ChunkReset() { c->tc_chunk = 0; } } reset{ctx};
     for (int c = 0; c < chunks && rc == ERP_OK; c++) {
         const int r0 = c * rows, n = nq - r0 < rows ? nq - r0 : rows;
         ERP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[c], 0));
         ctx->tc_chunk = c;
         rc = erp_knn2_dev(ctx, dq + (size_t)r0 * dim, n, dt, nt, dim, d_idx2 + 2 * (size_t)r0, d_dist2 + 2 * (size_t)r0, nullptr);
     }
-    ctx->tc_chunk = 0;
     return rc;
 }
 
@@ -462,6 +475,7 @@ ERP_API int erp_eight_point_batch(erp_ctx* ctx, const double* l3, const double* 
                                   double* E_out, float* pose_out)
 {
     ERP_ARG(ctx && E_out && H >= 0 && m >= 0, ERP_E_ARG, "erp_eight_point_batch: bad argument");
+    ERP_ARG(S >= 8 && m >= S, ERP_E_TOO_FEW_POINTS, "erp_eight_point_batch: sample size %d of %d correspondences (need 8 <= S <= m)", S, m);
     if (H == 0) return ERP_OK;
     DeviceGuard g(ctx->device);
     double *dl, *dr;
@@ -577,29 +591,64 @@ ERP_API int erp_inlier_mask(erp_ctx* ctx, const double* E9, const double* l3, co
     return ERP_OK;
 }
 
+namespace erp {
+
+// search + (multi-GPU: one 8-byte max all-reduce) + finish, everything enqueued, nothing awaited.
+// k_ready: the correspondence operand of the tensor-core search was written by the gather.
+int pose_chain_tail(erp_ctx* ctx, const double* dl, const double* dr, const float* dl4, const float* dr4, int m_cap, const int32_t* d_m,
+                    uint64_t seed, uint64_t hyp_offset, int H, int S, int metric, float tau, bool k_ready, bool reduce,
+                    uint8_t* d_mask, erp_ransac_result* d_res)
+{
+    int st = ERP_OK;
+    uint64_t* d_packed = ctx->scratch<uint64_t>(S_PACKED, 4, &st);
+    ERP_TRY(st);
+    ERP_CUDA(cudaMemsetAsync(d_packed, 0, sizeof(uint64_t), ctx->stream));
+    ERP_TRY(ransac_search(ctx, dl, dr, dl4, dr4, m_cap, d_m, seed, hyp_offset, H, S, metric, tau, k_ready, d_packed));
+    if (reduce) ERP_TRY(comm_allreduce_best(ctx, d_packed));
+    return ransac_finish(ctx, dl, dr, dl4, dr4, m_cap, d_m, seed, d_packed, S, metric, tau, d_mask, d_res);
+}
+
+// scratch of the chain for up to m_cap correspondences
+int pose_chain_buffers(erp_ctx* ctx, int m_cap, PoseBuffers* b)
+{
+    int st = ERP_OK;
+    b->l3 = ctx->scratch<double>(S_L3, (size_t)m_cap * 3 + 4, &st);
+    b->r3 = ctx->scratch<double>(S_R3, (size_t)m_cap * 3 + 4, &st);
+    b->l4 = ctx->scratch<float>(S_L4, (size_t)m_cap * 4 + 4, &st);
+    b->r4 = ctx->scratch<float>(S_R4, (size_t)m_cap * 4 + 4, &st);
+    b->mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m_cap + 4, &st);
+    b->res = ctx->scratch<erp_ransac_result>(S_RESULT, 1, &st);
+    return st;
+}
+
+} // namespace erp
+
+static int check_ransac_args(const char* who, erp_ctx* ctx, int H, int S, int metric, uint64_t hyp_offset)
+{
+    ERP_ARG(ctx && H >= 1, ERP_E_ARG, "%s: bad argument", who);
+    ERP_ARG(S >= 8 && S <= 32, ERP_E_ARG, "%s: sample size must be in [8,32], got %d", who, S);
+    ERP_ARG(metric >= 0 && metric <= 2, ERP_E_ARG, "%s: unknown metric %d", who, metric);
+    ERP_ARG(hyp_offset + (uint64_t)H <= 0xFFFFFFFFull, ERP_E_LIMIT, "%s: hypothesis ids must fit 32 bits", who);
+    return ERP_OK;
+}
+
 ERP_API int erp_ransac(erp_ctx* ctx, const double* l3, const double* r3, int m, uint64_t seed,
                        uint64_t hyp_offset, int H, int S, int metric, float tau,
                        erp_ransac_result* result, uint8_t* mask)
 {
-    ERP_ARG(ctx && result && H >= 1, ERP_E_ARG, "erp_ransac: bad argument");
-    ERP_ARG(m >= S && S >= 8, ERP_E_TOO_FEW_POINTS, "erp_ransac: %d correspondences for sample size %d", m, S);
+    ERP_ARG(result, ERP_E_ARG, "erp_ransac: result is null");
+    ERP_TRY(check_ransac_args("erp_ransac", ctx, H, S, metric, hyp_offset));
+    ERP_ARG(m >= S, ERP_E_TOO_FEW_POINTS, "erp_ransac: %d correspondences for sample size %d", m, S);
     DeviceGuard g(ctx->device);
     double *dl, *dr;
     float *dl4, *dr4;
     ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, &dl4, &dr4));
-    int st = ERP_OK;
-    uint64_t* d_packed = ctx->scratch<uint64_t>(S_PACKED, 2, &st);
-    uint8_t* d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m + 4, &st);
-    ERP_TRY(st);
-    ERP_TRY(erp_ransac_local_dev(ctx, dl, dr, dl4, dr4, m, seed, hyp_offset, H, S, metric, tau, d_packed));
-    uint64_t packed = 0;
-    ERP_CUDA(cudaMemcpyAsync(&packed, d_packed, sizeof packed, cudaMemcpyDeviceToHost, ctx->stream));
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, m, &b));
+    ERP_TRY(pose_chain_tail(ctx, dl, dr, dl4, dr4, m, nullptr, seed, hyp_offset, H, S, metric, tau, false, false, b.mask, b.res));
+    ERP_CUDA(cudaMemcpyAsync(result, b.res, sizeof *result, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask) ERP_CUDA(cudaMemcpyAsync(mask, b.mask, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    ERP_TRY(erp_ransac_finish_dev(ctx, dl, dr, dl4, dr4, m, seed, packed, S, metric, tau, d_mask, result));
-    if (mask) {
-        ERP_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
-        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
     return ERP_OK;
 }
 
@@ -607,33 +656,61 @@ ERP_API int erp_ransac_pixels(erp_ctx* ctx, int width, int height, const void* l
                               size_t stride_bytes, int m, uint64_t seed, uint64_t hyp_offset, int H, int S, int metric,
                               float tau, erp_ransac_result* result, uint8_t* mask)
 {
-    ERP_ARG(ctx && result && H >= 1 && width > 0 && height > 0, ERP_E_ARG, "erp_ransac_pixels: bad argument");
+    ERP_ARG(result && width > 0 && height > 0, ERP_E_ARG, "erp_ransac_pixels: bad argument");
+    ERP_TRY(check_ransac_args("erp_ransac_pixels", ctx, H, S, metric, hyp_offset));
     ERP_ARG(stride_bytes >= 8 && stride_bytes % 4 == 0, ERP_E_ARG, "erp_ransac_pixels: bad stride %zu", stride_bytes);
-    ERP_ARG(m >= S && S >= 8, ERP_E_TOO_FEW_POINTS, "erp_ransac_pixels: %d correspondences for sample size %d", m, S);
+    ERP_ARG(m >= S, ERP_E_TOO_FEW_POINTS, "erp_ransac_pixels: %d correspondences for sample size %d", m, S);
     ERP_ARG(left_xy && right_xy, ERP_E_ARG, "erp_ransac_pixels: null keypoints");
     DeviceGuard g(ctx->device);
     int st = ERP_OK;
     float* d_xy = ctx->scratch<float>(S_XY, (size_t)m * 4, &st);                 // left pairs, then right pairs
-    double* dl = ctx->scratch<double>(S_L3, (size_t)m * 3 + 4, &st);
-    double* dr = ctx->scratch<double>(S_R3, (size_t)m * 3 + 4, &st);
-    float* dl4 = ctx->scratch<float>(S_L4, (size_t)m * 4 + 4, &st);
-    float* dr4 = ctx->scratch<float>(S_R4, (size_t)m * 4 + 4, &st);
-    uint64_t* d_packed = ctx->scratch<uint64_t>(S_PACKED, 2, &st);
-    uint8_t* d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m + 4, &st);
     ERP_TRY(st);
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, m, &b));
     ERP_TRY(upload_rows(ctx, d_xy, left_xy, m, 8, stride_bytes));
     ERP_TRY(upload_rows(ctx, d_xy + (size_t)m * 2, right_xy, m, 8, stride_bytes));
-    ERP_TRY(erp_bearings_dev(ctx, d_xy, 8, m, width, height, dl, dl4));
-    ERP_TRY(erp_bearings_dev(ctx, d_xy + (size_t)m * 2, 8, m, width, height, dr, dr4));
-    ERP_TRY(erp_ransac_local_dev(ctx, dl, dr, dl4, dr4, m, seed, hyp_offset, H, S, metric, tau, d_packed));
-    uint64_t packed = 0;
-    ERP_CUDA(cudaMemcpyAsync(&packed, d_packed, sizeof packed, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    ERP_TRY(erp_ransac_finish_dev(ctx, dl, dr, dl4, dr4, m, seed, packed, S, metric, tau, d_mask, result));
-    if (mask) {
-        ERP_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
-        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    const bool tc = ransac_uses_tc(ctx, H, m, metric);
+    ScoreTcBuffers sb = {};
+    if (tc) {
+        ERP_TRY(score_tc_buffers(ctx, H < RANSAC_CHUNK ? H : RANSAC_CHUNK, m, &sb));
+        ERP_CUDA(cudaMemsetAsync(sb.w, 0, W_WORDS_BYTES, ctx->stream));
     }
+    ERP_TRY(bearings_pair_chain(ctx, d_xy, d_xy + (size_t)m * 2, 8, m, width, height, b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
+    ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, m, nullptr, seed, hyp_offset, H, S, metric, tau, tc, false, b.mask, b.res));
+    ERP_CUDA(cudaMemcpyAsync(result, b.res, sizeof *result, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask) ERP_CUDA(cudaMemcpyAsync(mask, b.mask, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ERP_OK;
+}
+
+ERP_API int erp_pair_pose_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, float ratio, int cross_check,
+                              const void* d_left_xy, const void* d_right_xy, size_t kp_stride_bytes, int width, int height,
+                              uint64_t seed, int H, int S, int metric, float tau,
+                              erp_dmatch* d_matches, int32_t* d_n_matches, uint8_t* d_mask, erp_ransac_result* d_result)
+{
+    ERP_TRY(check_knn_args("erp_pair_pose_dev", ctx, nq, nt, dim));
+    ERP_TRY(check_ransac_args("erp_pair_pose_dev", ctx, H, S, metric, 0));
+    ERP_ARG(d_matches && d_n_matches && d_result && width > 0 && height > 0, ERP_E_ARG, "erp_pair_pose_dev: bad argument");
+    ERP_ARG(d_left_xy && d_right_xy && kp_stride_bytes >= 8 && kp_stride_bytes % 4 == 0, ERP_E_ARG, "erp_pair_pose_dev: bad keypoints");
+    ERP_ARG(nq >= 1, ERP_E_TOO_FEW_POINTS, "erp_pair_pose_dev: no query descriptors");
+    DeviceGuard g(ctx->device);
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[0], ctx->stream));
+    ERP_TRY(erp_knn2_match_dev(ctx, d_q, nq, d_t, nt, dim, ratio, cross_check, d_matches, d_n_matches));
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[1], ctx->stream));
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, nq, &b));
+    const bool tc = ransac_uses_tc(ctx, H, nq, metric);
+    ScoreTcBuffers sb = {};
+    if (tc) {
+        ERP_TRY(score_tc_buffers(ctx, H < RANSAC_CHUNK ? H : RANSAC_CHUNK, nq, &sb));
+        ERP_CUDA(cudaMemsetAsync(sb.w, 0, W_WORDS_BYTES, ctx->stream));
+    }
+    ERP_TRY(gather_bearings_chain(ctx, d_matches, nq, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes, 0, width, height,
+                                  b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[2], ctx->stream));
+    ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, nq, d_n_matches, seed, 0, H, S, metric, tau, tc, false,
+                            d_mask ? d_mask : b.mask, d_result));
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[3], ctx->stream));
     return ERP_OK;
 }
 
@@ -644,54 +721,45 @@ ERP_API int erp_pair_pose(erp_ctx* ctx, const float* q, int nq, size_t q_stride_
                           erp_dmatch* matches_out, int* n_matches, erp_ransac_result* result, uint8_t* mask)
 {
     ERP_TRY(check_knn_args("erp_pair_pose", ctx, nq, nt, dim));
-    ERP_ARG(n_matches && result && matches_out && H >= 1 && S >= 8 && width > 0 && height > 0, ERP_E_ARG, "erp_pair_pose: bad argument");
+    ERP_TRY(check_ransac_args("erp_pair_pose", ctx, H, S, metric, 0));
+    ERP_ARG(n_matches && result && matches_out && width > 0 && height > 0, ERP_E_ARG, "erp_pair_pose: bad argument");
     ERP_ARG(left_xy && right_xy && kp_stride_bytes >= 8 && kp_stride_bytes % 4 == 0, ERP_E_ARG, "erp_pair_pose: bad keypoints");
     *n_matches = 0;
     ERP_ARG(nq >= 1, ERP_E_TOO_FEW_POINTS, "erp_pair_pose: no query descriptors");
+    const size_t row = (size_t)dim * sizeof(float);
+    ERP_ARG(q && t && q_stride_bytes >= row && t_stride_bytes >= row, ERP_E_ARG, "erp_pair_pose: bad descriptor buffers");
     DeviceGuard g(ctx->device);
     int st = ERP_OK;
     erp_dmatch* d_out = ctx->scratch<erp_dmatch>(S_OUT, (size_t)nq, &st);
     int32_t* d_n = ctx->scratch<int32_t>(S_NOUT, 4, &st);
-    int32_t* idx2 = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
-    float* dist2 = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
     float* d_xy = ctx->scratch<float>(S_XY, ((size_t)nq + nt) * 2, &st);           // left pairs, then right pairs
+    float* dq = ctx->scratch<float>(S_Q, (size_t)nq * dim + 4, &st);
+    float* dt = ctx->scratch<float>(S_T, (size_t)nt * dim + 4, &st);
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, nq, &b));
     ERP_TRY(st);
-    // keypoints first (small), so that the gather can follow the filter without another upload
+    ERP_TRY(upload_rows(ctx, dt, t, nt, row, t_stride_bytes));
+    ERP_TRY(upload_rows(ctx, dq, q, nq, row, q_stride_bytes));
     ERP_TRY(upload_rows(ctx, d_xy, left_xy, nq, 8, kp_stride_bytes));
     ERP_TRY(upload_rows(ctx, d_xy + (size_t)nq * 2, right_xy, nt, 8, kp_stride_bytes));
-    ERP_TRY(knn2_host(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, idx2, dist2));
-    int32_t* rev = nullptr;
-    if (cross_check) {
-        rev = ctx->scratch<int32_t>(S_REVQ, (size_t)nt, &st);
-        ERP_TRY(st);
-        ERP_TRY(erp_nn1_reverse_dev(ctx, ctx->dev[S_Q].as<float>(), nq, ctx->dev[S_T].as<float>(), nt, dim, 0, rev, nullptr));
-    }
-    ERP_TRY(erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n));
+    ERP_TRY(erp_pair_pose_dev(ctx, dq, nq, dt, nt, dim, ratio, cross_check, d_xy, d_xy + (size_t)nq * 2, 8, width, height,
+                              seed, H, S, metric, tau, d_out, d_n, b.mask, b.res));
+    // everything is enqueued: the host waits for the MATCH stage only (the pose chain keeps running), learns the match
+    // count and brings the records back on the copy stream while the hypotheses are being scored
     int32_t n = 0;
-    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaStreamSynchronize(ctx->stream));           // the launch shapes of the RANSAC depend on the match count
+    ERP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage[1], 0));
+    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     *n_matches = n;
-    if (n > 0) ERP_CUDA(cudaMemcpyAsync(matches_out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n > 0) ERP_CUDA(cudaMemcpyAsync(matches_out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ERP_CUDA(cudaMemcpyAsync(result, b.res, sizeof *result, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask && n > 0) ERP_CUDA(cudaMemcpyAsync(mask, b.mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     if (n < S) {
-        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
         set_error("erp_pair_pose: %d matches for sample size %d", n, S);
         return ERP_E_TOO_FEW_POINTS;
     }
-    double* dl = ctx->scratch<double>(S_L3, (size_t)n * 3 + 4, &st);
-    double* dr = ctx->scratch<double>(S_R3, (size_t)n * 3 + 4, &st);
-    float* dl4 = ctx->scratch<float>(S_L4, (size_t)n * 4 + 4, &st);
-    float* dr4 = ctx->scratch<float>(S_R4, (size_t)n * 4 + 4, &st);
-    uint64_t* d_packed = ctx->scratch<uint64_t>(S_PACKED, 2, &st);
-    uint8_t* d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)n + 4, &st);
-    ERP_TRY(st);
-    ERP_TRY(erp_gather_bearings_dev(ctx, d_out, n, d_xy, d_xy + (size_t)nq * 2, 8, 0, width, height, dl, dr, dl4, dr4));
-    ERP_TRY(erp_ransac_local_dev(ctx, dl, dr, dl4, dr4, n, seed, 0, H, S, metric, tau, d_packed));
-    uint64_t packed = 0;
-    ERP_CUDA(cudaMemcpyAsync(&packed, d_packed, sizeof packed, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    ERP_TRY(erp_ransac_finish_dev(ctx, dl, dr, dl4, dr4, n, seed, packed, S, metric, tau, d_mask, result));
-    if (mask) ERP_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
     return ERP_OK;
 }
 
@@ -749,10 +817,11 @@ ERP_API int erp_libstdcxx_sample_table(int m, int H, int S, unsigned seed, int32
     return ERP_OK;
 }
 
-ERP_API int erp_initial_guess(erp_ctx* ctx, const double* l3, const double* r3, int m,
-                              const int32_t* samples, int H, int S,
-                              float* R_vec_out, float* T_vec_out,
-                              float* cand_R, float* cand_T, int* n_cand, int* chosen)
+// initial_guess on bearings that are already on the device (dl, dr: m x 3 fp64)
+static int initial_guess_dev(erp_ctx* ctx, const double* dl, const double* dr, int m,
+                             const int32_t* samples, int H, int S,
+                             float* R_vec_out, float* T_vec_out,
+                             float* cand_R, float* cand_T, int* n_cand, int* chosen)
 {
     ERP_ARG(ctx && R_vec_out && T_vec_out && H >= 1 && H <= 4096, ERP_E_ARG, "erp_initial_guess: bad argument");
     ERP_ARG(S >= 8 && m >= S, ERP_E_TOO_FEW_POINTS,
@@ -763,13 +832,10 @@ ERP_API int erp_initial_guess(erp_ctx* ctx, const double* l3, const double* r3, 
         ERP_TRY(erp_libstdcxx_sample_table(m, H, S, 1, replay.data()));
         samples = replay.data();
     }
-    DeviceGuard g(ctx->device);
     int st = ERP_OK;
     float* dP = ctx->scratch<float>(S_POSE, (size_t)H * ERP_POSE_FLOATS + (size_t)H * 12 + 16, &st);
     ERP_TRY(st);
     // hypotheses solved exactly as erp_eight_point_batch does (pose included)
-    double *dl, *dr;
-    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, nullptr, nullptr));
     for (size_t i = 0; i < (size_t)H * S; i++)
         ERP_ARG(samples[i] >= 0 && samples[i] < m, ERP_E_ARG, "sample index %d out of range [0,%d)", samples[i], m);
     int32_t* d_s = ctx->scratch<int32_t>(S_SAMPLES, (size_t)H * S, &st);
@@ -802,6 +868,18 @@ ERP_API int erp_initial_guess(erp_ctx* ctx, const double* l3, const double* r3, 
     return ERP_OK;
 }
 
+ERP_API int erp_initial_guess(erp_ctx* ctx, const double* l3, const double* r3, int m,
+                              const int32_t* samples, int H, int S,
+                              float* R_vec_out, float* T_vec_out,
+                              float* cand_R, float* cand_T, int* n_cand, int* chosen)
+{
+    ERP_ARG(ctx && m >= 0, ERP_E_ARG, "erp_initial_guess: bad argument");
+    DeviceGuard g(ctx->device);
+    double *dl, *dr;
+    ERP_TRY(stage_bearings(ctx, l3, r3, m, &dl, &dr, nullptr, nullptr));
+    return initial_guess_dev(ctx, dl, dr, m, samples, H, S, R_vec_out, T_vec_out, cand_R, cand_T, n_cand, chosen);
+}
+
 ERP_API int erp_find(erp_ctx* ctx, int width, int height, const void* left_xy, const void* right_xy,
                      size_t stride_bytes, int match_size, const int32_t* samples, int H, int S,
                      float* R_vec_out, float* T_vec_out)
@@ -810,9 +888,17 @@ ERP_API int erp_find(erp_ctx* ctx, int width, int height, const void* left_xy, c
     if (H <= 0) H = 80;                               // src/eight_point.cpp:99
     if (S <= 0) S = (int)(match_size * 0.25);         // src/eight_point.cpp:102
     ERP_ARG(S >= 8, ERP_E_TOO_FEW_POINTS, "erp_find: match_size %d gives sample size %d < 8", match_size, S);
-    std::vector<double> l((size_t)match_size * 3), r((size_t)match_size * 3);
-    ERP_TRY(erp_bearings_from_pixels(ctx, left_xy, stride_bytes, match_size, width, height, l.data()));
-    ERP_TRY(erp_bearings_from_pixels(ctx, right_xy, stride_bytes, match_size, width, height, r.data()));
-    return erp_initial_guess(ctx, l.data(), r.data(), match_size, samples, H, S, R_vec_out, T_vec_out,
-                             nullptr, nullptr, nullptr, nullptr);
+    ERP_ARG(width > 0 && height > 0 && stride_bytes >= 8 && stride_bytes % 4 == 0, ERP_E_ARG, "erp_find: bad image size or stride");
+    // keypoints up once; the bearings (src/eight_point.cpp:163-186) never leave the device
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    float* d_xy = ctx->scratch<float>(S_XY, (size_t)match_size * 4, &st);
+    ERP_TRY(st);
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, match_size, &b));
+    ERP_TRY(upload_rows(ctx, d_xy, left_xy, match_size, 8, stride_bytes));
+    ERP_TRY(upload_rows(ctx, d_xy + (size_t)match_size * 2, right_xy, match_size, 8, stride_bytes));
+    ERP_TRY(bearings_pair_chain(ctx, d_xy, d_xy + (size_t)match_size * 2, 8, match_size, width, height, b.l3, b.r3, b.l4, b.r4,
+                                nullptr, nullptr));
+    return initial_guess_dev(ctx, b.l3, b.r3, match_size, samples, H, S, R_vec_out, T_vec_out, nullptr, nullptr, nullptr, nullptr);
 }

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -57,11 +58,13 @@ enum ScratchId {
     S_TC_Q, S_TC_T, S_TC_QN, S_TC_TN, S_TC_CAND, S_TC_LIST, S_TC_MISC,
     S_RS_IDX, S_RS_DIST, S_RS_D2, S_RS_PARTIAL,
     S_SC_E, S_SC_E2, S_SC_K, S_SC_MISC, S_SC_BOUNDS, S_SC_LIST,
-    S_IMG_IN, S_IMG_OUT,
+    S_IMG_IN, S_IMG_OUT, S_RESULT, S_GATHER, S_XCHG,
     S_COUNT_
 };
 
 } // namespace erp
+
+namespace erp { struct Comm; }
 
 struct erp_ctx {
     int device = 0;
@@ -76,6 +79,8 @@ struct erp_ctx {
     int32_t* sc_misc_dev = nullptr;                 // device words of the last tensor-core best search: ., max c_lo, list length
     int32_t* tc_misc_dev = nullptr;                 // device words of the last tcgen05 call: re-scan count, ., deviation
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around the dominant distance kernel
+    cudaEvent_t ev_stage[4] = {};                   // one pair: start, matches filtered, correspondences gathered, pose done
+    erp::Comm* comm = nullptr;                      // multi-GPU: this context's rank of an NCCL clique (dist.cu)
     std::vector<cudaEvent_t> ev_score;              // pairs around the scoring kernel launches of the last RANSAC call
     int n_ev_score = 0;                             // events used by that call
     erp::Buf dev[erp::S_COUNT_];
@@ -117,6 +122,34 @@ struct DeviceGuard {
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+#ifdef __CUDACC__
+__device__ __forceinline__ float tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// a length that lives on the device (the match count) capped by the capacity the launch was sized for
+__device__ __forceinline__ int dev_len(const int32_t* __restrict__ n_dev, int cap)
+{
+    if (!n_dev) return cap;
+    const int n = *n_dev;
+    return n < 0 ? 0 : (n < cap ? n : cap);
+}
+#endif
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: one bit per device ordinal and kernel
+// (a process may hold contexts on several GPUs).  Setting it twice is harmless, so the flag needs no lock.
+template <class Kernel>
+inline int ensure_dynamic_smem(erp_ctx* ctx, Kernel kernel, int bytes, std::atomic<uint64_t>& done)
+{
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return ERP_OK;
+    ERP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
+    return ERP_OK;
+}
+
 // next event of the scoring-kernel timer (created on demand, reused across calls)
 inline int score_event(erp_ctx* ctx, cudaEvent_t* ev)
 {
@@ -149,11 +182,46 @@ int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int 
 int knn2_exact_rescan(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
                       const int32_t* d_list, const int32_t* d_count, int max_rows,
                       int32_t* d_idx2, float* d_dist2, double* d_d2);
-int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m, float tau,
+// ---- RANSAC chain (score.cu, score_tc.cu, geometry.cu): every length that depends on the match count is read from
+// device memory (d_m, capped by m_cap, the size the launches are made for), so nothing between the matcher and the
+// final result copy waits for the host
+constexpr int RANSAC_CHUNK = 1 << 20;
+struct ScoreTcBuffers { float *Es, *Es2, *Ks; int32_t *w, *upper, *list; };
+struct Min8Fused { float* Es = nullptr; float big = 0.f; int32_t* upper = nullptr; int32_t* w = nullptr; };
+int score_tc_buffers(erp_ctx* ctx, int H, int m_cap, ScoreTcBuffers* b);
+int score_tc_prepare(erp_ctx* ctx, const ScoreTcBuffers& b, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m);
+int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap,
+                    float tau, uint64_t hyp0, bool es_ready, int32_t* d_counts_scratch, uint64_t* d_best);
+float score_tc_big(float tau);
+int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau,
                   uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best);
 int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,
-                    const float* d_l4, const float* d_r4, int m, float tau, uint64_t hyp0,
+                    const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau, uint64_t hyp0,
                     int32_t* d_counts, uint64_t* d_best);
 bool score_tc_preferred(int H, int m);
+bool ransac_uses_tc(erp_ctx* ctx, int H, int m_cap, int metric);
+int ransac_search(erp_ctx* ctx, const double* d_l3, const double* d_r3, const float* d_l4, const float* d_r4, int m_cap,
+                  const int32_t* d_m, uint64_t seed, uint64_t hyp_offset, int H, int S, int metric, float tau, bool k_ready,
+                  uint64_t* d_packed);
+int ransac_finish(erp_ctx* ctx, const double* d_l3, const double* d_r3, const float* d_l4, const float* d_r4, int m_cap,
+                  const int32_t* d_m, uint64_t seed, const uint64_t* d_packed, int S, int metric, float tau,
+                  uint8_t* d_mask, erp_ransac_result* d_result);
+struct PoseBuffers { double *l3, *r3; float *l4, *r4; uint8_t* mask; erp_ransac_result* res; };
+constexpr size_t W_WORDS_BYTES = 24 * sizeof(int32_t);     // == W_WORDS (score_common.cuh)
+int pose_chain_buffers(erp_ctx* ctx, int m_cap, PoseBuffers* b);
+int pose_chain_tail(erp_ctx* ctx, const double* dl, const double* dr, const float* dl4, const float* dr4, int m_cap, const int32_t* d_m,
+                    uint64_t seed, uint64_t hyp_offset, int H, int S, int metric, float tau, bool k_ready, bool reduce,
+                    uint8_t* d_mask, erp_ransac_result* d_res);
+// multi-GPU (dist.cu)
+int comm_allreduce_best(erp_ctx* ctx, uint64_t* d_packed);
+void comm_release(erp_ctx* ctx);
+int gather_bearings_chain(erp_ctx* ctx, const erp_dmatch* d_matches, int n_cap, const int32_t* d_n, const void* d_left_xy,
+                          const void* d_right_xy, size_t stride, int q_offset, int W, int H, double* d_l3, double* d_r3,
+                          float* d_l4, float* d_r4, float* Ks, int32_t* w);
+int gather_slots_chain(erp_ctx* ctx, const erp_dmatch* d_slots, int n_ranks, int slot_records, int n_cap, erp_dmatch* d_out,
+                       int32_t* d_n_out, const void* d_left_xy, const void* d_right_xy, size_t stride, int W, int H,
+                       double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w);
+int bearings_pair_chain(erp_ctx* ctx, const void* d_left_xy, const void* d_right_xy, size_t stride, int n, int W, int H,
+                        double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w);
 
 } // namespace erp

@@ -1,0 +1,574 @@
+// dist.cu -- one ERP pair split over several B200s (SURVEY 8e / north_star): query rows and hypothesis ids per GPU,
+// an all-gather of the per-rank match lists, ONE 8-byte max all-reduce of the packed best model, and a min all-reduce
+// for cross-check.  NCCL over NVLink / NVSwitch; the library does not link NCCL, it dlopen()s libnccl.so.2 on first use
+// (inside a torchrun rank that resolves to the copy torch already loaded, otherwise to the system one).
+//
+// Two cliques: erp_comm_init (one process per GPU, the caller distributes the unique id) and erp_group (one process,
+// one worker thread per device, ncclCommInitAll): the collectives are tiny (8 B, <= 1.6 MB, 25.6 MB for the train
+// all-gather of host-buffer calls), so a hand-written peer-memory kernel has nothing to overlap -- what matters is
+// that nothing between them waits for the host (the match count stays on the device, common.cuh: RANSAC chain).
+#include "score_common.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: every call goes through the table below
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+namespace erp {
+
+// ------------------------------------------------------------------------------------------ NCCL at run time
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+    std::string why;
+};
+
+static NcclApi load_nccl()
+{
+    NcclApi a;
+    const char* names[] = {getenv("ERP_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle) break;
+        a.why = dlerror();
+    }
+    if (!a.handle) return a;
+#define ERP_SYM(name) a.name = reinterpret_cast<decltype(a.name)>(dlsym(a.handle, "nccl" #name)); if (!a.name) { a.why = "symbol nccl" #name " missing"; a.handle = nullptr; return a; }
+    ERP_SYM(GetUniqueId) ERP_SYM(CommInitRank) ERP_SYM(CommInitAll) ERP_SYM(CommDestroy) ERP_SYM(AllReduce) ERP_SYM(AllGather)
+    ERP_SYM(GetErrorString) ERP_SYM(GetVersion)
+#undef ERP_SYM
+    return a;
+}
+static const NcclApi& nccl()
+{
+    static const NcclApi api = load_nccl();     // magic static: loaded once, thread safe
+    return api;
+}
+static int need_nccl()
+{
+    if (nccl().handle) return ERP_OK;
+    set_error("NCCL is not available (%s); multi-GPU calls need libnccl.so.2", nccl().why.c_str());
+    return ERP_E_NCCL;
+}
+#define ERP_NCCL(call)                                                                              \
+    do {                                                                                            \
+        ncclResult_t r_ = (call);                                                                   \
+        if (r_ != ncclSuccess) {                                                                    \
+            erp::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, nccl().GetErrorString(r_)); \
+            return ERP_E_NCCL;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+void comm_release(erp_ctx* ctx)
+{
+    if (!ctx->comm) return;
+    if (ctx->comm->comm && nccl().handle) nccl().CommDestroy(ctx->comm->comm);
+    delete ctx->comm;
+    ctx->comm = nullptr;
+}
+
+static inline int comm_size(const erp_ctx* ctx) { return ctx->comm ? ctx->comm->nranks : 1; }
+static inline int comm_rank(const erp_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
+
+static inline void shard_range(int n, int rank, int world, int* lo, int* hi)
+{
+    const int base = n / world, rem = n % world;
+    *lo = rank * base + (rank < rem ? rank : rem);
+    *hi = *lo + base + (rank < rem ? 1 : 0);
+}
+
+int comm_allreduce_best(erp_ctx* ctx, uint64_t* d_packed)
+{
+    if (comm_size(ctx) == 1) return ERP_OK;
+    // the packed word is < 2^63 (counts are < 2^31), unsigned max orders (count, then lowest id)
+    ERP_NCCL(nccl().AllReduce(d_packed, d_packed, 1, ncclUint64, ncclMax, ctx->comm->comm, ctx->stream));
+    return ERP_OK;
+}
+
+// candidates for the second reduction of the cross-check: my query id where I attain the global minimum
+__global__ void cross_candidates_kernel(const double* __restrict__ mine_d2, const double* __restrict__ gmin_d2, int32_t* __restrict__ best_q, int nt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt && !(mine_d2[i] == gmin_d2[i])) best_q[i] = 0x7fffffff;
+}
+__global__ void fill_reverse_kernel(int32_t* __restrict__ best_q, double* __restrict__ best_d2, int nt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nt) { best_q[i] = 0x7fffffff; best_d2[i] = INFINITY; }
+}
+
+static int comm_cross_check(erp_ctx* ctx, int32_t* d_best_q, double* d_best_d2, int nt)
+{
+    if (comm_size(ctx) == 1 || nt == 0) return ERP_OK;
+    int st = ERP_OK;
+    double* gmin = ctx->scratch<double>(S_REVD2, (size_t)nt * 2, &st) + nt;
+    ERP_TRY(st);
+    ERP_NCCL(nccl().AllReduce(d_best_d2, gmin, (size_t)nt, ncclDouble, ncclMin, ctx->comm->comm, ctx->stream));
+    cross_candidates_kernel<<<cdiv(nt, 256), 256, 0, ctx->stream>>>(d_best_d2, gmin, d_best_q, nt);
+    ERP_LAUNCH(ctx, "cross_candidates_kernel");
+    ERP_NCCL(nccl().AllReduce(d_best_q, d_best_q, (size_t)nt, ncclInt32, ncclMin, ctx->comm->comm, ctx->stream));
+    ERP_CUDA(cudaMemcpyAsync(d_best_d2, gmin, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ERP_OK;
+}
+
+// this rank's rows of the query set against the whole train set: 2-NN, (reduced) cross-check, ratio filter.
+// Matches carry global query ids.  d_out / d_n_out: device.
+static int match_shard_dev(erp_ctx* ctx, const float* d_q_shard, int lo, int hi, const float* d_t, int nt, int dim, float ratio,
+                           int cross_check, erp_dmatch* d_out, int32_t* d_n_out)
+{
+    const int nq = hi - lo;
+    int st = ERP_OK;
+    int32_t* idx2 = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
+    float* dist2 = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
+    ERP_TRY(st);
+    if (nq > 0) ERP_TRY(erp_knn2_dev(ctx, d_q_shard, nq, d_t, nt, dim, idx2, dist2, nullptr));
+    int32_t* rev = nullptr;
+    if (cross_check) {
+        rev = ctx->scratch<int32_t>(S_REVQ, (size_t)nt, &st);
+        double* rev_d2 = ctx->scratch<double>(S_REVD2, (size_t)nt * 2, &st);
+        ERP_TRY(st);
+        if (nq > 0) ERP_TRY(erp_nn1_reverse_dev(ctx, d_q_shard, nq, d_t, nt, dim, lo, rev, rev_d2));
+        else {
+            fill_reverse_kernel<<<cdiv(nt, 256), 256, 0, ctx->stream>>>(rev, rev_d2, nt);
+            ERP_LAUNCH(ctx, "fill_reverse_kernel");
+        }
+        ERP_TRY(comm_cross_check(ctx, rev, rev_d2, nt));
+    }
+    return erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, lo, d_out, d_n_out);
+}
+
+} // namespace erp
+
+using namespace erp;
+
+// ======================================================================================
+ERP_API int erp_shard_range(int n, int rank, int nranks, int* lo, int* hi)
+{
+    ERP_ARG(n >= 0 && nranks >= 1 && rank >= 0 && rank < nranks && lo && hi, ERP_E_ARG, "erp_shard_range: bad argument");
+    shard_range(n, rank, nranks, lo, hi);
+    return ERP_OK;
+}
+
+ERP_API int erp_comm_unique_id(void* id_out)
+{
+    ERP_ARG(id_out, ERP_E_ARG, "erp_comm_unique_id: null buffer");
+    ERP_TRY(need_nccl());
+    static_assert(sizeof(ncclUniqueId) == ERP_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ERP_NCCL(nccl().GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return ERP_OK;
+}
+
+ERP_API int erp_comm_init(erp_ctx* ctx, int nranks, int rank, const void* id)
+{
+    ERP_ARG(ctx && id && nranks >= 1 && rank >= 0 && rank < nranks, ERP_E_ARG, "erp_comm_init: bad argument");
+    ERP_ARG(nranks <= 64, ERP_E_LIMIT, "erp_comm_init: at most 64 ranks");
+    comm_release(ctx);
+    if (nranks == 1) return ERP_OK;
+    ERP_TRY(need_nccl());
+    DeviceGuard g(ctx->device);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    Comm* c = new Comm();
+    c->nranks = nranks; c->rank = rank;
+    ncclResult_t r = nccl().CommInitRank(&c->comm, nranks, uid, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank(rank %d of %d) -> %s", rank, nranks, nccl().GetErrorString(r));
+        delete c;
+        return ERP_E_NCCL;
+    }
+    ctx->comm = c;
+    return ERP_OK;
+}
+
+ERP_API int erp_comm_destroy(erp_ctx* ctx)
+{
+    ERP_ARG(ctx, ERP_E_ARG, "erp_comm_destroy: null context");
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    comm_release(ctx);
+    return ERP_OK;
+}
+
+ERP_API int erp_comm_size(erp_ctx* ctx) { return ctx ? comm_size(ctx) : 0; }
+ERP_API int erp_comm_rank(erp_ctx* ctx) { return ctx ? comm_rank(ctx) : -1; }
+
+ERP_API int erp_comm_allreduce_best_dev(erp_ctx* ctx, uint64_t* d_packed)
+{
+    ERP_ARG(ctx && d_packed, ERP_E_ARG, "erp_comm_allreduce_best_dev: bad argument");
+    DeviceGuard g(ctx->device);
+    return comm_allreduce_best(ctx, d_packed);
+}
+
+ERP_API int erp_comm_cross_check_dev(erp_ctx* ctx, int32_t* d_best_q, double* d_best_d2, int nt)
+{
+    ERP_ARG(ctx && d_best_q && d_best_d2 && nt >= 0, ERP_E_ARG, "erp_comm_cross_check_dev: bad argument");
+    DeviceGuard g(ctx->device);
+    return comm_cross_check(ctx, d_best_q, d_best_d2, nt);
+}
+
+ERP_API int erp_pair_pose_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_total, const float* d_t, int nt, int dim,
+                                   float ratio, int cross_check,
+                                   const void* d_left_xy, const void* d_right_xy, size_t kp_stride_bytes, int width, int height,
+                                   uint64_t seed, int H_total, int S, int metric, float tau,
+                                   erp_dmatch* d_matches, int32_t* d_n_matches, uint8_t* d_mask, erp_ransac_result* d_result)
+{
+    ERP_ARG(ctx, ERP_E_ARG, "erp_pair_pose_dist_dev: null context");
+    const int G = comm_size(ctx), rank = comm_rank(ctx);
+    if (G == 1)
+        return erp_pair_pose_dev(ctx, d_q_shard, nq_total, d_t, nt, dim, ratio, cross_check, d_left_xy, d_right_xy, kp_stride_bytes,
+                                 width, height, seed, H_total, S, metric, tau, d_matches, d_n_matches, d_mask, d_result);
+    ERP_ARG(nq_total >= 1 && nt >= 2, ERP_E_TOO_FEW_TRAIN, "erp_pair_pose_dist_dev: nq %d, nt %d", nq_total, nt);
+    ERP_ARG(dim > 0 && dim % 4 == 0 && dim <= 512, ERP_E_DIM, "erp_pair_pose_dist_dev: descriptor dimension %d", dim);
+    ERP_ARG(d_t && d_matches && d_n_matches && d_result && width > 0 && height > 0, ERP_E_ARG, "erp_pair_pose_dist_dev: bad argument");
+    ERP_ARG(d_left_xy && d_right_xy && kp_stride_bytes >= 8 && kp_stride_bytes % 4 == 0, ERP_E_ARG, "erp_pair_pose_dist_dev: bad keypoints");
+    ERP_ARG(S >= 8 && S <= 32 && metric >= 0 && metric <= 2, ERP_E_ARG, "erp_pair_pose_dist_dev: sample size / metric");
+    ERP_ARG(H_total >= G && (uint64_t)H_total <= 0xFFFFFFFFull, ERP_E_ARG, "erp_pair_pose_dist_dev: %d hypotheses for %d ranks", H_total, G);
+    DeviceGuard g(ctx->device);
+    int lo, hi, hlo, hhi;
+    shard_range(nq_total, rank, G, &lo, &hi);
+    shard_range(H_total, rank, G, &hlo, &hhi);
+    ERP_ARG(hi == lo || d_q_shard, ERP_E_ARG, "erp_pair_pose_dist_dev: null query shard");
+    // slots of the match exchange: [header | up to cap records] per rank
+    const int cap = cdiv(nq_total, G), slot = cap + 1;
+    int st = ERP_OK;
+    erp_dmatch* slots = ctx->scratch<erp_dmatch>(S_XCHG, (size_t)slot * G, &st);
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, nq_total, &b));
+    const bool tc = ransac_uses_tc(ctx, hhi - hlo, nq_total, metric);
+    ScoreTcBuffers sb = {};
+    if (tc) ERP_TRY(score_tc_buffers(ctx, (hhi - hlo) < RANSAC_CHUNK ? (hhi - hlo) : RANSAC_CHUNK, nq_total, &sb));
+    ERP_TRY(st);
+    erp_dmatch* mine = slots + (size_t)slot * rank;
+
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[0], ctx->stream));
+    ERP_CUDA(cudaMemsetAsync(mine, 0, sizeof(erp_dmatch), ctx->stream));
+    ERP_TRY(match_shard_dev(ctx, d_q_shard, lo, hi, d_t, nt, dim, ratio, cross_check, mine + 1, &mine->queryIdx));
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[1], ctx->stream));
+    // in place: rank r's slot is already at its position of the receive buffer
+    ERP_NCCL(nccl().AllGather(mine, slots, (size_t)slot * sizeof(erp_dmatch), ncclInt8, ctx->comm->comm, ctx->stream));
+    if (tc) ERP_CUDA(cudaMemsetAsync(sb.w, 0, W_WORDS_BYTES, ctx->stream));
+    ERP_TRY(gather_slots_chain(ctx, slots, G, slot, nq_total, d_matches, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes,
+                               width, height, b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[2], ctx->stream));
+    ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, nq_total, d_n_matches, seed, (uint64_t)hlo, hhi - hlo, S, metric, tau, tc, true,
+                            d_mask ? d_mask : b.mask, d_result));
+    ERP_CUDA(cudaEventRecord(ctx->ev_stage[3], ctx->stream));
+    return ERP_OK;
+}
+
+namespace erp {
+
+// upload of one rank's share for a host-buffer call: the query shard, 1/G of the train rows (then all-gathered over
+// NVLink into the replicated train set) -- G times less PCIe traffic per GPU than uploading everything everywhere
+static int upload_sharded(erp_ctx* ctx, const float* q, int lo, int hi, size_t qs, const float* t, int nt, size_t ts, int dim,
+                          float** dq_out, float** dt_out)
+{
+    const int G = comm_size(ctx), rank = comm_rank(ctx);
+    const size_t row = (size_t)dim * sizeof(float);
+    const int tcap = cdiv(nt, G);                    // train rows per rank in the all-gather (the last block may be short)
+    int st = ERP_OK;
+    float* dq = ctx->scratch<float>(S_Q, (size_t)(hi - lo) * dim + 4, &st);
+    float* dt = ctx->scratch<float>(S_T, (size_t)tcap * G * dim + 4, &st);
+    ERP_TRY(st);
+    if (hi > lo) {
+        if (qs == row) ERP_CUDA(cudaMemcpyAsync(dq, reinterpret_cast<const char*>(q) + (size_t)lo * qs, row * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+        else ERP_CUDA(cudaMemcpy2DAsync(dq, row, reinterpret_cast<const char*>(q) + (size_t)lo * qs, qs, row, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int t0 = rank * tcap < nt ? rank * tcap : nt, t1 = (rank + 1) * tcap < nt ? (rank + 1) * tcap : nt;
+    if (t1 > t0) {
+        float* dst = dt + (size_t)t0 * dim;
+        if (ts == row) ERP_CUDA(cudaMemcpyAsync(dst, reinterpret_cast<const char*>(t) + (size_t)t0 * ts, row * (t1 - t0), cudaMemcpyHostToDevice, ctx->stream));
+        else ERP_CUDA(cudaMemcpy2DAsync(dst, row, reinterpret_cast<const char*>(t) + (size_t)t0 * ts, ts, row, t1 - t0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (G > 1)
+        ERP_NCCL(nccl().AllGather(dt + (size_t)rank * tcap * dim, dt, (size_t)tcap * dim, ncclFloat, ctx->comm->comm, ctx->stream));
+    *dq_out = dq; *dt_out = dt;
+    return ERP_OK;
+}
+
+static int upload_xy(erp_ctx* ctx, float* d_dst, const void* src, int rows, size_t stride)
+{
+    if (rows == 0) return ERP_OK;
+    if (stride == 8) ERP_CUDA(cudaMemcpyAsync(d_dst, src, (size_t)8 * rows, cudaMemcpyHostToDevice, ctx->stream));
+    else ERP_CUDA(cudaMemcpy2DAsync(d_dst, 8, src, stride, 8, rows, cudaMemcpyHostToDevice, ctx->stream));
+    return ERP_OK;
+}
+
+} // namespace erp
+
+ERP_API int erp_pair_pose_dist(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                               int dim, float ratio, int cross_check,
+                               const void* left_xy, const void* right_xy, size_t kp_stride_bytes, int width, int height,
+                               uint64_t seed, int H, int S, int metric, float tau,
+                               erp_dmatch* matches_out, int* n_matches, erp_ransac_result* result, uint8_t* mask)
+{
+    ERP_ARG(ctx, ERP_E_ARG, "erp_pair_pose_dist: null context");
+    if (comm_size(ctx) == 1)
+        return erp_pair_pose(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, ratio, cross_check, left_xy, right_xy,
+                             kp_stride_bytes, width, height, seed, H, S, metric, tau, matches_out, n_matches, result, mask);
+    ERP_ARG(n_matches && result && matches_out && q && t && left_xy && right_xy, ERP_E_ARG, "erp_pair_pose_dist: null argument");
+    *n_matches = 0;
+    ERP_ARG(nq >= 1 && nt >= 2, ERP_E_TOO_FEW_TRAIN, "erp_pair_pose_dist: nq %d, nt %d", nq, nt);
+    ERP_ARG(dim > 0 && dim % 4 == 0 && dim <= 512, ERP_E_DIM, "erp_pair_pose_dist: descriptor dimension %d", dim);
+    const size_t row = (size_t)dim * sizeof(float);
+    ERP_ARG(q_stride_bytes >= row && t_stride_bytes >= row && kp_stride_bytes >= 8 && kp_stride_bytes % 4 == 0, ERP_E_ARG,
+            "erp_pair_pose_dist: bad stride");
+    DeviceGuard g(ctx->device);
+    const int G = comm_size(ctx), rank = comm_rank(ctx);
+    int lo, hi;
+    shard_range(nq, rank, G, &lo, &hi);
+    int st = ERP_OK;
+    erp_dmatch* d_out = ctx->scratch<erp_dmatch>(S_OUT, (size_t)nq, &st);
+    int32_t* d_n = ctx->scratch<int32_t>(S_NOUT, 4, &st);
+    float* d_xy = ctx->scratch<float>(S_XY, ((size_t)nq + nt) * 2, &st);
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, nq, &b));
+    ERP_TRY(st);
+    float *dq, *dt;
+    ERP_TRY(upload_sharded(ctx, q, lo, hi, q_stride_bytes, t, nt, t_stride_bytes, dim, &dq, &dt));
+    ERP_TRY(upload_xy(ctx, d_xy, left_xy, nq, kp_stride_bytes));
+    ERP_TRY(upload_xy(ctx, d_xy + (size_t)nq * 2, right_xy, nt, kp_stride_bytes));
+    ERP_TRY(erp_pair_pose_dist_dev(ctx, dq, nq, dt, nt, dim, ratio, cross_check, d_xy, d_xy + (size_t)nq * 2, 8, width, height,
+                                   seed, H, S, metric, tau, d_out, d_n, b.mask, b.res));
+    // the host waits for the exchange only; the records come back while the hypotheses are being scored
+    int32_t n = 0;
+    ERP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage[2], 0));
+    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    *n_matches = n;
+    if (n > 0) ERP_CUDA(cudaMemcpyAsync(matches_out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ERP_CUDA(cudaMemcpyAsync(result, b.res, sizeof *result, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask && n > 0) ERP_CUDA(cudaMemcpyAsync(mask, b.mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    if (n < S) {
+        set_error("erp_pair_pose_dist: %d matches for sample size %d", n, S);
+        return ERP_E_TOO_FEW_POINTS;
+    }
+    return ERP_OK;
+}
+
+ERP_API int erp_knn2_match_dist(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                                int dim, float ratio, int cross_check, erp_dmatch* out, int* n_out)
+{
+    ERP_ARG(ctx, ERP_E_ARG, "erp_knn2_match_dist: null context");
+    if (comm_size(ctx) == 1) return erp_knn2_match(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, ratio, cross_check, out, n_out);
+    ERP_ARG(n_out, ERP_E_ARG, "erp_knn2_match_dist: n_out is null");
+    *n_out = 0;
+    ERP_ARG(nq >= 0 && nt >= 0, ERP_E_ARG, "erp_knn2_match_dist: negative size");
+    ERP_ARG(dim > 0 && dim % 4 == 0 && dim <= 512, ERP_E_DIM, "erp_knn2_match_dist: descriptor dimension %d", dim);
+    ERP_ARG(nq == 0 || nt >= 2, ERP_E_TOO_FEW_TRAIN, "erp_knn2_match_dist: k=2 needs at least 2 train descriptors, got %d", nt);
+    if (nq == 0) return ERP_OK;
+    const size_t row = (size_t)dim * sizeof(float);
+    ERP_ARG(q && t && q_stride_bytes >= row && t_stride_bytes >= row, ERP_E_ARG, "erp_knn2_match_dist: bad descriptor buffers");
+    DeviceGuard g(ctx->device);
+    int lo, hi;
+    shard_range(nq, comm_rank(ctx), comm_size(ctx), &lo, &hi);
+    ERP_ARG(hi == lo || out, ERP_E_ARG, "erp_knn2_match_dist: out is null");
+    int st = ERP_OK;
+    erp_dmatch* d_out = ctx->scratch<erp_dmatch>(S_OUT, (size_t)(hi - lo) + 1, &st);
+    int32_t* d_n = ctx->scratch<int32_t>(S_NOUT, 4, &st);
+    ERP_TRY(st);
+    float *dq, *dt;
+    ERP_TRY(upload_sharded(ctx, q, lo, hi, q_stride_bytes, t, nt, t_stride_bytes, dim, &dq, &dt));
+    ERP_TRY(match_shard_dev(ctx, dq, lo, hi, dt, nt, dim, ratio, cross_check, d_out, d_n));
+    int32_t n = 0;
+    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n > 0) {
+        ERP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *n_out = n;
+    return ERP_OK;
+}
+
+ERP_API int erp_knn2_match_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_total, const float* d_t, int nt, int dim,
+                                    float ratio, int cross_check, erp_dmatch* d_out, int32_t* d_n_out)
+{
+    ERP_ARG(ctx && d_n_out && nq_total >= 0 && nt >= 0, ERP_E_ARG, "erp_knn2_match_dist_dev: bad argument");
+    ERP_ARG(dim > 0 && dim % 4 == 0 && dim <= 512, ERP_E_DIM, "erp_knn2_match_dist_dev: descriptor dimension %d", dim);
+    ERP_ARG(nq_total == 0 || nt >= 2, ERP_E_TOO_FEW_TRAIN, "erp_knn2_match_dist_dev: k=2 needs at least 2 train descriptors, got %d", nt);
+    DeviceGuard g(ctx->device);
+    int lo, hi;
+    shard_range(nq_total, comm_rank(ctx), comm_size(ctx), &lo, &hi);
+    ERP_ARG(hi == lo || (d_q_shard && d_t && d_out), ERP_E_ARG, "erp_knn2_match_dist_dev: null buffer");
+    return match_shard_dev(ctx, d_q_shard, lo, hi, d_t, nt, dim, ratio, cross_check, d_out, d_n_out);
+}
+
+// ======================================================================================
+// one process, several devices: contexts + clique + one worker thread per device
+// ======================================================================================
+struct erp_group {
+    std::vector<erp_ctx*> ctx;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::function<int(int)> job;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    std::vector<int> status;
+    std::vector<std::string> error;
+
+    void worker(int rank)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<int(int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_job.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                fn = job;
+            }
+            int st = fn(rank);
+            std::string msg = st != ERP_OK ? erp_last_error() : "";
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                status[rank] = st;
+                error[rank] = msg;
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // runs fn(rank) on every worker; first failing rank's status and message are reported to the caller
+    int run(std::function<int(int)> fn)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = std::move(fn);
+            pending = (int)ctx.size();
+            generation++;
+        }
+        cv_job.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        for (size_t r = 0; r < ctx.size(); r++)
+            if (status[r] != ERP_OK) {
+                set_error("rank %zu: %s", r, error[r].c_str());
+                return status[r];
+            }
+        return ERP_OK;
+    }
+};
+
+ERP_API void erp_group_destroy(erp_group* g)
+{
+    if (!g) return;
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->stop = true;
+    }
+    g->cv_job.notify_all();
+    for (auto& t : g->workers) if (t.joinable()) t.join();
+    for (erp_ctx* c : g->ctx) if (c) erp_ctx_destroy(c);
+    delete g;
+}
+
+ERP_API int erp_group_create(const int* devices, int ndev, erp_group** out)
+{
+    ERP_ARG(out, ERP_E_ARG, "erp_group_create: out is null");
+    *out = nullptr;
+    ERP_ARG(devices && ndev >= 1 && ndev <= 64, ERP_E_ARG, "erp_group_create: 1..64 devices");
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++) ERP_ARG(devices[i] != devices[j], ERP_E_ARG, "erp_group_create: device %d listed twice", devices[i]);
+    if (ndev > 1) ERP_TRY(need_nccl());
+    erp_group* g = new erp_group();
+    g->ctx.assign(ndev, nullptr);
+    g->status.assign(ndev, ERP_OK);
+    g->error.assign(ndev, "");
+    for (int i = 0; i < ndev; i++) {
+        int st = erp_ctx_create(devices[i], &g->ctx[i]);
+        if (st != ERP_OK) { erp_group_destroy(g); return st; }
+    }
+    if (ndev > 1) {
+        std::vector<ncclComm_t> comms(ndev);
+        ncclResult_t r = nccl().CommInitAll(comms.data(), ndev, devices);
+        if (r != ncclSuccess) {
+            set_error("ncclCommInitAll over %d devices -> %s", ndev, nccl().GetErrorString(r));
+            erp_group_destroy(g);
+            return ERP_E_NCCL;
+        }
+        for (int i = 0; i < ndev; i++) {
+            Comm* c = new Comm();
+            c->comm = comms[i]; c->nranks = ndev; c->rank = i;
+            g->ctx[i]->comm = c;
+        }
+    }
+    for (int i = 0; i < ndev; i++) g->workers.emplace_back([g, i] { g->worker(i); });
+    *out = g;
+    return ERP_OK;
+}
+
+ERP_API int erp_group_size(erp_group* g) { return g ? (int)g->ctx.size() : 0; }
+ERP_API erp_ctx* erp_group_ctx(erp_group* g, int rank) { return g && rank >= 0 && rank < (int)g->ctx.size() ? g->ctx[rank] : nullptr; }
+
+ERP_API int erp_group_pair_pose(erp_group* g, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                                int dim, float ratio, int cross_check,
+                                const void* left_xy, const void* right_xy, size_t kp_stride_bytes, int width, int height,
+                                uint64_t seed, int H, int S, int metric, float tau,
+                                erp_dmatch* matches_out, int* n_matches, erp_ransac_result* result, uint8_t* mask)
+{
+    ERP_ARG(g && n_matches && result && matches_out, ERP_E_ARG, "erp_group_pair_pose: bad argument");
+    const int G = (int)g->ctx.size();
+    // every rank ends with the same records; rank 0 writes the caller's buffers, the others a scratch of their own
+    std::vector<std::vector<erp_dmatch>> other(G);
+    std::vector<erp_ransac_result> res(G);
+    std::vector<int> n(G, 0);
+    int st = g->run([&](int r) {
+        if (r != 0) other[r].resize((size_t)(nq > 0 ? nq : 1));
+        return erp_pair_pose_dist(g->ctx[r], q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, ratio, cross_check, left_xy, right_xy,
+                                  kp_stride_bytes, width, height, seed, H, S, metric, tau,
+                                  r == 0 ? matches_out : other[r].data(), &n[r], &res[r], r == 0 ? mask : nullptr);
+    });
+    *n_matches = n[0];
+    *result = res[0];
+    return st;
+}
+
+ERP_API int erp_group_knn2_match(erp_group* g, const float* q, int nq, size_t q_stride_bytes,
+                                 const float* t, int nt, size_t t_stride_bytes, int dim,
+                                 float ratio, int cross_check, erp_dmatch* out, int* n_out)
+{
+    ERP_ARG(g && n_out, ERP_E_ARG, "erp_group_knn2_match: bad argument");
+    *n_out = 0;
+    const int G = (int)g->ctx.size();
+    if (G == 1) return erp_knn2_match(g->ctx[0], q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, ratio, cross_check, out, n_out);
+    ERP_ARG(nq == 0 || out, ERP_E_ARG, "erp_group_knn2_match: out is null");
+    // rank r's part lands at its shard offset of the caller's buffer (a shard never yields more records than rows) and is
+    // then moved down to close the gaps: rank order keeps ascending queryIdx
+    std::vector<int> n(G, 0), lo(G, 0), hi(G, 0);
+    for (int r = 0; r < G; r++) shard_range(nq > 0 ? nq : 0, r, G, &lo[r], &hi[r]);
+    int st = g->run([&](int r) {
+        return erp_knn2_match_dist(g->ctx[r], q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, ratio, cross_check,
+                                   out ? out + lo[r] : nullptr, &n[r]);
+    });
+    ERP_TRY(st);
+    int total = 0;
+    for (int r = 0; r < G; r++) {
+        if (n[r] > 0 && total != lo[r]) memmove(out + total, out + lo[r], sizeof(erp_dmatch) * (size_t)n[r]);
+        total += n[r];
+    }
+    *n_out = total;
+    return ERP_OK;
+}

@@ -9,7 +9,7 @@
 // without ever materialising A: S x 9 collapses to 45 doubles per hypothesis, which is what
 // lets a million hypotheses run concurrently.  The 3 x 3 SVDs (rank-2 projection and
 // cv::decomposeEssentialMat) are run one-sided exactly as OpenCV does.
-#include "common.cuh"
+#include "score_common.cuh"
 
 #include <float.h>
 
@@ -44,22 +44,95 @@ __device__ __forceinline__ void pixel_to_bearing(const float* p, int W, int H, d
     x = -sl * co; y = sl * so; z = cl;
 }
 
-// spherical_surf.cpp:155-162 (gather the matched keypoints) fused with eight_point.cpp:163-186
-__global__ void gather_bearings_kernel(const erp_dmatch* __restrict__ mt, int n, const char* __restrict__ lxy,
-                                       const char* __restrict__ rxy, size_t stride, int q_offset, int W, int H,
-                                       double* __restrict__ l3, double* __restrict__ r3,
-                                       float4* __restrict__ l4, float4* __restrict__ r4)
+// spherical_surf.cpp:155-162 (gather the matched keypoints) fused with eight_point.cpp:163-186.  The match count may live
+// on the device (n_dev; the launch covers n_cap slots).  With Ks the same pass also writes the correspondence operand of
+// the tensor-core hypothesis search and its m-dependent words (score_common.cuh: prep_k_slot) -- launched with whole warps.
+__global__ void gather_bearings_kernel(const erp_dmatch* __restrict__ mt, int n_cap, const int32_t* __restrict__ n_dev,
+                                       const char* __restrict__ lxy, const char* __restrict__ rxy, size_t stride, int q_offset,
+                                       int W, int H, double* __restrict__ l3, double* __restrict__ r3,
+                                       float4* __restrict__ l4, float4* __restrict__ r4, float* __restrict__ Ks, int32_t* __restrict__ w)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    erp_dmatch m = mt[i];
-    double x, y, z;
-    pixel_to_bearing(reinterpret_cast<const float*>(lxy + (size_t)(m.queryIdx - q_offset) * stride), W, H, x, y, z);
-    if (l3) { l3[3 * (size_t)i] = x; l3[3 * (size_t)i + 1] = y; l3[3 * (size_t)i + 2] = z; }
-    if (l4) l4[i] = make_float4((float)x, (float)y, (float)z, 0.f);
-    pixel_to_bearing(reinterpret_cast<const float*>(rxy + (size_t)m.trainIdx * stride), W, H, x, y, z);
-    if (r3) { r3[3 * (size_t)i] = x; r3[3 * (size_t)i + 1] = y; r3[3 * (size_t)i + 2] = z; }
-    if (r4) r4[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = dev_len(n_dev, n_cap);
+    float4 lf = make_float4(0.f, 0.f, 0.f, 0.f), rf = lf;
+    if (i < n) {
+        erp_dmatch m = mt[i];
+        double x, y, z;
+        pixel_to_bearing(reinterpret_cast<const float*>(lxy + (size_t)(m.queryIdx - q_offset) * stride), W, H, x, y, z);
+        if (l3) { l3[3 * (size_t)i] = x; l3[3 * (size_t)i + 1] = y; l3[3 * (size_t)i + 2] = z; }
+        lf = make_float4((float)x, (float)y, (float)z, 0.f);
+        if (l4) l4[i] = lf;
+        pixel_to_bearing(reinterpret_cast<const float*>(rxy + (size_t)m.trainIdx * stride), W, H, x, y, z);
+        if (r3) { r3[3 * (size_t)i] = x; r3[3 * (size_t)i + 1] = y; r3[3 * (size_t)i + 2] = z; }
+        rf = make_float4((float)x, (float)y, (float)z, 0.f);
+        if (r4) r4[i] = rf;
+    }
+    if (Ks) prep_k_slot(i, n, lf, rf, Ks, w);
+}
+
+// Multi-GPU form: the per-rank match lists arrive in fixed-size slots (all-gather; record 0 of a slot is a header whose
+// queryIdx holds the rank's count, the matches follow and already carry GLOBAL query ids).  This pass concatenates them
+// in rank order (= ascending queryIdx, feature_matcher.cpp:50-56) into `out`, publishes the total, and does the
+// gather + bearings + operand rows of gather_bearings_kernel on the fly.
+constexpr int GATHER_MAX_RANKS = 64;
+__global__ void gather_slots_kernel(const erp_dmatch* __restrict__ slots, int n_ranks, int slot_records, int n_cap,
+                                    erp_dmatch* __restrict__ out, int32_t* __restrict__ n_out,
+                                    const char* __restrict__ lxy, const char* __restrict__ rxy, size_t stride,
+                                    int W, int H, double* __restrict__ l3, double* __restrict__ r3,
+                                    float4* __restrict__ l4, float4* __restrict__ r4, float* __restrict__ Ks, int32_t* __restrict__ w)
+{
+    __shared__ int prefix[GATHER_MAX_RANKS + 1];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int r = 0; r < n_ranks; r++) {
+            prefix[r] = acc;
+            int c = slots[(size_t)r * slot_records].queryIdx;
+            acc += c < 0 ? 0 : (c < slot_records - 1 ? c : slot_records - 1);
+        }
+        prefix[n_ranks] = acc < n_cap ? acc : n_cap;
+    }
+    __syncthreads();
+    const int n = prefix[n_ranks];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_out = n;
+    float4 lf = make_float4(0.f, 0.f, 0.f, 0.f), rf = lf;
+    if (i < n) {
+        int r = 0;
+        while (r + 1 < n_ranks && prefix[r + 1] <= i) r++;
+        const erp_dmatch m = slots[(size_t)r * slot_records + 1 + (i - prefix[r])];
+        out[i] = m;
+        double x, y, z;
+        pixel_to_bearing(reinterpret_cast<const float*>(lxy + (size_t)m.queryIdx * stride), W, H, x, y, z);
+        l3[3 * (size_t)i] = x; l3[3 * (size_t)i + 1] = y; l3[3 * (size_t)i + 2] = z;
+        lf = make_float4((float)x, (float)y, (float)z, 0.f);
+        l4[i] = lf;
+        pixel_to_bearing(reinterpret_cast<const float*>(rxy + (size_t)m.trainIdx * stride), W, H, x, y, z);
+        r3[3 * (size_t)i] = x; r3[3 * (size_t)i + 1] = y; r3[3 * (size_t)i + 2] = z;
+        rf = make_float4((float)x, (float)y, (float)z, 0.f);
+        r4[i] = rf;
+    }
+    if (Ks) prep_k_slot(i, n, lf, rf, Ks, w);
+}
+
+// the same for keypoint pairs that are already gathered (erp_ransac_pixels): slot i of both views
+__global__ void bearings_pair_kernel(const char* __restrict__ lxy, const char* __restrict__ rxy, size_t stride, int n, int W, int H,
+                                     double* __restrict__ l3, double* __restrict__ r3, float4* __restrict__ l4, float4* __restrict__ r4,
+                                     float* __restrict__ Ks, int32_t* __restrict__ w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 lf = make_float4(0.f, 0.f, 0.f, 0.f), rf = lf;
+    if (i < n) {
+        double x, y, z;
+        pixel_to_bearing(reinterpret_cast<const float*>(lxy + (size_t)i * stride), W, H, x, y, z);
+        l3[3 * (size_t)i] = x; l3[3 * (size_t)i + 1] = y; l3[3 * (size_t)i + 2] = z;
+        lf = make_float4((float)x, (float)y, (float)z, 0.f);
+        l4[i] = lf;
+        pixel_to_bearing(reinterpret_cast<const float*>(rxy + (size_t)i * stride), W, H, x, y, z);
+        r3[3 * (size_t)i] = x; r3[3 * (size_t)i + 1] = y; r3[3 * (size_t)i + 2] = z;
+        rf = make_float4((float)x, (float)y, (float)z, 0.f);
+        r4[i] = rf;
+    }
+    if (Ks) prep_k_slot(i, n, lf, rf, Ks, w);
 }
 
 __global__ void pack4_kernel(const double* __restrict__ v3, int n, float4* __restrict__ v4)
@@ -116,15 +189,21 @@ constexpr int SMALL_S = 32;
 // One warp per hypothesis, S <= 32 (the minimal-sample RANSAC case, S = 8).
 // lane s builds row a_s = kron(l_s, r_s) (eight_point.cpp:28-36); lanes then own Gram entries.
 __global__ void __launch_bounds__(GW * 32)
-gram_small_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m,
+gram_small_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m_cap, const int32_t* __restrict__ m_dev,
                   const int32_t* __restrict__ samples, int H, int S, uint64_t seed, uint64_t hyp0,
-                  double* __restrict__ G /* H x 45 */)
+                  const uint64_t* __restrict__ packed_dev, double* __restrict__ G /* H x 45 */)
 {
     __shared__ double a[GW][SMALL_S][9];
     __shared__ int32_t smp[GW][SMALL_S];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x * GW + w;
     if (h >= H) return;
+    const int m = dev_len(m_dev, m_cap);
+    if (m < S) {                                            // too few correspondences (device count): a zero system
+        for (int e = lane; e < 45; e += 32) G[(size_t)h * 45 + e] = 0.0;
+        return;
+    }
+    if (packed_dev) hyp0 = 0xFFFFFFFFull - (*packed_dev & 0xFFFFFFFFull);      // replay of the winner: its id is in the packed word
     if (samples) { if (lane < S) smp[w][lane] = samples[(size_t)h * S + lane]; }
     else if (lane == 0) philox_sample(seed, hyp0 + h, m, S, smp[w]);
     __syncwarp();
@@ -463,12 +542,22 @@ solve_kernel(const double* __restrict__ Gin, int H, int max_sweeps,
 constexpr int MIN8_THREADS = 128;
 template <bool WANT_POSE>
 __global__ void __launch_bounds__(MIN8_THREADS)
-min8_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m,
-            const int32_t* __restrict__ samples, int H, uint64_t seed, uint64_t hyp0,
-            double* __restrict__ Eout, float* __restrict__ pose)
+min8_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m_cap, const int32_t* __restrict__ m_dev,
+            const int32_t* __restrict__ samples, int H, uint64_t seed, uint64_t hyp0, const uint64_t* __restrict__ packed_dev,
+            double* __restrict__ Eout, float* __restrict__ pose, const Min8Fused fused)
 {
     const int h = blockIdx.x * MIN8_THREADS + threadIdx.x;
+    // fused tail of the RANSAC chain: the hypothesis operand of the tensor-core search, its cleared bounds and pass A's shape
+    if (fused.Es && h == 0) { fused.w[W_DYN_A] = H; fused.w[W_DYN_A + 1] = 0; fused.w[W_DYN_A + 2] = fused.w[W_N0]; fused.w[W_DYN_A + 3] = fused.w[W_M]; }
     if (h >= H) return;
+    const int m = dev_len(m_dev, m_cap);
+    if (packed_dev) hyp0 = 0xFFFFFFFFull - (*packed_dev & 0xFFFFFFFFull);      // replay of the winner: its id is in the packed word
+    if (m < 8) {                                            // too few correspondences (device count): the zero matrix
+#pragma unroll
+        for (int k = 0; k < 9; k++) Eout[(size_t)h * 9 + k] = 0.0;
+        if (fused.Es) { zero_row(fused.Es + (size_t)h * 32); fused.upper[h] = 0; fused.upper[(size_t)H + h] = 0; }
+        return;
+    }
     int32_t idx[8];
     if (samples) {
 #pragma unroll
@@ -525,6 +614,12 @@ min8_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m,
 #pragma unroll
     for (int k = 0; k < 9; k++) E.v[k] = q[k] * inv;
     finish_hypothesis<WANT_POSE>(E, Eout + (size_t)h * 9, pose ? pose + (size_t)h * ERP_POSE_FLOATS : nullptr);
+    if (fused.Es) {
+        float e[9];
+        scale_E(Eout + (size_t)h * 9, e);
+        write_e_row(e, fused.big, fused.Es + (size_t)h * 32);
+        fused.upper[h] = 0; fused.upper[(size_t)H + h] = 0;
+    }
 }
 
 // ------------------------------------------------------------------ one 9x9 solve on one warp
@@ -532,13 +627,16 @@ min8_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m,
 // latency for a single refit).  Here lane k owns row/column k of G and column k of V in shared memory
 // and every rotation is applied by nine lanes at once; same pivot order and element formulas as
 // solve_kernel, so the two agree to the last bit.
+struct Solve1Smem { double G[9][9], V[9][9]; int flag[1]; };
+
+// one warp (lane k); Gin: the packed upper triangle in global or shared memory
 template <bool WANT_POSE>
-__global__ void __launch_bounds__(32)
-solve1_kernel(const double* __restrict__ Gin, int max_sweeps, double* __restrict__ Eout, float* __restrict__ pose)
+__device__ void solve1_warp(Solve1Smem& sm, const double* Gin, int max_sweeps, double* __restrict__ Eout, float* __restrict__ pose)
 {
-    __shared__ double G[9][9], V[9][9];
-    __shared__ int flag[1];
-    const int k = threadIdx.x;
+    double (&G)[9][9] = sm.G;
+    double (&V)[9][9] = sm.V;
+    int (&flag)[1] = sm.flag;
+    const int k = threadIdx.x & 31;
     if (k < 9)
         for (int j = 0; j < 9; j++) { G[k][j] = Gin[tri(k, j)]; V[k][j] = (k == j) ? 1.0 : 0.0; }
     __syncwarp();
@@ -597,6 +695,102 @@ solve1_kernel(const double* __restrict__ Gin, int max_sweeps, double* __restrict
     M3 E;
     for (int q = 0; q < 9; q++) E.v[q] = V[perm[8]][q];
     finish_hypothesis<WANT_POSE>(E, Eout, pose);
+}
+
+template <bool WANT_POSE>
+__global__ void __launch_bounds__(32)
+solve1_kernel(const double* __restrict__ Gin, int max_sweeps, double* __restrict__ Eout, float* __restrict__ pose)
+{
+    __shared__ Solve1Smem sm;
+    solve1_warp<WANT_POSE>(sm, Gin, max_sweeps, Eout, pose);
+}
+
+// ------------------------------------------------------------------ end of a RANSAC call, one launch
+// Inlier mask of the winning model, the Gram matrix of its inliers and the least-squares refit (eight_point.cpp:16-50 on
+// the inlier set): every block marks 256 correspondences and reduces their 45 Gram entries in a fixed order; the last
+// block to finish (one ticket) sums the per-block partials in block order (deterministic), solves the 9 x 9 system on its
+// first warp and writes the whole erp_ransac_result.  cnt: [0] inliers, [1] ticket (both zeroed by the caller).
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_SWEEPS = 12;
+template <int METRIC>
+__global__ void __launch_bounds__(FIN_THREADS)
+finish_kernel(const double* __restrict__ Eb, const uint64_t* __restrict__ packed_dev, const double* __restrict__ l3,
+              const double* __restrict__ r3, const float4* __restrict__ l4, const float4* __restrict__ r4, int m_cap,
+              const int32_t* __restrict__ m_dev, float tau, float tau2, float sin2, uint8_t* __restrict__ mask,
+              double* __restrict__ P /* gridDim.x x 45 */, int32_t* __restrict__ cnt, erp_ransac_result* __restrict__ out)
+{
+    __shared__ float Es[9];
+    __shared__ double red[FIN_THREADS / 32][45];
+    __shared__ double Gs[45];
+    __shared__ Solve1Smem sm;
+    __shared__ int last;
+    const int m = dev_len(m_dev, m_cap);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) scale_E(Eb, Es);
+    __syncthreads();
+    const int c = blockIdx.x * FIN_THREADS + threadIdx.x;
+    bool in = false;
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < m) {
+        float e[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) e[i] = Es[i];
+        const float4 l = l4[c], r = r4[c];
+        float k[9];
+        kron9(l, r, k);
+        in = inlier<METRIC>(e, k, l, r, tau, tau2, sin2);
+        if (mask) mask[c] = in ? 1 : 0;
+        if (in) {
+            const double lx = l3[3 * (size_t)c], ly = l3[3 * (size_t)c + 1], lz = l3[3 * (size_t)c + 2];
+            const double rx = r3[3 * (size_t)c], ry = r3[3 * (size_t)c + 1], rz = r3[3 * (size_t)c + 2];
+            v[0] = lx * rx; v[1] = lx * ry; v[2] = lx * rz;
+            v[3] = ly * rx; v[4] = ly * ry; v[5] = ly * rz;
+            v[6] = lz * rx; v[7] = lz * ry; v[8] = lz * rz;
+        }
+    }
+    const int n_in = __reduce_add_sync(0xffffffffu, in ? 1 : 0);
+    if (lane == 0 && n_in) atomicAdd(cnt, n_in);
+    if ((size_t)blockIdx.x * FIN_THREADS < (size_t)m) {
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+#pragma unroll
+            for (int j = i; j < 9; j++) {
+                double x = v[i] * v[j];
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                if (lane == 0) red[wid][e] = x;
+                e++;
+            }
+        __syncthreads();
+        if (threadIdx.x < 45) {
+            double x = 0.0;
+            for (int w = 0; w < FIN_THREADS / 32; w++) x += red[w][threadIdx.x];
+            P[(size_t)blockIdx.x * 45 + threadIdx.x] = x;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(cnt + 1, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nb = (m + FIN_THREADS - 1) / FIN_THREADS;
+    if (threadIdx.x < 45) {
+        double x = 0.0;
+        for (int b = 0; b < nb; b++) x += *reinterpret_cast<volatile const double*>(&P[(size_t)b * 45 + threadIdx.x]);
+        Gs[threadIdx.x] = x;
+    }
+    __syncthreads();
+    if (wid != 0) return;
+    solve1_warp<true>(sm, Gs, FIN_SWEEPS, out->E_refit, out->pose);
+    if (lane == 0) {
+        const uint64_t packed = *packed_dev;
+        out->packed = packed;
+        out->hyp_id = 0xFFFFFFFFull - (packed & 0xFFFFFFFFull);
+        out->count = (int32_t)(packed >> 32);
+        out->n_refit = *reinterpret_cast<volatile int32_t*>(cnt);
+        for (int i = 0; i < 9; i++) out->E_best[i] = Eb[i];
+    }
 }
 
 // ------------------------------------------------------------------ consensus pick (eight_point.cpp:117-149)
@@ -679,9 +873,9 @@ ERP_API int erp_gather_bearings_dev(erp_ctx* ctx, const erp_dmatch* d_matches, i
     if (n == 0) return ERP_OK;
     ERP_ARG(d_matches && d_left_xy && d_right_xy, ERP_E_ARG, "erp_gather_bearings_dev: null buffer");
     DeviceGuard g(ctx->device);
-    gather_bearings_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_matches, n, (const char*)d_left_xy, (const char*)d_right_xy,
+    gather_bearings_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_matches, n, nullptr, (const char*)d_left_xy, (const char*)d_right_xy,
                                                                  stride_bytes, q_offset, width, height, d_l3, d_r3,
-                                                                 (float4*)d_l4, (float4*)d_r4);
+                                                                 (float4*)d_l4, (float4*)d_r4, nullptr, nullptr);
     ERP_LAUNCH(ctx, "gather_bearings_kernel");
     return ERP_OK;
 }
@@ -698,12 +892,47 @@ ERP_API int erp_pack_float4_dev(erp_ctx* ctx, const double* d_v3, int n, float* 
 
 namespace erp {
 
+// gather of the matched keypoints + bearings with the match count on the device; Ks / w: also the correspondence
+// operand of the tensor-core search (w must have been cleared)
+int gather_bearings_chain(erp_ctx* ctx, const erp_dmatch* d_matches, int n_cap, const int32_t* d_n, const void* d_left_xy,
+                          const void* d_right_xy, size_t stride, int q_offset, int W, int H, double* d_l3, double* d_r3,
+                          float* d_l4, float* d_r4, float* Ks, int32_t* w)
+{
+    if (n_cap <= 0) return ERP_OK;
+    gather_bearings_kernel<<<cdiv(n_cap, 256), 256, 0, ctx->stream>>>(d_matches, n_cap, d_n, (const char*)d_left_xy, (const char*)d_right_xy,
+                                                                     stride, q_offset, W, H, d_l3, d_r3, (float4*)d_l4, (float4*)d_r4, Ks, w);
+    ERP_LAUNCH(ctx, "gather_bearings_kernel");
+    return ERP_OK;
+}
+
+int gather_slots_chain(erp_ctx* ctx, const erp_dmatch* d_slots, int n_ranks, int slot_records, int n_cap, erp_dmatch* d_out,
+                       int32_t* d_n_out, const void* d_left_xy, const void* d_right_xy, size_t stride, int W, int H,
+                       double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w)
+{
+    if (n_ranks > GATHER_MAX_RANKS) { set_error("more than %d ranks", GATHER_MAX_RANKS); return ERP_E_LIMIT; }
+    gather_slots_kernel<<<max(1, cdiv(n_cap, 256)), 256, 0, ctx->stream>>>(d_slots, n_ranks, slot_records, n_cap, d_out, d_n_out,
+                                                                          (const char*)d_left_xy, (const char*)d_right_xy, stride, W, H,
+                                                                          d_l3, d_r3, (float4*)d_l4, (float4*)d_r4, Ks, w);
+    ERP_LAUNCH(ctx, "gather_slots_kernel");
+    return ERP_OK;
+}
+
+int bearings_pair_chain(erp_ctx* ctx, const void* d_left_xy, const void* d_right_xy, size_t stride, int n, int W, int H,
+                        double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w)
+{
+    if (n <= 0) return ERP_OK;
+    bearings_pair_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const char*)d_left_xy, (const char*)d_right_xy, stride, n, W, H,
+                                                               d_l3, d_r3, (float4*)d_l4, (float4*)d_r4, Ks, w);
+    ERP_LAUNCH(ctx, "bearings_pair_kernel");
+    return ERP_OK;
+}
+
 // G for H hypotheses into d_G (H x 45)
-int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples,
-               int H, int S, uint64_t seed, uint64_t hyp0, double* d_G)
+int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_m, const int32_t* d_samples,
+               int H, int S, uint64_t seed, uint64_t hyp0, const uint64_t* d_packed, double* d_G)
 {
     if (S <= SMALL_S) {
-        gram_small_kernel<<<cdiv(H, GW), GW * 32, 0, ctx->stream>>>(d_l3, d_r3, m, d_samples, H, S, seed, hyp0, d_G);
+        gram_small_kernel<<<cdiv(H, GW), GW * 32, 0, ctx->stream>>>(d_l3, d_r3, m, d_m, d_samples, H, S, seed, hyp0, d_packed, d_G);
         ERP_LAUNCH(ctx, "gram_small_kernel");
         return ERP_OK;
     }
@@ -751,13 +980,35 @@ int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_po
 }
 
 // minimal samples (S = 8): sample, solve and project in one kernel
-int solve_min8(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples, int H,
-               uint64_t seed, uint64_t hyp0, double* d_E, float* d_pose)
+int solve_min8(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_m, const int32_t* d_samples, int H,
+               uint64_t seed, uint64_t hyp0, const uint64_t* d_packed, double* d_E, float* d_pose, const Min8Fused* fused)
 {
     if (H <= 0) return ERP_OK;
-    if (d_pose) min8_kernel<true><<<cdiv(H, MIN8_THREADS), MIN8_THREADS, 0, ctx->stream>>>(d_l3, d_r3, m, d_samples, H, seed, hyp0, d_E, d_pose);
-    else min8_kernel<false><<<cdiv(H, MIN8_THREADS), MIN8_THREADS, 0, ctx->stream>>>(d_l3, d_r3, m, d_samples, H, seed, hyp0, d_E, nullptr);
+    Min8Fused f;
+    if (fused) f = *fused;
+    if (d_pose) min8_kernel<true><<<cdiv(H, MIN8_THREADS), MIN8_THREADS, 0, ctx->stream>>>(d_l3, d_r3, m, d_m, d_samples, H, seed, hyp0, d_packed, d_E, d_pose, f);
+    else min8_kernel<false><<<cdiv(H, MIN8_THREADS), MIN8_THREADS, 0, ctx->stream>>>(d_l3, d_r3, m, d_m, d_samples, H, seed, hyp0, d_packed, d_E, nullptr, f);
     ERP_LAUNCH(ctx, "min8_kernel");
+    return ERP_OK;
+}
+
+int finish_launch(erp_ctx* ctx, const double* d_Eb, const uint64_t* d_packed, const double* d_l3, const double* d_r3,
+                  const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, int metric, float tau, float tau2, float sin2,
+                  uint8_t* d_mask, erp_ransac_result* d_result)
+{
+    const int grid = max(1, cdiv(m_cap, FIN_THREADS));
+    int st = ERP_OK;
+    double* P = ctx->scratch<double>(S_PARTIAL, (size_t)grid * 45 + 2, &st);
+    ERP_TRY(st);
+    int32_t* cnt = reinterpret_cast<int32_t*>(P + (size_t)grid * 45);
+    ERP_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), ctx->stream));
+    const float4 *l4 = (const float4*)d_l4, *r4 = (const float4*)d_r4;
+    switch (metric) {
+    case ERP_METRIC_ALGEBRAIC: finish_kernel<ERP_METRIC_ALGEBRAIC><<<grid, FIN_THREADS, 0, ctx->stream>>>(d_Eb, d_packed, d_l3, d_r3, l4, r4, m_cap, d_m, tau, tau2, sin2, d_mask, P, cnt, d_result); break;
+    case ERP_METRIC_SAMPSON: finish_kernel<ERP_METRIC_SAMPSON><<<grid, FIN_THREADS, 0, ctx->stream>>>(d_Eb, d_packed, d_l3, d_r3, l4, r4, m_cap, d_m, tau, tau2, sin2, d_mask, P, cnt, d_result); break;
+    default: finish_kernel<ERP_METRIC_ANGULAR><<<grid, FIN_THREADS, 0, ctx->stream>>>(d_Eb, d_packed, d_l3, d_r3, l4, r4, m_cap, d_m, tau, tau2, sin2, d_mask, P, cnt, d_result); break;
+    }
+    ERP_LAUNCH(ctx, "finish_kernel");
     return ERP_OK;
 }
 
@@ -784,11 +1035,11 @@ ERP_API int erp_eight_point_batch_dev(erp_ctx* ctx, const double* d_l3, const do
     ERP_ARG(d_samples || S <= SMALL_S, ERP_E_ARG, "erp_eight_point_batch_dev: samples table required for S > %d", SMALL_S);
     if (H == 0) return ERP_OK;
     DeviceGuard g(ctx->device);
-    if (S == 8) return solve_min8(ctx, d_l3, d_r3, m, d_samples, H, seed, hyp_offset, d_E, d_pose);
+    if (S == 8) return solve_min8(ctx, d_l3, d_r3, m, nullptr, d_samples, H, seed, hyp_offset, nullptr, d_E, d_pose, nullptr);
     int st = ERP_OK;
     double* G = ctx->scratch<double>(S_GRAM, (size_t)H * 45, &st);
     ERP_TRY(st);
-    ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, d_samples, H, S, seed, hyp_offset, G));
+    ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, d_samples, H, S, seed, hyp_offset, nullptr, G));
     ERP_TRY(solve_batch(ctx, G, H, d_E, d_pose));
     return ERP_OK;
 }

@@ -230,6 +230,8 @@ __device__ __forceinline__ bool keep_match(const int32_t* idx2, const float* dis
                                            const int32_t* rev, int q_offset)
 {
     // if (m[0].distance < ratio_thresh * m[1].distance)   -- fp32 product, strict <
+    // a row of NaN descriptors has no nearest neighbour (idx -1): it never matches
+    if (idx2[2 * i] < 0) return false;
     bool keep = ratio < 0.f ? true : (dist2[2 * i] < __fmul_rn(ratio, dist2[2 * i + 1]));
     if (keep && rev) keep = rev[idx2[2 * i]] == i + q_offset;
     return keep;

@@ -533,11 +533,8 @@ static int launch_tc(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt,
     constexpr int NS = n_slots(KCH);
     constexpr int smem = 2 * KCH * Q_CHUNK_BYTES + NS * T_CHUNK_BYTES + SMEM_TAIL;
     static_assert(smem <= SMEM_LIMIT, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        ERP_CUDA(cudaFuncSetAttribute(knn2_tc_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};
+    ERP_TRY(ensure_dynamic_smem(ctx, knn2_tc_kernel<KCH>, smem, configured));
     knn2_tc_kernel<KCH><<<grid, TC_THREADS, smem, ctx->stream>>>(mq, mt, p);
     ERP_LAUNCH(ctx, "knn2_tc_kernel");
     return ERP_OK;

@@ -49,10 +49,13 @@ static __device__ unsigned long long erp_clk[8];
 #define TCC_FLUSH()
 #endif
 // |s_tc - s_exact| <= 2^-10 (|q|^2 + max|t|^2) in the worst case: both operands are rounded to 11
-// significant bits (relative error 2^-11 each), products are exact, and 2|q||t| <= |q|^2 + |t|^2;
-// the 1 % on top covers the fp32 accumulation.  refine_kernel reports the deviation it observes
-// (0.28 of the bound on the synthetic sets).
-constexpr double F_KAPPA = 1.01 / 1024.0;
+// significant bits (relative error 2^-11 each), products are exact, and 2|q||t| <= |q|^2 + |t|^2.
+// On top of 2^-10: the second-order rounding term (2^-22 relative = 2^-12 of the budget), the column id packed into the
+// three low mantissa bits of a score (<= 7 ulp = 2^-21 relative), and the fp32 accumulation inside the tensor pipe,
+// whose rounding mode is not documented: with truncating adds over D + 3 <= 131 terms the worst case is 131 * 2^-24
+// of the scale = 0.8 % of 2^-10.  Together < 2 %; 5 % is taken.  refine_kernel reports the deviation it observes
+// (0.28 of the bound on the synthetic sets; tests/test_gpu_parity.py holds a worst-case-rounding adversarial set).
+constexpr double F_KAPPA = 1.05 / 1024.0;
 constexpr uint32_t F_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(F_BN >> 3) << 17) | ((uint32_t)(F_BM >> 4) << 24);
 
 __host__ __device__ constexpr int f_sub(int kch) { return kch <= 3 ? F_SUB_MAX : 1; }
@@ -418,11 +421,8 @@ static int launch_tc1(erp_ctx* ctx, const CUtensorMap& mq, const CUtensorMap& mt
 {
     constexpr int smem = f_smem(KCH);
     static_assert(smem <= TC_SMEM_LIMIT, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        ERP_CUDA(cudaFuncSetAttribute(knn2_tc1_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};
+    ERP_TRY(ensure_dynamic_smem(ctx, knn2_tc1_kernel<KCH>, smem, configured));
     knn2_tc1_kernel<KCH><<<grid, F_THREADS, smem, ctx->stream>>>(mq, mt, ma, p);
     ERP_LAUNCH(ctx, "knn2_tc1_kernel");
 #if ERP_TC_COUNTERS

@@ -22,14 +22,19 @@ constexpr int SC_THREADS = 256;
 template <int METRIC, int C>
 __global__ void __launch_bounds__(SC_THREADS)
 score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
-             const float4* __restrict__ r4, int m, float tau, float tau2, float sin2,
+             const float4* __restrict__ r4, int m_cap, const int32_t* __restrict__ m_dev, float tau, float tau2, float sin2,
              int32_t* __restrict__ counts,
-             const int32_t* __restrict__ hlist, const int32_t* __restrict__ hlist_len)
+             const int32_t* __restrict__ hlist, const int32_t* __restrict__ hlist_len,
+             unsigned long long* __restrict__ best, unsigned long long hyp0, int32_t* __restrict__ tile_done)
 {
     // with hlist: row i of the launch is hypothesis hlist[i], i < *hlist_len (blocks past the end
-    // exit: the host does not know the length); counts are indexed by list position
+    // exit: the host does not know the length); counts are indexed by list position.
+    // with best: the block that completes a hypothesis tile (the last of its gridDim.y correspondence slices, found
+    // with one ticket per tile) merges the tile's packed (count << 32 | ~id) maximum into *best.
     __shared__ __align__(16) float Es[TH][12];
     __shared__ int cs[TH];
+    __shared__ int last_slice;
+    const int m = dev_len(m_dev, m_cap);
     if (hlist) H = min(H, *hlist_len);
     // hypothesis tiles are walked with a grid stride: list launches are sized for a plausible length,
     // not for the worst case (thousands of blocks that would only read the length and exit)
@@ -78,6 +83,26 @@ score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
         if (gridDim.y == 1) counts[h0 + t] = cs[t];
         else if (cs[t]) atomicAdd(&counts[h0 + t], cs[t]);
     }
+    if (best) {
+        if (gridDim.y > 1) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) last_slice = atomicAdd(&tile_done[h0 / TH], 1) == (int)gridDim.y - 1;
+            __syncthreads();
+        }
+        if (gridDim.y == 1 || last_slice) {
+            __threadfence();
+            unsigned long long b = 0;
+            for (int t = threadIdx.x; t < nh; t += SC_THREADS) {
+                const int c = gridDim.y == 1 ? cs[t] : *reinterpret_cast<volatile int32_t*>(&counts[h0 + t]);
+                const unsigned long long id = hyp0 + (unsigned long long)(hlist ? hlist[h0 + t] : h0 + t);
+                const unsigned long long pk = ((unsigned long long)(uint32_t)c << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)id);
+                b = pk > b ? pk : b;
+            }
+            for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_down_sync(0xffffffffu, b, o); b = y > b ? y : b; }
+            if ((threadIdx.x & 31) == 0 && b) atomicMax(best, b);
+        }
+    }
     __syncthreads();
     }
 }
@@ -125,12 +150,14 @@ __global__ void mask_kernel(const double* __restrict__ E9, const float4* __restr
     if ((threadIdx.x & 31) == 0 && s && n_in) atomicAdd(n_in, s);
 }
 
-int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples,
-               int H, int S, uint64_t seed, uint64_t hyp0, double* d_G);
-int gram_masked(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const uint8_t* d_mask, double* d_G);
+int gram_batch(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_m, const int32_t* d_samples,
+               int H, int S, uint64_t seed, uint64_t hyp0, const uint64_t* d_packed, double* d_G);
 int solve_batch(erp_ctx* ctx, const double* d_G, int H, double* d_E, float* d_pose, int max_sweeps = 30);
-int solve_min8(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_samples, int H,
-               uint64_t seed, uint64_t hyp0, double* d_E, float* d_pose);
+int solve_min8(erp_ctx* ctx, const double* d_l3, const double* d_r3, int m, const int32_t* d_m, const int32_t* d_samples, int H,
+               uint64_t seed, uint64_t hyp0, const uint64_t* d_packed, double* d_E, float* d_pose, const Min8Fused* fused);
+int finish_launch(erp_ctx* ctx, const double* d_Eb, const uint64_t* d_packed, const double* d_l3, const double* d_r3,
+                  const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, int metric, float tau, float tau2, float sin2,
+                  uint8_t* d_mask, erp_ransac_result* d_result);
 
 static inline void thresholds(float tau, float& tau2, float& sin2)
 {
@@ -139,7 +166,7 @@ static inline void thresholds(float tau, float& tau2, float& sin2)
     sin2 = (float)(sd * sd);
 }
 
-int score_launch(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m,
+int score_launch(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m,
                  int metric, float tau, int32_t* d_counts)
 {
     float tau2, sin2;
@@ -147,40 +174,39 @@ int score_launch(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, cons
     int gx = cdiv(H, TH);
     // split the correspondences when there are too few hypothesis tiles to fill the machine
     int msplit = 1;
-    if (gx < ctx->sm_count * 4) msplit = max(1, min(cdiv(m, SC_THREADS * 8), (ctx->sm_count * 4) / gx));
+    if (gx < ctx->sm_count * 4) msplit = max(1, min(cdiv(m_cap, SC_THREADS * 8), (ctx->sm_count * 4) / gx));
     // (a zero-padded lane contributes res = 0 < tau, hence the live[] predicate in the kernel)
     if (msplit > 1) ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H, ctx->stream));
     dim3 grid(gx, msplit);
     const float4* l4 = (const float4*)d_l4;
     const float4* r4 = (const float4*)d_r4;
     switch (metric) {
-    case ERP_METRIC_ALGEBRAIC: score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts, nullptr, nullptr); break;
-    case ERP_METRIC_SAMPSON: score_kernel<ERP_METRIC_SAMPSON, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts, nullptr, nullptr); break;
-    case ERP_METRIC_ANGULAR: score_kernel<ERP_METRIC_ANGULAR, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m, tau, tau2, sin2, d_counts, nullptr, nullptr); break;
+    case ERP_METRIC_ALGEBRAIC: score_kernel<ERP_METRIC_ALGEBRAIC, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m_cap, d_m, tau, tau2, sin2, d_counts, nullptr, nullptr, nullptr, 0, nullptr); break;
+    case ERP_METRIC_SAMPSON: score_kernel<ERP_METRIC_SAMPSON, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m_cap, d_m, tau, tau2, sin2, d_counts, nullptr, nullptr, nullptr, 0, nullptr); break;
+    case ERP_METRIC_ANGULAR: score_kernel<ERP_METRIC_ANGULAR, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H, l4, r4, m_cap, d_m, tau, tau2, sin2, d_counts, nullptr, nullptr, nullptr, 0, nullptr); break;
     default: set_error("unknown metric %d", metric); return ERP_E_ARG;
     }
     ERP_LAUNCH(ctx, "score_kernel");
     return ERP_OK;
 }
 
-// exact counts of the listed hypotheses, then their packed best merged into *d_best
+// exact counts of the listed hypotheses, their packed best merged into *d_best by the same launch
 int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,
-                    const float* d_l4, const float* d_r4, int m, float tau, uint64_t hyp0,
-                    int32_t* d_counts /* H_max, scratch */, uint64_t* d_best)
+                    const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau, uint64_t hyp0,
+                    int32_t* d_counts /* H_max + H_max / 128 + 1, scratch */, uint64_t* d_best)
 {
     float tau2, sin2;
     thresholds(tau, tau2, sin2);
-    ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H_max, ctx->stream));
+    const int tiles = cdiv(H_max, TH);
+    ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * ((size_t)H_max + tiles), ctx->stream));
     // the list is usually short (cfg3: ~900 contenders = 14 hypothesis tiles): split the correspondences finely so that
     // it still fills the machine (14 x 16 blocks of 8 correspondences per thread took 100 us, 14 x 48 of 4: see profiles/)
-    int msplit = max(1, min(cdiv(m, SC_THREADS * 4), 48));
-    dim3 grid(min(cdiv(H_max, TH), 64), msplit);
-    score_kernel<ERP_METRIC_ALGEBRAIC, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m,
-                                                                              tau, tau2, sin2, d_counts, d_list, d_len);
+    int msplit = max(1, min(cdiv(m_cap, SC_THREADS * 4), 48));
+    dim3 grid(min(tiles, 64), msplit);
+    score_kernel<ERP_METRIC_ALGEBRAIC, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m_cap, d_m,
+                                                                              tau, tau2, sin2, d_counts, d_list, d_len,
+                                                                              (unsigned long long*)d_best, (unsigned long long)hyp0, d_counts + H_max);
     ERP_LAUNCH(ctx, "score_kernel(list)");
-    best_kernel<<<min(cdiv(H_max, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(d_counts, H_max, hyp0,
-                                                                                  (unsigned long long*)d_best, d_list, d_len);
-    ERP_LAUNCH(ctx, "best_kernel(list)");
     return ERP_OK;
 }
 
@@ -204,6 +230,81 @@ int mask_launch(erp_ctx* ctx, const double* d_E9, const float* d_l4, const float
     return ERP_OK;
 }
 
+bool ransac_uses_tc(erp_ctx* ctx, int H, int m_cap, int metric)
+{
+    const int n = H < RANSAC_CHUNK ? H : RANSAC_CHUNK;
+    return metric == ERP_METRIC_ALGEBRAIC &&
+           (ctx->engine == ERP_ENGINE_TCGEN05 || ctx->engine == ERP_ENGINE_TCGEN05_1X ||
+            (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m_cap)));
+}
+
+// Hypotheses [hyp_offset, hyp_offset + H): sample, solve, score, packed best into *d_packed (max-merged: the caller
+// zeroes it).  m lives on the device when d_m is given (m_cap sizes the launches); nothing here waits for the host.
+// k_ready: the correspondence operand of the tensor-core search is already in place (fused gather).
+int ransac_search(erp_ctx* ctx, const double* d_l3, const double* d_r3, const float* d_l4, const float* d_r4, int m_cap,
+                  const int32_t* d_m, uint64_t seed, uint64_t hyp_offset, int H, int S, int metric, float tau, bool k_ready,
+                  uint64_t* d_packed)
+{
+    const int CH = RANSAC_CHUNK;   // hypotheses per pass: 75 MB of E, 2 x 134 MB of split rows (S != 8: 377 MB of Gram)
+    int st = ERP_OK;
+    int chunk = H < CH ? H : CH;
+    double* G = S == 8 ? nullptr : ctx->scratch<double>(S_GRAM, (size_t)chunk * 45, &st);
+    double* E = ctx->scratch<double>(S_E, (size_t)chunk * 9, &st);
+    int32_t* counts = ctx->scratch<int32_t>(S_COUNTS, (size_t)chunk + chunk / 128 + 2, &st);
+    ERP_TRY(st);
+    ctx->n_ev_score = 0;
+    const bool tc = ransac_uses_tc(ctx, H, m_cap, metric);
+    ScoreTcBuffers b;
+    Min8Fused fused;
+    if (tc) {
+        ERP_TRY(score_tc_buffers(ctx, chunk, m_cap, &b));
+        if (!k_ready) ERP_TRY(score_tc_prepare(ctx, b, d_l4, d_r4, m_cap, d_m));
+        fused.Es = b.Es; fused.big = score_tc_big(tau); fused.upper = b.upper; fused.w = b.w;
+    }
+    for (int h0 = 0; h0 < H; h0 += CH) {
+        int n = H - h0 < CH ? H - h0 : CH;
+        // (the per-chunk words must be clear before the solver publishes pass A's shape)
+        if (tc && h0 > 0) ERP_CUDA(cudaMemsetAsync(b.w + W_CHUNK0, 0, (W_WORDS - W_CHUNK0) * sizeof(int32_t), ctx->stream));
+        if (S == 8) ERP_TRY(solve_min8(ctx, d_l3, d_r3, m_cap, d_m, nullptr, n, seed, hyp_offset + h0, nullptr, E, nullptr, tc ? &fused : nullptr));
+        else {
+            ERP_TRY(gram_batch(ctx, d_l3, d_r3, m_cap, d_m, nullptr, n, S, seed, hyp_offset + h0, nullptr, G));
+            ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
+        }
+        if (tc) ERP_TRY(score_tc_search(ctx, b, E, n, d_l4, d_r4, m_cap, tau, hyp_offset + h0, S == 8, counts, d_packed));
+        else {
+            cudaEvent_t e0, e1;
+            ERP_TRY(score_event(ctx, &e0));
+            ERP_TRY(score_launch(ctx, E, n, d_l4, d_r4, m_cap, d_m, metric, tau, counts));
+            best_kernel<<<min(cdiv(n, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(counts, n, hyp_offset + h0,
+                                                                                    (unsigned long long*)d_packed, nullptr, nullptr);
+            ERP_LAUNCH(ctx, "best_kernel");
+            ERP_TRY(score_event(ctx, &e1));
+        }
+    }
+    return ERP_OK;
+}
+
+// Replays the winning sample (*d_packed names it) with the arithmetic that scored it, marks its inliers, refits on them
+// (eight_point.cpp:16-50 as a least-squares solve) and leaves the whole erp_ransac_result on the device.
+int ransac_finish(erp_ctx* ctx, const double* d_l3, const double* d_r3, const float* d_l4, const float* d_r4, int m_cap,
+                  const int32_t* d_m, uint64_t seed, const uint64_t* d_packed, int S, int metric, float tau,
+                  uint8_t* d_mask, erp_ransac_result* d_result)
+{
+    ERP_ARG(metric >= 0 && metric <= 2, ERP_E_ARG, "unknown metric %d", metric);
+    int st = ERP_OK;
+    double* misc = ctx->scratch<double>(S_MISC, 128, &st);
+    ERP_TRY(st);
+    double *G = misc, *Eb = misc + 45;
+    if (S == 8) ERP_TRY(solve_min8(ctx, d_l3, d_r3, m_cap, d_m, nullptr, 1, seed, 0, d_packed, Eb, nullptr, nullptr));
+    else {
+        ERP_TRY(gram_batch(ctx, d_l3, d_r3, m_cap, d_m, nullptr, 1, S, seed, 0, d_packed, G));
+        ERP_TRY(solve_batch(ctx, G, 1, Eb, nullptr));
+    }
+    float tau2, sin2;
+    thresholds(tau, tau2, sin2);
+    return finish_launch(ctx, Eb, d_packed, d_l3, d_r3, d_l4, d_r4, m_cap, d_m, metric, tau, tau2, sin2, d_mask, d_result);
+}
+
 } // namespace erp
 
 using namespace erp;
@@ -219,7 +320,7 @@ ERP_API int erp_score_dev(erp_ctx* ctx, const double* d_E, int H, const float* d
     int st = ERP_OK;
     if (!d_counts) { d_counts = ctx->scratch<int32_t>(S_COUNTS, H, &st); ERP_TRY(st); }
     if (m == 0) ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)H, ctx->stream));
-    else ERP_TRY(score_launch(ctx, d_E, H, d_l4, d_r4, m, metric, tau, d_counts));
+    else ERP_TRY(score_launch(ctx, d_E, H, d_l4, d_r4, m, nullptr, metric, tau, d_counts));
     if (d_best_packed) {
         best_kernel<<<min(cdiv(H, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(d_counts, H, hyp_offset,
                                                                                 (unsigned long long*)d_best_packed, nullptr, nullptr);
@@ -239,33 +340,7 @@ ERP_API int erp_ransac_local_dev(erp_ctx* ctx, const double* d_l3, const double*
     ERP_ARG(hyp_offset + (uint64_t)H <= 0xFFFFFFFFull, ERP_E_LIMIT, "hypothesis ids must fit 32 bits");
     DeviceGuard g(ctx->device);
     ERP_CUDA(cudaMemsetAsync(d_packed, 0, sizeof(uint64_t), ctx->stream));
-    const int CH = 1 << 20;   // hypotheses per pass: 75 MB of E, 2 x 134 MB of split rows (S != 8: 377 MB of Gram)
-    int st = ERP_OK;
-    int chunk = H < CH ? H : CH;
-    double* G = S == 8 ? nullptr : ctx->scratch<double>(S_GRAM, (size_t)chunk * 45, &st);
-    double* E = ctx->scratch<double>(S_E, (size_t)chunk * 9, &st);
-    int32_t* counts = ctx->scratch<int32_t>(S_COUNTS, chunk, &st);
-    ERP_TRY(st);
-    ctx->n_ev_score = 0;
-    for (int h0 = 0; h0 < H; h0 += CH) {
-        int n = H - h0 < CH ? H - h0 : CH;
-        if (S == 8) ERP_TRY(solve_min8(ctx, d_l3, d_r3, m, nullptr, n, seed, hyp_offset + h0, E, nullptr));
-        else {
-            ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, n, S, seed, hyp_offset + h0, G));
-            ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
-        }
-        if (metric == ERP_METRIC_ALGEBRAIC &&
-            (ctx->engine == ERP_ENGINE_TCGEN05 || ctx->engine == ERP_ENGINE_TCGEN05_1X ||
-             (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m))))
-            ERP_TRY(score_tc_best(ctx, E, n, d_l4, d_r4, m, tau, hyp_offset + h0, counts, d_packed));
-        else {
-            cudaEvent_t e0, e1;
-            ERP_TRY(score_event(ctx, &e0));
-            ERP_TRY(erp_score_dev(ctx, E, n, d_l4, d_r4, m, metric, tau, hyp_offset + h0, counts, d_packed));
-            ERP_TRY(score_event(ctx, &e1));
-        }
-    }
-    return ERP_OK;
+    return ransac_search(ctx, d_l3, d_r3, d_l4, d_r4, m, nullptr, seed, hyp_offset, H, S, metric, tau, false, d_packed);
 }
 
 ERP_API int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3,
@@ -277,36 +352,13 @@ ERP_API int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double
     ERP_ARG(S >= 8 && S <= 32 && m >= S, ERP_E_TOO_FEW_POINTS, "erp_ransac_finish_dev: bad sample size / too few points");
     DeviceGuard g(ctx->device);
     int st = ERP_OK;
-    uint64_t hyp = 0xFFFFFFFFull - (packed & 0xFFFFFFFFull);
-    // layout of the small result scratch: G(45) | E_best(9) | G_refit(45) | E_refit(9) | pose(12 floats) | n(int)
-    double* misc = ctx->scratch<double>(S_MISC, 128, &st);
+    uint64_t* d_pk = ctx->scratch<uint64_t>(S_PACKED, 4, &st) + 2;              // [2]: the caller's word, away from the search's
+    erp_ransac_result* d_res = ctx->scratch<erp_ransac_result>(S_RESULT, 1, &st);
     if (!d_mask) d_mask = ctx->scratch<uint8_t>(S_MASK, (size_t)m, &st);
     ERP_TRY(st);
-    double *G = misc, *Eb = misc + 45, *Gr = misc + 54, *Er = misc + 99;
-    float* pose = reinterpret_cast<float*>(misc + 108);
-    int32_t* n_in = reinterpret_cast<int32_t*>(misc + 116);
-    // replay the winning sample with the arithmetic that scored it
-    if (S == 8) ERP_TRY(solve_min8(ctx, d_l3, d_r3, m, nullptr, 1, seed, hyp, Eb, nullptr));
-    else {
-        ERP_TRY(gram_batch(ctx, d_l3, d_r3, m, nullptr, 1, S, seed, hyp, G));
-        ERP_TRY(solve_batch(ctx, G, 1, Eb, nullptr));
-    }
-    ERP_TRY(mask_launch(ctx, Eb, d_l4, d_r4, m, metric, tau, d_mask, n_in));
-    ERP_TRY(gram_masked(ctx, d_l3, d_r3, m, d_mask, Gr));                   // refit on the inliers
-    ERP_TRY(solve_batch(ctx, Gr, 1, Er, pose, 12));
-    struct { double Eb[9]; } hb;
-    struct { double Er[9]; float pose[12]; int32_t n; } hr;
-    ERP_CUDA(cudaMemcpyAsync(&hb, Eb, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaMemcpyAsync(hr.Er, Er, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaMemcpyAsync(hr.pose, pose, sizeof(float) * 12, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaMemcpyAsync(&hr.n, n_in, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaMemcpyAsync(d_pk, &packed, sizeof packed, cudaMemcpyHostToDevice, ctx->stream));
+    ERP_TRY(ransac_finish(ctx, d_l3, d_r3, d_l4, d_r4, m, nullptr, seed, d_pk, S, metric, tau, d_mask, d_res));
+    ERP_CUDA(cudaMemcpyAsync(result, d_res, sizeof *result, cudaMemcpyDeviceToHost, ctx->stream));
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    result->packed = packed;
-    result->hyp_id = hyp;
-    result->count = (int32_t)(packed >> 32);
-    result->n_refit = hr.n;
-    memcpy(result->E_best, hb.Eb, sizeof hb.Eb);
-    memcpy(result->E_refit, hr.Er, sizeof hr.Er);
-    memcpy(result->pose, hr.pose, sizeof hr.pose);
     return ERP_OK;
 }

@@ -43,4 +43,76 @@ __device__ __forceinline__ void scale_E(const double* __restrict__ E, float* __r
     for (int i = 0; i < 9; i++) Eh[i] = (float)(E[i] * s);
 }
 
+// ---- operands and device words of the tensor-core best-hypothesis search (score_tc.cu) -----------------------
+// One 128-byte row (32 floats) per hypothesis / correspondence carries the three 3xTF32 products of the 9-term dot:
+//     hypothesis     [ Eh_hi(9) | Eh_hi(9) | Eh_lo(9) | 0 x 5 ]   (times a power of two, see score_tc.cu)
+//     correspondence [ K_hi(9)  | K_lo(9)  | K_hi(9)  | 0 x 5 ]
+__device__ __forceinline__ void write_e_row(const float e[9], float big, float* __restrict__ row)
+{
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const float hi = tf32_rna(e[i]), lo = tf32_rna(__fsub_rn(e[i], hi));
+        v[i] = hi * big; v[9 + i] = hi * big; v[18 + i] = lo * big;       // exact: power of two
+    }
+#pragma unroll
+    for (int i = 27; i < 32; i++) v[i] = 0.f;
+    float4* o = reinterpret_cast<float4*>(row);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+// returns |l||r| (the scale of the certificate's band)
+__device__ __forceinline__ float write_k_row(float4 l, float4 r, float* __restrict__ row)
+{
+    float k[9], v[32];
+    kron9(l, r, k);
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const float hi = tf32_rna(k[i]), lo = tf32_rna(__fsub_rn(k[i], hi));
+        v[i] = hi; v[9 + i] = lo; v[18 + i] = hi;
+    }
+#pragma unroll
+    for (int i = 27; i < 32; i++) v[i] = 0.f;
+    float4* o = reinterpret_cast<float4*>(row);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return sqrtf((l.x * l.x + l.y * l.y + l.z * l.z) * (r.x * r.x + r.y * r.y + r.z * r.z));
+}
+__device__ __forceinline__ void zero_row(float* __restrict__ row)
+{
+    float4* o = reinterpret_cast<float4*>(row);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+constexpr int SC_TILE = 256;      // correspondences per tile of the search (UMMA N)
+constexpr int SC_N0 = 8;          // tiles of pass A
+
+// int32 words every pass reads from device memory (no length of the search ever visits the host)
+enum ScoreWords {
+    W_KMAX = 0, W_M = 1, W_NCT = 2, W_N0 = 3,                // set once per call by the correspondence prep
+    W_AMAX = 4 /* 2 words */, W_DONE = 6, W_LEN1 = 7, W_LENF = 8, W_LSTAR = 9, W_REMAIN = 10, W_FIRST = 11,
+    W_DYN_A = 12, W_DYN_B = 16, W_DYN_C = 20,                // { rows of the A matrix, first tile, end tile, m }
+    W_WORDS = 24, W_CHUNK0 = 4                               // words [W_CHUNK0, W_WORDS) are reset per hypothesis chunk
+};
+static_assert(W_WORDS * sizeof(int32_t) == W_WORDS_BYTES, "common.cuh: W_WORDS_BYTES");
+
+// the correspondence side of the search, one thread per correspondence slot c < capacity: operand row (zeros up to the
+// tile boundary past m: those columns have res = 0 exactly and are subtracted by the kernel), |l||r| maximum, and the
+// m-dependent words (by the thread that owns slot 0)
+__device__ __forceinline__ void prep_k_slot(int c, int m, float4 l, float4 r, float* __restrict__ Ks, int32_t* __restrict__ w)
+{
+    if (c == 0) {
+        const int nct = (m + SC_TILE - 1) / SC_TILE;
+        w[W_M] = m; w[W_NCT] = nct; w[W_N0] = nct < SC_N0 ? nct : SC_N0;
+    }
+    float nrm = 0.f;
+    if (c < m) nrm = write_k_row(l, r, Ks + (size_t)c * 32);
+    else if (c < ((m + SC_TILE - 1) / SC_TILE) * SC_TILE) zero_row(Ks + (size_t)c * 32);
+    // non-negative floats (inf, NaN included) order like their bit patterns
+    unsigned b = __float_as_uint(nrm);
+    b = __reduce_max_sync(__activemask(), b);
+    if ((threadIdx.x & 31) == 0 && b > *reinterpret_cast<volatile unsigned*>(w + W_KMAX)) atomicMax(reinterpret_cast<unsigned*>(w + W_KMAX), b);
+}
+
 } // namespace erp

@@ -48,70 +48,44 @@ constexpr uint32_t S_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SN
 constexpr float S_KAPPA = 1.0f / 65536.0f;
 
 // ---- operand preparation ---------------------------------------------------------------
-// row i of Es = split scaled E of hypothesis list[i] (i < *list_len) or of hypothesis i
-__global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __restrict__ Es /* H x 32 */,
-                              const int32_t* __restrict__ list, const int32_t* __restrict__ list_len, float big)
+// row i of Es = split scaled E of hypothesis i; also clears the two bound arrays and publishes pass A's shape
+// (the minimal-sample solver does the same in its own epilogue, geometry.cu: min8_kernel)
+__global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __restrict__ Es /* H x 32 */, float big,
+                              int32_t* __restrict__ upper /* 2 x H */, int32_t* __restrict__ w)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (list) H = min(H, *list_len);
+    if (h == 0) { w[W_DYN_A] = H; w[W_DYN_A + 1] = 0; w[W_DYN_A + 2] = w[W_N0]; w[W_DYN_A + 3] = w[W_M]; }
     if (h >= H) return;
-    float e[9], hi[9], lo[9];
-    scale_E(E + (size_t)(list ? list[h] : h) * 9, e);
-#pragma unroll
-    for (int i = 0; i < 9; i++) { hi[i] = tf32_rna(e[i]); lo[i] = tf32_rna(__fsub_rn(e[i], hi[i])); }
-    float row[32];
-#pragma unroll
-    for (int i = 0; i < 9; i++) { row[i] = hi[i] * big; row[9 + i] = hi[i] * big; row[18 + i] = lo[i] * big; }   // exact: power of two
-#pragma unroll
-    for (int i = 27; i < 32; i++) row[i] = 0.f;
-    float4* o = reinterpret_cast<float4*>(Es + (size_t)h * 32);
-#pragma unroll
-    for (int i = 0; i < 8; i++) o[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+    float e[9];
+    scale_E(E + (size_t)h * 9, e);
+    write_e_row(e, big, Es + (size_t)h * 32);
+    upper[h] = 0; upper[(size_t)H + h] = 0;
 }
 
-__global__ void prep_k_kernel(const float4* __restrict__ l4, const float4* __restrict__ r4, int m,
-                              float* __restrict__ Ks /* m x 32 */, unsigned* __restrict__ kmax_bits)
+__global__ void prep_k_kernel(const float4* __restrict__ l4, const float4* __restrict__ r4, int m_cap, const int32_t* __restrict__ m_dev,
+                              float* __restrict__ Ks /* roundup(m_cap, 256) x 32 */, int32_t* __restrict__ w)
 {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    float nrm = 0.f;
-    if (c < m) {
-        float4 l = l4[c], r = r4[c];
-        float k[9], hi[9], lo[9];
-        kron9(l, r, k);
-#pragma unroll
-        for (int i = 0; i < 9; i++) { hi[i] = tf32_rna(k[i]); lo[i] = tf32_rna(__fsub_rn(k[i], hi[i])); }
-        float row[32];
-#pragma unroll
-        for (int i = 0; i < 9; i++) { row[i] = hi[i]; row[9 + i] = lo[i]; row[18 + i] = hi[i]; }
-#pragma unroll
-        for (int i = 27; i < 32; i++) row[i] = 0.f;
-        float4* o = reinterpret_cast<float4*>(Ks + (size_t)c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
-        nrm = sqrtf((l.x * l.x + l.y * l.y + l.z * l.z) * (r.x * r.x + r.y * r.y + r.z * r.z));
-    }
-    // non-negative floats (inf, NaN included) order like their bit patterns
-    unsigned b = __float_as_uint(nrm);
-    b = __reduce_max_sync(0xffffffffu, b);
-    if ((threadIdx.x & 31) == 0 && b > *reinterpret_cast<volatile unsigned*>(kmax_bits)) atomicMax(kmax_bits, b);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = dev_len(m_dev, m_cap);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    prep_k_slot(c, m, c < m ? l4[c] : zero, c < m ? r4[c] : zero, Ks, w);
 }
 
 // ---- the scoring kernel ------------------------------------------------------------------
 struct ScoreTcParams {
-    int m;
     float tau;
     float big;                    // 2^k applied to every A row: tau * big in [2^30, 2^31)
     const unsigned* kmax_bits;
-    const int32_t* dyn;           // device: { hypotheses (rows of the A matrix), first correspondence tile, end tile }
+    const int32_t* dyn;           // device: { hypotheses (rows of the A matrix), first correspondence tile, end tile, m }
     int32_t* upper;               // one counter per A row, zeroed by the caller: partial sums are added
 };
 
 // the launch's unit grid, read from device memory by every role
 struct ScoreShape {
-    int H, ct_begin, n_htiles, n_ctiles, units_per_cta;
+    int H, ct_begin, n_htiles, n_ctiles, units_per_cta, m;
     __device__ explicit ScoreShape(const ScoreTcParams& p)
     {
-        H = p.dyn[0]; ct_begin = p.dyn[1];
+        H = p.dyn[0]; ct_begin = p.dyn[1]; m = p.dyn[3];
         n_ctiles = max(p.dyn[2] - ct_begin, 0);
         n_htiles = (H + SM_ROWS * S_SUB - 1) / (SM_ROWS * S_SUB);            // tile PAIRS
         long total = (long)n_htiles * n_ctiles;
@@ -330,7 +304,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
                     }
                 }
                 // zero-filled columns past m have res = 0 exactly and were counted
-                pad_total += S_EPI_COLS - min(max(p.m - colbase, 0), S_EPI_COLS);
+                pad_total += S_EPI_COLS - min(max(sh.m - colbase, 0), S_EPI_COLS);
             }
 #pragma unroll
             for (int sub = 0; sub < S_SUB; sub++) {
@@ -352,59 +326,85 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
     }
 }
 
-// packed (bound << 32 | ~h) maximum: the hypothesis with the largest bound, lowest index on ties
-__global__ void upper_argmax_kernel(const int32_t* __restrict__ upper, int H, unsigned long long* __restrict__ best)
+// ---- the small kernels between the passes ------------------------------------------------------
+// After pass A: the hypothesis with the largest bound (lowest index on ties) is scored exactly over ALL correspondences
+// -> L*, a lower bound of the best count; the last block to finish the arg-max does it (1024 threads: ~50 correspondences
+// each) and plans passes B and C.  Its packed (count, ~id) is merged into *best like any other exact count.
+constexpr int AP_THREADS = 1024;
+__global__ void __launch_bounds__(AP_THREADS)
+argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__ E, const float4* __restrict__ l4,
+                   const float4* __restrict__ r4, float tau, unsigned long long hyp0, int32_t* __restrict__ w,
+                   unsigned long long* __restrict__ best)
 {
+    __shared__ unsigned long long wbest[AP_THREADS / 32];
+    __shared__ int wsum[AP_THREADS / 32];
+    __shared__ float Es[9];
+    __shared__ int last;
+    const int H = w[W_DYN_A], lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned long long b = 0;
-    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < H; h += gridDim.x * blockDim.x) {
+    for (int h = blockIdx.x * AP_THREADS + threadIdx.x; h < H; h += gridDim.x * AP_THREADS) {
         unsigned long long v = ((unsigned long long)(uint32_t)upper[h] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)h);
         b = v > b ? v : b;
     }
     for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_down_sync(0xffffffffu, b, o); b = y > b ? y : b; }
-    if ((threadIdx.x & 31) == 0) atomicMax(best, b);
-}
-
-// device words shared by the passes (int32 view of the misc scratch)
-enum { W_KMAX = 0, W_LEN1 = 2, W_LENF = 3, W_AMAX = 4 /* 2 words */, W_DYN_A = 8, W_DYN_B = 12, W_DYN_C = 16, W_LSTAR = 20,
-       W_REMAIN = 21, W_WORDS = 24 };
-
-__global__ void set_dyn_kernel(int32_t* __restrict__ dyn, int H, int ct_begin, int ct_end)
-{
-    dyn[0] = H; dyn[1] = ct_begin; dyn[2] = ct_end;
-}
-
-__global__ void first_candidate_kernel(const unsigned long long* __restrict__ best, int32_t* __restrict__ list, int32_t* __restrict__ len)
-{
-    list[0] = (int32_t)(0xFFFFFFFFu - (uint32_t)(*best & 0xFFFFFFFFull));
-    *len = 1;
-}
-
-// after pass A: L* is known (exact count of the best-looking hypothesis).  Pass B extends the bounds
-// to tile ct1: far enough that a hypothesis with nothing so far can no longer reach L*.
-__global__ void plan_passes_kernel(int32_t* __restrict__ w, const int32_t* __restrict__ exact_first, int H, int m, int n0, int n_ct)
-{
-    const int lstar = *exact_first;
-    w[W_LSTAR] = lstar;
-    // correspondences a discarded hypothesis may still be missing: m - seen < L*  <=>  seen > m - L*
+    if (lane == 0) wbest[wid] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < AP_THREADS / 32; i++) b = wbest[i] > b ? wbest[i] : b;
+        atomicMax(reinterpret_cast<unsigned long long*>(w + W_AMAX), b);
+        __threadfence();
+        last = atomicAdd(w + W_DONE, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const unsigned long long amax = *reinterpret_cast<volatile unsigned long long*>(w + W_AMAX);
+    const int first = (int)(0xFFFFFFFFu - (uint32_t)(amax & 0xFFFFFFFFull));
+    const int m = w[W_M];
+    if (threadIdx.x == 0) scale_E(E + (size_t)first * 9, Es);
+    __syncthreads();
+    float e[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) e[i] = Es[i];
+    int cnt = 0;
+    for (int c = threadIdx.x; c < m; c += AP_THREADS) {
+        const float4 l = l4[c], r = r4[c];
+        float k[9];
+        kron9(l, r, k);
+        cnt += inlier<ERP_METRIC_ALGEBRAIC>(e, k, l, r, tau, 0.f, 0.f) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) wsum[wid] = cnt;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int lstar = 0;
+    for (int i = 0; i < AP_THREADS / 32; i++) lstar += wsum[i];
+    w[W_LSTAR] = lstar; w[W_FIRST] = first;
+    if (H > 0) atomicMax(best, ((unsigned long long)(uint32_t)lstar << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(hyp0 + (unsigned long long)first)));
+    // pass B extends the bounds to tile ct1: far enough that a hypothesis with nothing so far can no longer reach L*
+    // (correspondences a discarded hypothesis may still be missing: m - seen < L*  <=>  seen > m - L*)
+    const int n0 = w[W_N0], n_ct = w[W_NCT];
     long need = (long)m - lstar;
     need += need / 8 + 2 * SN_ROWS;                        // slack: bad hypotheses still collect a few inliers
     int ct1 = (int)((need + SN_ROWS - 1) / SN_ROWS);
     if (ct1 < n0) ct1 = n0;
     if (ct1 > n_ct || lstar * 4 < m) ct1 = n_ct;           // weak best model: pruning cannot pay, finish in pass B
-    w[W_DYN_B] = H; w[W_DYN_B + 1] = n0; w[W_DYN_B + 2] = ct1;
-    w[W_DYN_C] = 0; w[W_DYN_C + 1] = ct1; w[W_DYN_C + 2] = n_ct;           // [0] = survivors, counted by the select kernel
-    long seen = (long)ct1 * SN_ROWS;
+    w[W_DYN_B] = H; w[W_DYN_B + 1] = n0; w[W_DYN_B + 2] = ct1; w[W_DYN_B + 3] = m;
+    w[W_DYN_C] = 0; w[W_DYN_C + 1] = ct1; w[W_DYN_C + 2] = n_ct; w[W_DYN_C + 3] = m;   // [0] = survivors, counted by the select kernel
+    const long seen = (long)ct1 * SN_ROWS;
     w[W_REMAIN] = seen >= m ? 0 : (int)(m - seen);
 }
 
-// survivors of pass B: bound so far + correspondences not yet seen >= L*.  One atomic per block (the per-warp version
-// spent its 24 us on ~27k atomics to one word); launched with 256 threads.
+// survivors of pass B: bound so far + correspondences not yet seen >= L*.  A survivor's operand row moves to its slot
+// of the pass-C matrix right here.  One atomic per block (the per-warp version spent its 24 us on ~27k atomics to one word).
 __global__ void __launch_bounds__(256)
-survivor_select_kernel(const int32_t* __restrict__ upper, int H, int32_t* __restrict__ w, int32_t* __restrict__ list)
+survivor_select_kernel(const int32_t* __restrict__ upper, int32_t* __restrict__ w, int32_t* __restrict__ list,
+                       const float4* __restrict__ Es, float4* __restrict__ Es2)
 {
     __shared__ int wcount[8], wbase[8];
+    const int H = w[W_DYN_A];
     const int h = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool keep = h < H && upper[h] + w[W_REMAIN] >= w[W_LSTAR];
+    const bool keep = h < H && upper[h] + w[W_REMAIN] >= w[W_LSTAR] && w[W_REMAIN] > 0;
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) wcount[wid] = __popc(bal);
     __syncthreads();
@@ -415,17 +415,25 @@ survivor_select_kernel(const int32_t* __restrict__ upper, int H, int32_t* __rest
         for (int i = 0; i < 8; i++) wbase[i] += base;
     }
     __syncthreads();
-    if (keep) list[wbase[wid] + __popc(bal & ((1u << lane) - 1))] = h;
+    if (keep) {
+        const int s = wbase[wid] + __popc(bal & ((1u << lane) - 1));
+        list[s] = h;
+#pragma unroll
+        for (int i = 0; i < 8; i++) Es2[(size_t)s * 8 + i] = Es[(size_t)h * 8 + i];
+    }
 }
 
-// contenders: survivors whose completed bound still reaches L*
+// contenders: hypotheses whose completed bound still reaches L*.  With nothing left for pass C (REMAIN == 0) every
+// hypothesis is complete after pass B and the survivor list is empty.
 __global__ void final_select_kernel(const int32_t* __restrict__ upper, const int32_t* __restrict__ upper2,
                                     const int32_t* __restrict__ survivors, int32_t* __restrict__ w, int32_t* __restrict__ list)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    int h = s < w[W_DYN_C] ? survivors[s] : -1;
-    bool keep = h >= 0 && upper[h] + upper2[s] >= w[W_LSTAR];
-    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool direct = w[W_REMAIN] == 0;
+    const int n = direct ? w[W_DYN_A] : w[W_DYN_C];
+    const int h = s < n ? (direct ? s : survivors[s]) : -1;
+    const bool keep = h >= 0 && upper[h] + (direct ? 0 : upper2[s]) >= w[W_LSTAR];
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (!bal) return;
     int lane = threadIdx.x & 31, base = 0;
     if (lane == 0) base = atomicAdd(&w[W_LENF], __popc(bal));
@@ -437,11 +445,8 @@ bool score_tc_preferred(int H, int m) { return (double)H * (double)m >= 3.0e7 &&
 
 static int launch_score_tc(erp_ctx* ctx, const CUtensorMap& me, const CUtensorMap& mk, const ScoreTcParams& p)
 {
-    static bool configured = false;
-    if (!configured) {
-        ERP_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};
+    ERP_TRY(ensure_dynamic_smem(ctx, score_tc_kernel, S_SMEM, configured));
     cudaEvent_t e0, e1;
     ERP_TRY(score_event(ctx, &e0));
     score_tc_kernel<<<ctx->sm_count, S_THREADS, S_SMEM, ctx->stream>>>(me, mk, p);
@@ -450,69 +455,86 @@ static int launch_score_tc(erp_ctx* ctx, const CUtensorMap& me, const CUtensorMa
     return ERP_OK;
 }
 
-// merges into *d_best the packed (count << 32 | ~id) of the best of the H hypotheses, exactly as
-// erp_score_dev + best_kernel would (algebraic residual)
-int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m, float tau,
-                  uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best)
+// power-of-two factor on the hypothesis operand: the scaled threshold lies in [2^30, 2^31) (see count_chunk)
+float score_tc_big(float tau)
 {
-    if (m >= (1 << 24)) { set_error("score_tc_best: more than 2^24 correspondences"); return ERP_E_LIMIT; }
-    // power-of-two factor on the hypothesis operand: the scaled threshold lies in [2^30, 2^31) (see count_chunk)
     int ex = 0;
     frexpf(tau > 1e-30f ? tau : 1e-30f, &ex);            // tau = f * 2^ex, f in [0.5, 1)
-    const float big = ldexpf(1.0f, 31 - ex);
+    return ldexpf(1.0f, 31 - ex);
+}
+
+// scratch of one search: operand matrices, bound arrays, lists, device words
+int score_tc_buffers(erp_ctx* ctx, int H, int m_cap, ScoreTcBuffers* b)
+{
     int st = ERP_OK;
-    float* Es = ctx->scratch<float>(S_SC_E, (size_t)H * 32, &st);
-    float* Es2 = ctx->scratch<float>(S_SC_E2, (size_t)H * 32, &st);
-    float* Ks = ctx->scratch<float>(S_SC_K, (size_t)m * 32, &st);
-    int32_t* w = ctx->scratch<int32_t>(S_SC_MISC, W_WORDS, &st);
-    int32_t* upper = ctx->scratch<int32_t>(S_SC_BOUNDS, (size_t)H * 2, &st);   // [H] all hypotheses, [H] pass C rows
-    int32_t* list = ctx->scratch<int32_t>(S_SC_LIST, (size_t)H * 2 + 1, &st);  // [H] survivors, [H] contenders, [1] first
-    ERP_TRY(st);
-    int32_t *upper2 = upper + H, *survivors = list, *contenders = list + H, *first = list + 2 * (size_t)H;
-    const int n_ct = cdiv(m, SN_ROWS), n0 = n_ct < 8 ? n_ct : 8;
-    ERP_CUDA(cudaMemsetAsync(w, 0, W_WORDS * sizeof(int32_t), ctx->stream));
-    set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(w + W_DYN_A, H, 0, n0);
-    ERP_LAUNCH(ctx, "set_dyn_kernel");
-    ERP_CUDA(cudaMemsetAsync(upper, 0, sizeof(int32_t) * (size_t)H * 2, ctx->stream));
-    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es, nullptr, nullptr, big);
-    ERP_LAUNCH(ctx, "prep_e_kernel");
-    prep_k_kernel<<<cdiv(m, 256), 256, 0, ctx->stream>>>((const float4*)d_l4, (const float4*)d_r4, m, Ks, (unsigned*)(w + W_KMAX));
+    b->Es = ctx->scratch<float>(S_SC_E, (size_t)H * 32, &st);
+    b->Es2 = ctx->scratch<float>(S_SC_E2, (size_t)H * 32, &st);
+    b->Ks = ctx->scratch<float>(S_SC_K, (size_t)cdiv(m_cap, SC_TILE) * SC_TILE * 32, &st);
+    b->w = ctx->scratch<int32_t>(S_SC_MISC, W_WORDS, &st);
+    b->upper = ctx->scratch<int32_t>(S_SC_BOUNDS, (size_t)H * 2, &st);       // [H] all hypotheses, [H] pass C rows
+    b->list = ctx->scratch<int32_t>(S_SC_LIST, (size_t)H * 2, &st);          // [H] survivors, [H] contenders
+    return st;
+}
+
+// the correspondence side, once per call (all hypothesis chunks share it)
+int score_tc_prepare(erp_ctx* ctx, const ScoreTcBuffers& b, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m)
+{
+    if (m_cap >= (1 << 24)) { set_error("score_tc: more than 2^24 correspondences"); return ERP_E_LIMIT; }
+    ERP_CUDA(cudaMemsetAsync(b.w, 0, W_WORDS * sizeof(int32_t), ctx->stream));
+    prep_k_kernel<<<cdiv(m_cap, 256), 256, 0, ctx->stream>>>((const float4*)d_l4, (const float4*)d_r4, m_cap, d_m, b.Ks, b.w);
     ERP_LAUNCH(ctx, "prep_k_kernel");
+    return ERP_OK;
+}
+
+// merges into *d_best the packed (count << 32 | ~id) of the best of the H hypotheses, exactly as
+// erp_score_dev + best_kernel would (algebraic residual).  The correspondence operand and the m-dependent words are
+// in place (score_tc_prepare, or the fused gather of geometry.cu) and the per-chunk words are clear; es_ready: the
+// hypothesis operand and the cleared bounds are in place too (min8_kernel wrote them).
+int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap,
+                    float tau, uint64_t hyp0, bool es_ready, int32_t* d_counts_scratch, uint64_t* d_best)
+{
+    const float big = score_tc_big(tau);
+    int32_t* w = b.w;
+    int32_t *upper = b.upper, *upper2 = b.upper + H, *survivors = b.list, *contenders = b.list + H;
+    if (!es_ready) {
+        prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, b.Es, big, upper, w);
+        ERP_LAUNCH(ctx, "prep_e_kernel");
+    }
     CUtensorMap me, me2, mk;
-    ERP_TRY(make_map(&me, Es, H, 32, SM_ROWS));
-    ERP_TRY(make_map(&me2, Es2, H, 32, SM_ROWS));
-    ERP_TRY(make_map(&mk, Ks, m, 32, SN_ROWS));
+    ERP_TRY(make_map(&me, b.Es, H, 32, SM_ROWS));
+    ERP_TRY(make_map(&me2, b.Es2, H, 32, SM_ROWS));
+    ERP_TRY(make_map(&mk, b.Ks, m_cap, 32, SN_ROWS));
     ScoreTcParams p;
-    p.m = m; p.tau = tau; p.big = big; p.kmax_bits = (const unsigned*)(w + W_KMAX);
+    p.tau = tau; p.big = big; p.kmax_bits = (const unsigned*)(w + W_KMAX);
 
     // pass A: every hypothesis, the first n0 correspondence tiles
     p.dyn = w + W_DYN_A; p.upper = upper;
     ERP_TRY(launch_score_tc(ctx, me, mk, p));
-    unsigned long long* amax = reinterpret_cast<unsigned long long*>(w + W_AMAX);
-    upper_argmax_kernel<<<min(cdiv(H, 256), ctx->sm_count * 4), 256, 0, ctx->stream>>>(upper, H, amax);
-    ERP_LAUNCH(ctx, "upper_argmax_kernel");
-    first_candidate_kernel<<<1, 1, 0, ctx->stream>>>(amax, first, w + W_LEN1);
-    ERP_LAUNCH(ctx, "first_candidate_kernel");
-    // exact count of the most promising hypothesis over ALL correspondences: counts_scratch[0] = L*
-    ERP_TRY(score_list_best(ctx, d_E, 1, first, w + W_LEN1, d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best));
-    plan_passes_kernel<<<1, 1, 0, ctx->stream>>>(w, d_counts_scratch, H, m, n0, n_ct);
-    ERP_LAUNCH(ctx, "plan_passes_kernel");
-
+    argmax_plan_kernel<<<min(cdiv(H, AP_THREADS), ctx->sm_count), AP_THREADS, 0, ctx->stream>>>(
+        upper, d_E, (const float4*)d_l4, (const float4*)d_r4, tau, (unsigned long long)hyp0, w, (unsigned long long*)d_best);
+    ERP_LAUNCH(ctx, "argmax_plan_kernel");
     // pass B: every hypothesis, tiles [n0, ct1)
     p.dyn = w + W_DYN_B;
     ERP_TRY(launch_score_tc(ctx, me, mk, p));
-    survivor_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, H, w, survivors);
+    survivor_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, w, survivors, (const float4*)b.Es, (float4*)b.Es2);
     ERP_LAUNCH(ctx, "survivor_select_kernel");
-
     // pass C: the survivors, tiles [ct1, n_ct)
-    prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, Es2, survivors, w + W_DYN_C, big);
-    ERP_LAUNCH(ctx, "prep_e_kernel(survivors)");
     p.dyn = w + W_DYN_C; p.upper = upper2;
     ERP_TRY(launch_score_tc(ctx, me2, mk, p));
     final_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, upper2, survivors, w, contenders);
     ERP_LAUNCH(ctx, "final_select_kernel");
     ctx->sc_misc_dev = w;
-    return score_list_best(ctx, d_E, H, contenders, w + W_LENF, d_l4, d_r4, m, tau, hyp0, d_counts_scratch, d_best);
+    return score_list_best(ctx, d_E, H, contenders, w + W_LENF, d_l4, d_r4, m_cap, w + W_M, tau, hyp0, d_counts_scratch, d_best);
+}
+
+// stand-alone form (arbitrary E matrix, host or device m)
+int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau,
+                  uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best)
+{
+    ScoreTcBuffers b;
+    ERP_TRY(score_tc_buffers(ctx, H, m_cap, &b));
+    ERP_TRY(score_tc_prepare(ctx, b, d_l4, d_r4, m_cap, d_m));
+    return score_tc_search(ctx, b, d_E, H, d_l4, d_r4, m_cap, tau, hyp0, false, d_counts_scratch, d_best);
 }
 
 } // namespace erp

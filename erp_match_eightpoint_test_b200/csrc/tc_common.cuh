@@ -133,12 +133,6 @@ __device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr)
 }
 // instruction descriptor: D fp32, A/B tf32, both K-major, N = 256, M = 128
 
-__device__ __forceinline__ float tf32_rna(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 
 // wait for this thread's outstanding tcgen05.ld; the registers are operands so that no use of
 // them can be scheduled above the wait
@@ -175,20 +169,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+inline EncodeTiledFn lookup_encode_fn()
+{
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+    return nullptr;
+}
 inline EncodeTiledFn encode_fn()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
+    static const EncodeTiledFn fn = lookup_encode_fn();     // C++11 magic static: initialised once, thread safe
     return fn;
 }
 

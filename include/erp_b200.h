@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ERP_B200_VERSION 100
+#define ERP_B200_VERSION 200
 
 typedef struct erp_ctx erp_ctx;
 
@@ -49,7 +49,8 @@ typedef enum {
     ERP_E_LIMIT = 6,           /* a size exceeds an implementation limit                        */
     ERP_E_CUDA = -1,
     ERP_E_NO_DEVICE = -2,
-    ERP_E_ARCH = -3            /* device is not sm_100                                          */
+    ERP_E_ARCH = -3,           /* device is not sm_100                                          */
+    ERP_E_NCCL = -4            /* NCCL missing (libnccl.so.2 not loadable) or a collective failed */
 } erp_status;
 
 typedef enum {
@@ -104,6 +105,10 @@ int  erp_ctx_last_score_kernel_ms(erp_ctx* ctx, float* ms, int* launches);
  * [1] correspondence tiles (256 each) every hypothesis was bounded on, [2] tiles in total,
  * [3] survivors bounded on the remaining tiles, [4] contenders scored exactly, [5] L* */
 int  erp_ctx_last_score_stats(erp_ctx* ctx, int64_t out[6]);
+/* device time of the stages of the last erp_pair_pose* call on this context, from CUDA events on its stream:
+ * [0] matching (2-NN, certificate, ratio / cross-check filter), [1] match exchange (multi-GPU all-gather) + gather of
+ * the matched keypoints + bearings, [2] RANSAC (sample, solve, score, best-model reduction, mask, refit) */
+int  erp_ctx_last_stage_ms(erp_ctx* ctx, float out[3]);
 
 /* ---------------------------------------------------------------- matching
  * replaces feature_matcher::match_two_image      src/feature_matcher.hpp:36, .cpp:42-59
@@ -207,6 +212,14 @@ int erp_pair_pose(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, c
                   const void* left_xy, const void* right_xy, size_t kp_stride_bytes, int width, int height,
                   uint64_t seed, int H, int S, int metric, float tau,
                   erp_dmatch* matches_out /* nq */, int* n_matches, erp_ransac_result* result, uint8_t* mask /* nq or NULL */);
+/* the same with everything on the device (dense rows, kp_stride_bytes between keypoint records) and NOTHING awaited: the
+ * call only enqueues.  d_matches needs room for nq records, d_n_matches is one int32, d_mask nq bytes or NULL, d_result one
+ * erp_ransac_result -- all device memory.  The match count never visits the host: every launch of the pose chain is sized
+ * for nq and reads the count from d_n_matches.  With fewer than S matches the result is meaningless (check *d_n_matches). */
+int erp_pair_pose_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, float ratio, int cross_check,
+                      const void* d_left_xy, const void* d_right_xy, size_t kp_stride_bytes, int width, int height,
+                      uint64_t seed, int H, int S, int metric, float tau,
+                      erp_dmatch* d_matches, int32_t* d_n_matches, uint8_t* d_mask, erp_ransac_result* d_result);
 /* sharded form: every rank scores its hypothesis range and leaves its packed best in
  * d_packed (one uint64 on the device); the caller max-reduces it across ranks (one 8-byte
  * NCCL allreduce) and calls erp_ransac_finish_dev with the winning packed value. */
@@ -218,6 +231,75 @@ int erp_ransac_finish_dev(erp_ctx* ctx, const double* d_l3, const double* d_r3,
                           const float* d_l4, const float* d_r4, int m, uint64_t seed,
                           uint64_t packed, int S, int metric, float tau,
                           uint8_t* d_mask /* m or NULL */, erp_ransac_result* result /* host */);
+
+/* ---------------------------------------------------------------- multi-GPU (north_star's split of ONE pair)
+ * The reference is single-process CPU code (src/automatic.cpp:117-126 calls match_two_image then find): there is no
+ * reference interface to cite for the split itself.  The work is cut where it is independent:
+ *   - query rows  [lo, hi) = erp_shard_range(nq, rank, nranks) per GPU, train set replicated (host-buffer calls upload
+ *     1/nranks of it per GPU and all-gather it over NVLink);
+ *   - hypothesis ids erp_shard_range(H, rank, nranks) per GPU (Philox is keyed by the global id: results do not depend
+ *     on nranks);
+ * and the exchange steps are: one all-gather of the per-rank match lists (fixed-size slots, rank order = ascending
+ * queryIdx), ONE 8-byte max all-reduce of the packed best model, and for cross-check a min all-reduce over the
+ * per-train (d2, queryIdx).  NCCL is loaded at run time (dlopen of libnccl.so.2; the library does not link it).
+ * Two ways to form the clique:
+ *   a) one process per GPU (torchrun, MPI ...): rank 0 calls erp_comm_unique_id, the caller broadcasts the 128 bytes,
+ *      every rank calls erp_comm_init on its own context;
+ *   b) one process, several GPUs: erp_group_create(devices) builds the contexts, the clique (ncclCommInitAll) and one
+ *      worker thread per device; erp_group_* calls fan out inside the call (what the C++ classes do when
+ *      $ERP_B200_DEVICES names more than one device). */
+#define ERP_COMM_ID_BYTES 128
+int erp_shard_range(int n, int rank, int nranks, int* lo, int* hi);   /* contiguous, sizes differ by at most one */
+int erp_comm_unique_id(void* id_out /* ERP_COMM_ID_BYTES */);
+int erp_comm_init(erp_ctx* ctx, int nranks, int rank, const void* id /* ERP_COMM_ID_BYTES */);
+int erp_comm_destroy(erp_ctx* ctx);
+int erp_comm_size(erp_ctx* ctx);                                    /* 1 without a clique */
+int erp_comm_rank(erp_ctx* ctx);
+/* in-place max all-reduce of one packed best-model word (the single small collective of north_star) */
+int erp_comm_allreduce_best_dev(erp_ctx* ctx, uint64_t* d_packed);
+/* cross-check: global nearest query per train row from the per-rank results of erp_nn1_reverse_dev (min d2, then the
+ * lowest query id among the ranks that attain it: cv::BFMatcher(crossCheck) tie order); in place, nt entries */
+int erp_comm_cross_check_dev(erp_ctx* ctx, int32_t* d_best_q, double* d_best_d2, int nt);
+/* one ERP pair split over the clique of ctx; collective: every rank calls it with the same arguments.
+ * d_q_shard: this rank's query rows [lo, hi) of nq_total; d_t: all nt train rows; keypoints of ALL queries / train rows.
+ * Outputs as erp_pair_pose_dev, identical on every rank (d_matches holds the concatenated list, nq_total records).
+ * Only enqueues.  Without a clique it is erp_pair_pose_dev. */
+int erp_pair_pose_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_total, const float* d_t, int nt, int dim,
+                           float ratio, int cross_check,
+                           const void* d_left_xy, const void* d_right_xy, size_t kp_stride_bytes, int width, int height,
+                           uint64_t seed, int H_total, int S, int metric, float tau,
+                           erp_dmatch* d_matches, int32_t* d_n_matches, uint8_t* d_mask, erp_ransac_result* d_result);
+/* host buffers, same arguments as erp_pair_pose on every rank (all ranks see the same host data): a rank uploads its
+ * query shard, 1/nranks of the train rows (all-gathered on the device) and the keypoints; results on every rank. */
+int erp_pair_pose_dist(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                       int dim, float ratio, int cross_check,
+                       const void* left_xy, const void* right_xy, size_t kp_stride_bytes, int width, int height,
+                       uint64_t seed, int H, int S, int metric, float tau,
+                       erp_dmatch* matches_out /* nq */, int* n_matches, erp_ransac_result* result, uint8_t* mask /* nq or NULL */);
+/* query-sharded feature_matcher::match_two_image (src/feature_matcher.cpp:42-59): this rank's part of the match list
+ * (global query ids, ascending); the caller concatenates the parts in rank order.  out needs room for hi - lo records. */
+int erp_knn2_match_dist(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                        int dim, float ratio, int cross_check, erp_dmatch* out, int* n_out);
+
+/* the same on device-resident descriptors (d_q_shard: this rank's rows of the nq_total queries), enqueue only;
+ * d_out needs room for the shard's rows, d_n_out is one int32 on the device */
+int erp_knn2_match_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_total, const float* d_t, int nt, int dim,
+                            float ratio, int cross_check, erp_dmatch* d_out, int32_t* d_n_out);
+
+typedef struct erp_group erp_group;
+int  erp_group_create(const int* devices, int ndev, erp_group** out);   /* ndev == 1 works without NCCL */
+void erp_group_destroy(erp_group* g);
+int  erp_group_size(erp_group* g);
+erp_ctx* erp_group_ctx(erp_group* g, int rank);
+/* erp_pair_pose / erp_knn2_match fanned out over the group's devices inside the call; same arguments and results */
+int erp_group_pair_pose(erp_group* g, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,
+                        int dim, float ratio, int cross_check,
+                        const void* left_xy, const void* right_xy, size_t kp_stride_bytes, int width, int height,
+                        uint64_t seed, int H, int S, int metric, float tau,
+                        erp_dmatch* matches_out, int* n_matches, erp_ransac_result* result, uint8_t* mask);
+int erp_group_knn2_match(erp_group* g, const float* q, int nq, size_t q_stride_bytes,
+                         const float* t, int nt, size_t t_stride_bytes, int dim,
+                         float ratio, int cross_check, erp_dmatch* out, int* n_out);
 
 /* ---------------------------------------------------------------- rows next to the hot path
  * 8-bit, 3-channel images (cv::Mat CV_8UC3), strides in bytes.  Unmapped output pixels are written 0

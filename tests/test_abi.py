@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in erp_b200.h but not exported"
     assert set(names) == set(binding._SIGNATURES), "binding.py and erp_b200.h disagree"
-    assert lib.erp_version() == 100
+    assert lib.erp_version() == 200
 
 
 def test_exports_are_plain_c_and_torch_free():

@@ -1,0 +1,102 @@
+"""GPU tests of north_star's split of ONE ERP pair over several B200s: query rows and hypothesis ids per
+GPU, match lists all-gathered in rank order, one 8-byte max all-reduce of the packed best model, min all-reduce for
+cross-check -- all inside liberp_b200.so (NCCL, no torch).  The bar: the match records (bytes), the packed winner, the
+inlier mask and the refit are IDENTICAL for G = 1, 2, 4, 8 devices.  Group sizes beyond the box's device count are
+skipped (the 1-GPU box runs G = 1; `gpurun --gpus 8` runs all of them, log under profiles/)."""
+import numpy as np
+import pytest
+
+import erp_match_eightpoint_test_b200 as erp
+import oracle as O
+from erp_match_eightpoint_test_b200 import binding, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def n_devices():
+    return erp.lib().erp_device_count()
+
+
+def scene_pair(nq, nt, dim, W, H, seed):
+    q, t, planted = synth.descriptor_pair(nq, nt, dim, seed=seed)
+    kp = synth.keypoint_pair(int((planted >= 0).sum()), W, H, seed=seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    left = (rng.uniform(0, 1, (nq, 2)) * [W, H - 1]).astype(np.float32)
+    right = (rng.uniform(0, 1, (nt, 2)) * [W, H - 1]).astype(np.float32)
+    qi = np.nonzero(planted >= 0)[0]
+    left[qi] = kp["left_xy"]
+    right[planted[qi]] = kp["right_xy"]
+    return q, t, left, right
+
+
+@pytest.fixture(scope="module")
+def single():
+    c = erp.Context(0)
+    yield c
+    c.close()
+
+
+def test_shard_range_matches_the_python_helper():
+    from erp_match_eightpoint_test_b200 import sharding
+    for n in (0, 1, 7, 100, 100003):
+        for w in (1, 2, 3, 8):
+            for r in range(w):
+                assert erp.shard_range(n, r, w) == sharding.shard_range(n, r, w)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_group_pair_pose_is_independent_of_the_group_size(single, G):
+    if n_devices() < G:
+        pytest.skip(f"{G} devices needed, {n_devices()} visible")
+    with erp.Group(range(G)) as grp:
+        assert len(grp) == G
+        # tensor-core search (H * m >= 3e7) and the SIMT path; ragged sizes: nq, nt, H not multiples of G
+        for (nq, nt, H, cross, seed) in [(6001, 7003, 60001, False, 41), (6001, 7003, 60001, True, 41), (1501, 1999, 2049, False, 43)]:
+            q, t, left, right = scene_pair(nq, nt, 64, 4096, 2048, seed)
+            wm, want = single.pair_pose(q, t, left, right, 4096, 2048, ratio=0.3, cross_check=cross, seed=7, H=H)
+            gm, got = grp.pair_pose(q, t, left, right, 4096, 2048, ratio=0.3, cross_check=cross, seed=7, H=H)
+            assert gm.tobytes() == wm.tobytes()
+            assert got["packed"] == want["packed"] and got["count"] == want["count"]
+            assert np.array_equal(got["mask"], want["mask"])
+            assert np.array_equal(got["E"], want["E"]) and np.array_equal(got["E_refit"], want["E_refit"])
+            assert np.array_equal(got["pose"], want["pose"])
+        # the oracle on the last one: records and winner
+        om = O.match(q, t, 0.3, False)
+        assert gm.tobytes() == om.tobytes()
+        l, r = O.bearings(left[om["queryIdx"]], 4096, 2048), O.bearings(right[om["trainIdx"]], 4096, 2048)
+        assert got["packed"] == O.ransac(l, r, seed=7, hyp0=0, H=2049)["packed"]
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("dim", [64, 128])
+def test_group_match_with_cross_check_min_reduce(single, G, dim):
+    """Query-sharded match_two_image: the per-train nearest query is min-reduced over the ranks (d2, then lowest id)."""
+    if n_devices() < G:
+        pytest.skip(f"{G} devices needed, {n_devices()} visible")
+    q, t, _ = synth.descriptor_pair(5003, 4099, dim, seed=51 + dim)
+    t[100] = t[7]; q[11] = q[4000]; q[12] = q[4000]                 # ties across shards: lowest index wins on both sides
+    with erp.Group(range(G)) as grp:
+        for ratio, cross in [(0.3, False), (0.3, True), (-1.0, True), (0.8, True)]:
+            want = O.match(q, t, ratio, cross)
+            got = grp.knn2_match(q, t, ratio, cross)
+            assert got.tobytes() == want.tobytes(), (G, dim, ratio, cross)
+            assert single.knn2_match(q, t, ratio, cross).tobytes() == want.tobytes()
+        # fewer queries than ranks: empty shards take part in the collectives
+        few = grp.knn2_match(q[:3], t, -1.0, True)
+        assert few.tobytes() == O.match(q[:3], t, -1.0, True).tobytes()
+
+
+def test_pair_pose_dev_keeps_the_match_count_on_the_device(single):
+    """erp_pair_pose (one call, no host synchronisation between matcher and pose) against the oracle end to end."""
+    q, t, left, right = scene_pair(5000, 6000, 64, 4096, 2048, 61)
+    for metric in (0, 1, 2):
+        m, r = single.pair_pose(q, t, left, right, 4096, 2048, ratio=0.3, seed=9, H=4000, metric=metric)
+        om = O.match(q, t, 0.3, False)
+        assert m.tobytes() == om.tobytes()
+        l, rr = O.bearings(left[om["queryIdx"]], 4096, 2048), O.bearings(right[om["trainIdx"]], 4096, 2048)
+        ref = O.ransac(l, rr, seed=9, hyp0=0, H=4000, metric=metric)
+        assert r["packed"] == ref["packed"]
+        assert np.array_equal(r["mask"], O.inlier_mask(ref["E"], l, rr, metric=metric))
+        assert r["n_refit"] == int(r["mask"].sum())
+    ms = single.last_stage_ms()
+    assert all(x >= 0 for x in ms) and sum(ms) > 0
