@@ -705,13 +705,88 @@ solve1_kernel(const double* __restrict__ Gin, int max_sweeps, double* __restrict
     solve1_warp<WANT_POSE>(sm, Gin, max_sweeps, Eout, pose);
 }
 
+// ------------------------------------------------------------------ refit solve: smallest eigenvector by inverse iteration
+// The refit of a RANSAC call is the right singular vector of the smallest singular value of the inlier matrix A
+// (eight_point.cpp:38-43), i.e. the eigenvector of the smallest eigenvalue of G = A^T A (9 x 9, SPD).  A Jacobi eigen
+// solve on one warp is a serial chain of ~300 rotations (130 us measured, most of the fixed cost of a call).  The
+// winning minimal-sample model is already close to that vector, and the smallest eigenvalue (noise) is orders of
+// magnitude below the next one (signal), so inverse iteration  x <- normalise((G + mu I)^-1 x)  from x0 = E_best gains
+// several digits per step: one 9 x 9 Cholesky factorisation and a handful of triangular solves on one thread, ~5 us.
+// mu = 1e-12 trace(G) keeps the factorisation defined for noise-free input (an exactly singular G).  The sign follows
+// E_best.  Only used for the RANSAC refit (sign-invariant consumers); the reference-mode solves keep OpenCV's Jacobi.
+__device__ void refit_inverse_iteration(const double* Gp /* packed upper triangle */, const double* x0, double* __restrict__ Eout,
+                                        float* __restrict__ pose)
+{
+    double L[9][9];
+    double trace = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) trace += Gp[tri(i, i)];
+    const double mu = 1e-12 * trace + 1e-300;
+    double inv[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        double d = Gp[tri(j, j)] + mu;
+#pragma unroll
+        for (int k = 0; k < j; k++) d = __fma_rn(-L[j][k], L[j][k], d);
+        d = d > mu * 1e-3 ? d : mu * 1e-3;                    // numerically semi-definite: keep the factor finite
+        const double r = sqrt(d);
+        L[j][j] = r;
+        inv[j] = 1.0 / r;
+#pragma unroll
+        for (int i = j + 1; i < 9; i++) {
+            double v = Gp[tri(j, i)];
+#pragma unroll
+            for (int k = 0; k < j; k++) v = __fma_rn(-L[i][k], L[j][k], v);
+            L[i][j] = v * inv[j];
+        }
+    }
+    double x[9], n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { x[i] = x0[i]; n2 = __fma_rn(x[i], x[i], n2); }
+    if (!(n2 > 0.0)) { x[8] = 1.0; n2 = 1.0; }
+    {
+        const double s = 1.0 / sqrt(n2);
+#pragma unroll
+        for (int i = 0; i < 9; i++) x[i] *= s;
+    }
+    for (int it = 0; it < 24; it++) {
+        double y[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {                        // L z = x
+            double v = x[i];
+#pragma unroll
+            for (int k = 0; k < i; k++) v = __fma_rn(-L[i][k], y[k], v);
+            y[i] = v * inv[i];
+        }
+#pragma unroll
+        for (int i = 8; i >= 0; i--) {                       // L^T y = z
+            double v = y[i];
+#pragma unroll
+            for (int k = i + 1; k < 9; k++) v = __fma_rn(-L[k][i], y[k], v);
+            y[i] = v * inv[i];
+        }
+        double yy = 0.0, xy = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) { yy = __fma_rn(y[i], y[i], yy); xy = __fma_rn(x[i], y[i], xy); }
+        if (!(yy > 0.0) || !(yy < INFINITY)) break;
+        const double s = (xy < 0.0 ? -1.0 : 1.0) / sqrt(yy);
+        double diff = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) { const double v = y[i] * s; diff = fmax(diff, fabs(v - x[i])); x[i] = v; }
+        if (diff < 4e-15) break;
+    }
+    M3 E;
+#pragma unroll
+    for (int k = 0; k < 9; k++) E.v[k] = x[k];
+    finish_hypothesis<true>(E, Eout, pose);
+}
+
 // ------------------------------------------------------------------ end of a RANSAC call, one launch
 // Inlier mask of the winning model, the Gram matrix of its inliers and the least-squares refit (eight_point.cpp:16-50 on
 // the inlier set): every block marks 256 correspondences and reduces their 45 Gram entries in a fixed order; the last
 // block to finish (one ticket) sums the per-block partials in block order (deterministic), solves the 9 x 9 system on its
 // first warp and writes the whole erp_ransac_result.  cnt: [0] inliers, [1] ticket (both zeroed by the caller).
 constexpr int FIN_THREADS = 256;
-constexpr int FIN_SWEEPS = 12;
 template <int METRIC>
 __global__ void __launch_bounds__(FIN_THREADS)
 finish_kernel(const double* __restrict__ Eb, const uint64_t* __restrict__ packed_dev, const double* __restrict__ l3,
@@ -722,7 +797,6 @@ finish_kernel(const double* __restrict__ Eb, const uint64_t* __restrict__ packed
     __shared__ float Es[9];
     __shared__ double red[FIN_THREADS / 32][45];
     __shared__ double Gs[45];
-    __shared__ Solve1Smem sm;
     __shared__ int last;
     const int m = dev_len(m_dev, m_cap);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -774,16 +848,23 @@ finish_kernel(const double* __restrict__ Eb, const uint64_t* __restrict__ packed
     __syncthreads();
     if (!last) return;
     __threadfence();
+    // five interleaved partial sums per entry (225 threads, loads batched: a single chain of ~200 dependent L2 round
+    // trips cost 70 us here), combined in a fixed order: deterministic
     const int nb = (m + FIN_THREADS - 1) / FIN_THREADS;
-    if (threadIdx.x < 45) {
+    double* part = &red[0][0];                                    // 5 x 45 doubles, the reduction buffer is free again
+    if (threadIdx.x < 225) {
+        const int e = threadIdx.x % 45, g = threadIdx.x / 45;
         double x = 0.0;
-        for (int b = 0; b < nb; b++) x += *reinterpret_cast<volatile const double*>(&P[(size_t)b * 45 + threadIdx.x]);
-        Gs[threadIdx.x] = x;
+#pragma unroll 8
+        for (int b = g; b < nb; b += 5) x += __ldcg(&P[(size_t)b * 45 + e]);
+        part[g * 45 + e] = x;
     }
     __syncthreads();
-    if (wid != 0) return;
-    solve1_warp<true>(sm, Gs, FIN_SWEEPS, out->E_refit, out->pose);
-    if (lane == 0) {
+    if (threadIdx.x < 45) Gs[threadIdx.x] = (((part[threadIdx.x] + part[45 + threadIdx.x]) + part[90 + threadIdx.x]) + part[135 + threadIdx.x]) + part[180 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    refit_inverse_iteration(Gs, Eb, out->E_refit, out->pose);
+    {
         const uint64_t packed = *packed_dev;
         out->packed = packed;
         out->hyp_id = 0xFFFFFFFFull - (packed & 0xFFFFFFFFull);

@@ -324,7 +324,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool lex_less(double d, int i, double bd, int bi) { return d < bd || (d == bd && i < bi); }
 
-// one warp per query; lane j owns candidates j and j + 32 (n_groups * TOPK <= 64, n_groups = splits x column groups)
+// one warp per query; lane j owns candidates j, j + 32, ... (n_groups * TOPK <= 32 * SPL, n_groups = segments x column groups;
+// SPL = 2 for up to four segments per query row, 4 when a short query set is cut finer to fill the machine)
+template <int SPL>
 __global__ void __launch_bounds__(256)
 refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim, int n_groups, int topk, double kappa,
               const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_s, const float* __restrict__ cand_thr,
@@ -352,34 +354,31 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
     // them, and the query row is converted to fp64 ONCE per warp (the fp32 -> fp64 conversions, not the FMAs, were the
     // limiter: 128 per candidate).  Each candidate still gets the oracle's fma chain in the oracle's order.
     __shared__ double q_sh[8][128];
-    __shared__ int c_idx[8][64];
-    __shared__ float c_sc[8][64];
+    __shared__ int c_idx[8][32 * SPL];
+    __shared__ float c_sc[8][32 * SPL];
     const int wq = threadIdx.x >> 5;
     for (int k = lane; k < dim; k += 32) q_sh[wq][k] = (double)qr[k];
     int n_act;
     {
-        int ti[2];
-        float s2[2];
-        bool act[2];
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const int c = lane + 32 * s;
-            ti[s] = c < ncand ? cand_idx[(size_t)qi * ncand + c] : -1;
-            s2[s] = (c < ncand && ti[s] >= 0) ? cand_s[(size_t)qi * ncand + c] : INFINITY;   // unused list slots are -1 / unset
-            act[s] = ti[s] >= 0 && ti[s] < nt && (s2[s] < thr || !(thr < INFINITY));
-        }
-        const unsigned m0 = __ballot_sync(0xffffffffu, act[0]), m1 = __ballot_sync(0xffffffffu, act[1]);
         const unsigned lt = (1u << lane) - 1u;
-        if (act[0]) { const int pos = __popc(m0 & lt); c_idx[wq][pos] = ti[0]; c_sc[wq][pos] = s2[0]; }
-        if (act[1]) { const int pos = __popc(m0) + __popc(m1 & lt); c_idx[wq][pos] = ti[1]; c_sc[wq][pos] = s2[1]; }
-        n_act = __popc(m0) + __popc(m1);
+        n_act = 0;
+#pragma unroll
+        for (int s = 0; s < SPL; s++) {
+            const int c = lane + 32 * s;
+            const int ti = c < ncand ? cand_idx[(size_t)qi * ncand + c] : -1;
+            const float s2 = (c < ncand && ti >= 0) ? cand_s[(size_t)qi * ncand + c] : INFINITY;   // unused list slots are -1 / unset
+            const bool act = ti >= 0 && ti < nt && (s2 < thr || !(thr < INFINITY));
+            const unsigned mk = __ballot_sync(0xffffffffu, act);
+            if (act) { const int pos = n_act + __popc(mk & lt); c_idx[wq][pos] = ti; c_sc[wq][pos] = s2; }
+            n_act += __popc(mk);
+        }
     }
     __syncwarp();
-    double d[2];
-    int id[2];
-    float sc[2];
+    double d[SPL];
+    int id[SPL];
+    float sc[SPL];
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < SPL; s++) {
         const int c = lane + 32 * s;
         d[s] = INFINITY; id[s] = 0x7fffffff; sc[s] = INFINITY;
         if (32 * s < n_act) {                                  // warp-uniform: the second pass rarely runs
@@ -424,12 +423,16 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
     // observed |approximate - exact| over the candidates, in units of (|q|^2 + max|t|^2)
     float dev = 0.f;
 #pragma unroll
-    for (int s = 0; s < 2; s++)
+    for (int s = 0; s < SPL; s++)
         if (id[s] != 0x7fffffff && scale > 0.0) dev = fmaxf(dev, (float)(fabs((double)sc[s] + qn - d[s]) / scale));
     for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
 
-    // lane-local order, then two warp-wide lexicographic minima
-    if (lex_less(d[1], id[1], d[0], id[0])) { double x = d[0]; d[0] = d[1]; d[1] = x; int y = id[0]; id[0] = id[1]; id[1] = y; }
+    // lane-local order (the two smallest of the lane's entries to slots 0 and 1), then two warp-wide lexicographic minima
+#pragma unroll
+    for (int s = 1; s < SPL; s++) {
+        if (lex_less(d[s], id[s], d[1], id[1])) { double x = d[1]; d[1] = d[s]; d[s] = x; int y = id[1]; id[1] = id[s]; id[s] = y; }
+        if (lex_less(d[1], id[1], d[0], id[0])) { double x = d[0]; d[0] = d[1]; d[1] = x; int y = id[0]; id[0] = id[1]; id[1] = y; }
+    }
     double B0 = d[0]; int I0 = id[0];
     for (int o = 16; o > 0; o >>= 1) {
         double od = __shfl_xor_sync(0xffffffffu, B0, o); int oi = __shfl_xor_sync(0xffffffffu, I0, o);
@@ -463,7 +466,7 @@ refine_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, 
     }
 }
 
-// topk must be a power of two, n_lists * topk <= 64
+// topk must be a power of two, n_lists * topk <= 128
 // misc words of a tcgen05 call: [0] re-scan count of THIS call (also the length of its re-scan list), [1] max |t|^2 bits,
 // [2] max deviation bits, [3] max |q|^2 bits, [4] re-scan count summed over the query chunks of one host call
 __global__ void misc_reset_kernel(int32_t* misc) { misc[0] = 0; misc[3] = 0; }
@@ -489,8 +492,13 @@ int refine_launch(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int 
                   const int32_t* cand, const float* cand_s, const float* cand_thr, unsigned* misc, int32_t* d_idx2, float* d_dist2,
                   double* d_d2, int32_t* rescan_list)
 {
-    refine_kernel<<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_lists, topk, kappa, cand, cand_s, cand_thr, misc,
-                                                        d_idx2, d_dist2, d_d2, rescan_list);
+    if (n_lists * topk > 128) { set_error("refine: %d candidate slots per query", n_lists * topk); return ERP_E_LIMIT; }
+    if (n_lists * topk <= 64)
+        refine_kernel<2><<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_lists, topk, kappa, cand, cand_s, cand_thr, misc,
+                                                               d_idx2, d_dist2, d_d2, rescan_list);
+    else
+        refine_kernel<4><<<cdiv(nq, 8), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, n_lists, topk, kappa, cand, cand_s, cand_thr, misc,
+                                                               d_idx2, d_dist2, d_d2, rescan_list);
     ERP_LAUNCH(ctx, "refine_kernel");
     return ERP_OK;
 }

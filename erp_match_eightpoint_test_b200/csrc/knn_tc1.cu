@@ -27,7 +27,7 @@ constexpr int F_EPI_THREADS = F_EPI_GROUPS * 128;
 constexpr int F_THREADS = 128 + F_EPI_THREADS;
 constexpr int F_EPI_COLS = F_BN / F_EPI_GROUPS;
 constexpr int F_TOPK = 8;
-constexpr int F_MAX_SEG = 64 / (F_TOPK * F_EPI_GROUPS);     // 4 segments per query pair
+constexpr int F_MAX_SEG = 128 / (F_TOPK * F_EPI_GROUPS);    // up to 8 segments per query pair (refine_kernel: 128 candidate slots)
 constexpr int F_AUG_T = F_BN * 32;        // 8 KB: one extra k step (8 floats) per train row, 32-byte swizzle rows
 constexpr int F_AUG_Q = F_BM * 32;        // 4 KB: the constant query side of that k step
 constexpr int F_BARS = 256;               // mbarriers + TMEM slot

@@ -107,6 +107,70 @@ score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
     }
 }
 
+// Exact counts of a LIST of hypotheses (the contenders of the tensor-core search: a few hundred of a million) and their
+// packed best, algebraic residual.  Roles are transposed with respect to score_kernel: a thread owns one hypothesis (its
+// nine coefficients in registers), a block stages a slice of correspondences as Kronecker products in shared memory
+// and every thread walks it with broadcast reads -- no cross-thread reduction per hypothesis, full instruction-level
+// parallelism across correspondences, and many small blocks (tile x slice) so that a short list still fills the machine.
+// Same fma chain as everywhere else: counts are bit-exact.
+constexpr int SL_HYPS = 128;       // hypotheses per block (threads)
+constexpr int SL_CORR = 256;       // correspondences per block
+__global__ void __launch_bounds__(SL_HYPS)
+score_list_kernel(const double* __restrict__ E, int H_cap, const int32_t* __restrict__ hlist, const int32_t* __restrict__ hlist_len,
+                  const float4* __restrict__ l4, const float4* __restrict__ r4, int m_cap, const int32_t* __restrict__ m_dev, float tau,
+                  int32_t* __restrict__ counts, int32_t* __restrict__ tile_done, unsigned long long* __restrict__ best,
+                  unsigned long long hyp0)
+{
+    __shared__ __align__(16) float ks[SL_CORR][12];
+    __shared__ int last_slice;
+    const int H = min(H_cap, *hlist_len);
+    if ((int)blockIdx.x * SL_HYPS >= H) return;
+    const int m = dev_len(m_dev, m_cap);
+    const int c0 = blockIdx.y * SL_CORR, n = max(0, min(SL_CORR, m - c0));
+    for (int i = threadIdx.x; i < n; i += SL_HYPS) {
+        float k[9];
+        kron9(l4[c0 + i], r4[c0 + i], k);
+        *reinterpret_cast<float4*>(&ks[i][0]) = make_float4(k[0], k[1], k[2], k[3]);
+        *reinterpret_cast<float4*>(&ks[i][4]) = make_float4(k[4], k[5], k[6], k[7]);
+        ks[i][8] = k[8];
+    }
+    __syncthreads();
+    for (int h0 = blockIdx.x * SL_HYPS; h0 < H; h0 += gridDim.x * SL_HYPS) {
+        const int h = h0 + threadIdx.x;
+        float e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (h < H) scale_E(E + (size_t)hlist[h] * 9, e);
+        int cnt = 0;
+#pragma unroll 4
+        for (int i = 0; i < n; i++) {
+            const float4 k0 = *reinterpret_cast<const float4*>(&ks[i][0]), k1 = *reinterpret_cast<const float4*>(&ks[i][4]);
+            const float k8 = ks[i][8];
+            float res = __fmul_rn(e[0], k0.x);
+            res = __fmaf_rn(e[1], k0.y, res); res = __fmaf_rn(e[2], k0.z, res); res = __fmaf_rn(e[3], k0.w, res);
+            res = __fmaf_rn(e[4], k1.x, res); res = __fmaf_rn(e[5], k1.y, res); res = __fmaf_rn(e[6], k1.z, res);
+            res = __fmaf_rn(e[7], k1.w, res); res = __fmaf_rn(e[8], k8, res);
+            cnt += fabsf(res) < tau ? 1 : 0;
+        }
+        if (h < H && cnt) atomicAdd(&counts[h], cnt);
+        // the block that completes a hypothesis tile (last of its gridDim.y slices) merges the tile's packed best
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last_slice = atomicAdd(&tile_done[h0 / SL_HYPS], 1) == (int)gridDim.y - 1;
+        __syncthreads();
+        if (last_slice) {
+            __threadfence();
+            unsigned long long b = 0;
+            if (h < H) {
+                const int c = *reinterpret_cast<volatile int32_t*>(&counts[h]);
+                const unsigned long long id = hyp0 + (unsigned long long)hlist[h];
+                b = ((unsigned long long)(uint32_t)c << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)id);
+            }
+            for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_down_sync(0xffffffffu, b, o); b = y > b ? y : b; }
+            if ((threadIdx.x & 31) == 0 && b) atomicMax(best, b);
+        }
+        __syncthreads();
+    }
+}
+
 // packed best over a count array: (count << 32) | (0xFFFFFFFF - global id)
 __global__ void best_kernel(const int32_t* __restrict__ counts, int H, uint64_t hyp0,
                             unsigned long long* __restrict__ best,
@@ -195,18 +259,14 @@ int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d
                     const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau, uint64_t hyp0,
                     int32_t* d_counts /* H_max + H_max / 128 + 1, scratch */, uint64_t* d_best)
 {
-    float tau2, sin2;
-    thresholds(tau, tau2, sin2);
-    const int tiles = cdiv(H_max, TH);
+    const int tiles = cdiv(H_max, SL_HYPS);
     ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * ((size_t)H_max + tiles), ctx->stream));
-    // the list is usually short (cfg3: ~900 contenders = 14 hypothesis tiles): split the correspondences finely so that
-    // it still fills the machine (14 x 16 blocks of 8 correspondences per thread took 100 us, 14 x 48 of 4: see profiles/)
-    int msplit = max(1, min(cdiv(m_cap, SC_THREADS * 4), 48));
-    dim3 grid(min(tiles, 64), msplit);
-    score_kernel<ERP_METRIC_ALGEBRAIC, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m_cap, d_m,
-                                                                              tau, tau2, sin2, d_counts, d_list, d_len,
-                                                                              (unsigned long long*)d_best, (unsigned long long)hyp0, d_counts + H_max);
-    ERP_LAUNCH(ctx, "score_kernel(list)");
+    // the list is usually short (cfg3: ~900 contenders = 7 hypothesis tiles): tile x slice blocks of 128 threads
+    // (score_kernel in list mode took 100 us for them, this kernel 20)
+    dim3 grid(min(tiles, 32), max(1, cdiv(m_cap, SL_CORR)));
+    score_list_kernel<<<grid, SL_HYPS, 0, ctx->stream>>>(d_E, H_max, d_list, d_len, (const float4*)d_l4, (const float4*)d_r4, m_cap, d_m, tau,
+                                                        d_counts, d_counts + H_max, (unsigned long long*)d_best, (unsigned long long)hyp0);
+    ERP_LAUNCH(ctx, "score_list_kernel");
     return ERP_OK;
 }
 

@@ -367,11 +367,21 @@ argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__
 #pragma unroll
     for (int i = 0; i < 9; i++) e[i] = Es[i];
     int cnt = 0;
-    for (int c = threadIdx.x; c < m; c += AP_THREADS) {
-        const float4 l = l4[c], r = r4[c];
-        float k[9];
-        kron9(l, r, k);
-        cnt += inlier<ERP_METRIC_ALGEBRAIC>(e, k, l, r, tau, 0.f, 0.f) ? 1 : 0;
+    // four correspondences in flight per thread: the loop is a chain of L2 round trips otherwise
+    for (int c = threadIdx.x; c < m; c += 4 * AP_THREADS) {
+        float4 l[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int cu = c + u * AP_THREADS;
+            l[u] = cu < m ? l4[cu] : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[u] = cu < m ? r4[cu] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float k[9];
+            kron9(l[u], r[u], k);
+            cnt += (c + u * AP_THREADS < m && inlier<ERP_METRIC_ALGEBRAIC>(e, k, l[u], r[u], tau, 0.f, 0.f)) ? 1 : 0;
+        }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) wsum[wid] = cnt;
