@@ -120,6 +120,7 @@ ERP_API void erp_ctx_destroy(erp_ctx* ctx)
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     for (cudaEvent_t e : ctx->ev_stage) if (e) cudaEventDestroy(e);
+    graph_release(ctx);
     comm_release(ctx);
     for (cudaEvent_t e : ctx->ev_score) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -244,9 +245,9 @@ ERP_API int erp_knn2_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_
         return knn2_tc(ctx, d_q, nq, d_t, nt, dim, d_idx2, d_dist2, d_d2);
     ctx->knn_stats[0] = ERP_ENGINE_EXACT_SIMT; ctx->knn_stats[1] = 0; ctx->knn_stats[2] = 1; ctx->knn_stats[3] = cdiv(nq, 64);
     ctx->knn_stats[4] = 0;
-    ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_k0));
     ERP_TRY(knn2_exact(ctx, d_q, nq, d_t, nt, dim, nullptr, 0, 0, d_idx2, d_dist2, d_d2));
-    ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_k1));
     return ERP_OK;
 }
 
@@ -593,6 +594,89 @@ ERP_API int erp_inlier_mask(erp_ctx* ctx, const double* E9, const double* l3, co
 
 namespace erp {
 
+// ---- CUDA graph of a device-resident pair call ------------------------------------------------------------------
+// One pair is ~25 stream operations of which most are a few microseconds long: issued one by one the host cannot stay
+// ahead of the GPU (and, multi-GPU, the ranks drift apart between two collectives).  The calls that only enqueue
+// (erp_pair_pose_dev, erp_pair_pose_dist_dev) are therefore captured: first call with a given argument set runs
+// directly (it also sizes the scratch), the second one is captured into a graph, later ones are one cudaGraphLaunch.
+// A cached graph holds device pointers: any scratch re-allocation, engine change or new clique invalidates it.
+// ERP_B200_GRAPH=0 turns the cache off.
+struct GraphCache {
+    std::vector<uint8_t> key, seen;
+    uint64_t key_gen = 0, seen_gen = 0;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;
+    int64_t knn_stats[5] = {0, 0, 0, 0, 0};
+    int32_t *sc_misc_dev = nullptr, *tc_misc_dev = nullptr;
+    int n_ev_score = 0;
+    bool disabled = false;
+};
+
+void graph_release(erp_ctx* ctx)
+{
+    if (!ctx->graph) return;
+    if (ctx->graph->exec) cudaGraphExecDestroy(ctx->graph->exec);
+    delete ctx->graph;
+    ctx->graph = nullptr;
+}
+
+int graph_run(erp_ctx* ctx, const void* key, size_t key_bytes, const std::function<int()>& body)
+{
+    static const bool off = [] { const char* e = getenv("ERP_B200_GRAPH"); return e && atoi(e) == 0; }();
+    if (off) return body();
+    if (!ctx->graph) ctx->graph = new GraphCache();
+    GraphCache& g = *ctx->graph;
+    if (g.disabled) return body();
+    std::vector<uint8_t> k((const uint8_t*)key, (const uint8_t*)key + key_bytes);
+    const void* extra[2] = {(const void*)(intptr_t)ctx->engine, (const void*)ctx->comm};
+    k.insert(k.end(), (const uint8_t*)extra, (const uint8_t*)extra + sizeof extra);
+    if (g.exec && g.key == k && g.key_gen == ctx->scratch_gen) {
+        ERP_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+        ctx->launches += g.launches;
+        memcpy(ctx->knn_stats, g.knn_stats, sizeof g.knn_stats);
+        ctx->sc_misc_dev = g.sc_misc_dev; ctx->tc_misc_dev = g.tc_misc_dev; ctx->n_ev_score = g.n_ev_score;
+        return ERP_OK;
+    }
+    if (g.seen == k && g.seen_gen == ctx->scratch_gen) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        const uint64_t l0 = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            g.disabled = true;
+            return body();
+        }
+        ctx->capturing = true;
+        const int st = body();
+        ctx->capturing = false;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        const bool usable = st == ERP_OK && e == cudaSuccess && graph && ctx->scratch_gen == g.seen_gen;
+        if (usable && cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) g.exec = nullptr;
+        if (graph) cudaGraphDestroy(graph);
+        if (!usable || !g.exec) {
+            // nothing was executed: run the call directly; a body that cannot be captured stays on the direct path
+            cudaGetLastError();
+            ctx->launches = l0;
+            g.exec = nullptr;
+            g.seen.clear();
+            if (st != ERP_OK) return st;
+            if (e != cudaSuccess) g.disabled = true;
+            return body();
+        }
+        g.launches = ctx->launches - l0;
+        ctx->launches = l0;
+        g.key = k; g.key_gen = ctx->scratch_gen;
+        memcpy(g.knn_stats, ctx->knn_stats, sizeof g.knn_stats);
+        g.sc_misc_dev = ctx->sc_misc_dev; g.tc_misc_dev = ctx->tc_misc_dev; g.n_ev_score = ctx->n_ev_score;
+        ERP_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+        ctx->launches += g.launches;
+        return ERP_OK;
+    }
+    const int st = body();
+    g.seen = k; g.seen_gen = ctx->scratch_gen;
+    return st;
+}
+
 // search + (multi-GPU: one 8-byte max all-reduce) + finish, everything enqueued, nothing awaited.
 // k_ready: the correspondence operand of the tensor-core search was written by the gather.
 int pose_chain_tail(erp_ctx* ctx, const double* dl, const double* dr, const float* dl4, const float* dr4, int m_cap, const int32_t* d_m,
@@ -694,9 +778,11 @@ ERP_API int erp_pair_pose_dev(erp_ctx* ctx, const float* d_q, int nq, const floa
     ERP_ARG(d_left_xy && d_right_xy && kp_stride_bytes >= 8 && kp_stride_bytes % 4 == 0, ERP_E_ARG, "erp_pair_pose_dev: bad keypoints");
     ERP_ARG(nq >= 1, ERP_E_TOO_FEW_POINTS, "erp_pair_pose_dev: no query descriptors");
     DeviceGuard g(ctx->device);
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[0], ctx->stream));
+    const uint64_t key[] = {(uint64_t)(uintptr_t)d_q, (uint64_t)(uintptr_t)d_t, (uint64_t)(uintptr_t)d_left_xy, (uint64_t)(uintptr_t)d_right_xy, (uint64_t)(uintptr_t)d_matches, (uint64_t)(uintptr_t)d_n_matches, (uint64_t)(uintptr_t)d_mask, (uint64_t)(uintptr_t)d_result, (uint64_t)nq, (uint64_t)nt, (uint64_t)dim, (uint64_t)cross_check, (uint64_t)width, (uint64_t)height, (uint64_t)H, (uint64_t)S, (uint64_t)metric, (uint64_t)__builtin_bit_cast(uint32_t, ratio), (uint64_t)__builtin_bit_cast(uint32_t, tau), (uint64_t)seed, (uint64_t)kp_stride_bytes};      // every argument, no padding bytes
+    return graph_run(ctx, key, sizeof key, [&]() -> int {
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[0]));
     ERP_TRY(erp_knn2_match_dev(ctx, d_q, nq, d_t, nt, dim, ratio, cross_check, d_matches, d_n_matches));
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[1], ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[1]));
     PoseBuffers b;
     ERP_TRY(pose_chain_buffers(ctx, nq, &b));
     const bool tc = ransac_uses_tc(ctx, H, nq, metric);
@@ -707,11 +793,12 @@ ERP_API int erp_pair_pose_dev(erp_ctx* ctx, const float* d_q, int nq, const floa
     }
     ERP_TRY(gather_bearings_chain(ctx, d_matches, nq, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes, 0, width, height,
                                   b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[2], ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[2]));
     ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, nq, d_n_matches, seed, 0, H, S, metric, tau, tc, false,
                             d_mask ? d_mask : b.mask, d_result));
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[3], ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[3]));
     return ERP_OK;
+    });
 }
 
 ERP_API int erp_pair_pose(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes, const float* t, int nt, size_t t_stride_bytes,

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -64,7 +65,7 @@ enum ScratchId {
 
 } // namespace erp
 
-namespace erp { struct Comm; }
+namespace erp { struct Comm; struct GraphCache; }
 
 struct erp_ctx {
     int device = 0;
@@ -81,14 +82,21 @@ struct erp_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around the dominant distance kernel
     cudaEvent_t ev_stage[4] = {};                   // one pair: start, matches filtered, correspondences gathered, pose done
     erp::Comm* comm = nullptr;                      // multi-GPU: this context's rank of an NCCL clique (dist.cu)
+    // CUDA graph of the last device-resident pair call (api.cu: graph_run): the second identical call is captured,
+    // later ones are one cudaGraphLaunch.  scratch_gen counts scratch re-allocations (a cached graph holds pointers).
+    bool capturing = false;
+    uint64_t scratch_gen = 0;
+    erp::GraphCache* graph = nullptr;
     std::vector<cudaEvent_t> ev_score;              // pairs around the scoring kernel launches of the last RANSAC call
     int n_ev_score = 0;                             // events used by that call
     erp::Buf dev[erp::S_COUNT_];
     erp::Buf pinned[8];
 
     template <class T> T* scratch(int id, size_t count, int* status) {
+        void* before = dev[id].p;
         int s = dev[id].reserve(count * sizeof(T));
         if (s != ERP_OK) *status = s;
+        if (dev[id].p != before) scratch_gen++;
         return dev[id].as<T>();
     }
     template <class T> T* host_scratch(int id, size_t count, int* status) {
@@ -150,6 +158,13 @@ inline int ensure_dynamic_smem(erp_ctx* ctx, Kernel kernel, int bytes, std::atom
     return ERP_OK;
 }
 
+// timing events are recorded by the library on its own stream; inside a stream capture they become external event-record
+// nodes, so a replayed graph refreshes them like a direct call does
+inline cudaError_t record_timing(erp_ctx* ctx, cudaEvent_t ev)
+{
+    return cudaEventRecordWithFlags(ev, ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
 // next event of the scoring-kernel timer (created on demand, reused across calls)
 inline int score_event(erp_ctx* ctx, cudaEvent_t* ev)
 {
@@ -159,7 +174,7 @@ inline int score_event(erp_ctx* ctx, cudaEvent_t* ev)
         ctx->ev_score.push_back(e);
     }
     *ev = ctx->ev_score[ctx->n_ev_score++];
-    ERP_CUDA(cudaEventRecord(*ev, ctx->stream));
+    ERP_CUDA(record_timing(ctx, *ev));
     return ERP_OK;
 }
 
@@ -212,6 +227,10 @@ int pose_chain_buffers(erp_ctx* ctx, int m_cap, PoseBuffers* b);
 int pose_chain_tail(erp_ctx* ctx, const double* dl, const double* dr, const float* dl4, const float* dr4, int m_cap, const int32_t* d_m,
                     uint64_t seed, uint64_t hyp_offset, int H, int S, int metric, float tau, bool k_ready, bool reduce,
                     uint8_t* d_mask, erp_ransac_result* d_res);
+// graph cache (api.cu).  key: every argument of the call (bytes); body: enqueues the call on ctx->stream without
+// touching the host again.  The first call with a key runs directly, the second is captured, the rest replay.
+int graph_run(erp_ctx* ctx, const void* key, size_t key_bytes, const std::function<int()>& body);
+void graph_release(erp_ctx* ctx);
 // multi-GPU (dist.cu)
 int comm_allreduce_best(erp_ctx* ctx, uint64_t* d_packed);
 void comm_release(erp_ctx* ctx);

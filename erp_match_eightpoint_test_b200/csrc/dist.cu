@@ -246,6 +246,8 @@ ERP_API int erp_pair_pose_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_
     shard_range(nq_total, rank, G, &lo, &hi);
     shard_range(H_total, rank, G, &hlo, &hhi);
     ERP_ARG(hi == lo || d_q_shard, ERP_E_ARG, "erp_pair_pose_dist_dev: null query shard");
+    const uint64_t key[] = {(uint64_t)(uintptr_t)d_q_shard, (uint64_t)(uintptr_t)d_t, (uint64_t)(uintptr_t)d_left_xy, (uint64_t)(uintptr_t)d_right_xy, (uint64_t)(uintptr_t)d_matches, (uint64_t)(uintptr_t)d_n_matches, (uint64_t)(uintptr_t)d_mask, (uint64_t)(uintptr_t)d_result, (uint64_t)nq_total, (uint64_t)nt, (uint64_t)dim, (uint64_t)cross_check, (uint64_t)width, (uint64_t)height, (uint64_t)H_total, (uint64_t)S, (uint64_t)metric, (uint64_t)__builtin_bit_cast(uint32_t, ratio), (uint64_t)__builtin_bit_cast(uint32_t, tau), (uint64_t)seed, (uint64_t)kp_stride_bytes};      // every argument, no padding bytes
+    return graph_run(ctx, key, sizeof key, [&]() -> int {
     // slots of the match exchange: [header | up to cap records] per rank
     const int cap = cdiv(nq_total, G), slot = cap + 1;
     int st = ERP_OK;
@@ -258,20 +260,21 @@ ERP_API int erp_pair_pose_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_
     ERP_TRY(st);
     erp_dmatch* mine = slots + (size_t)slot * rank;
 
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[0], ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[0]));
     ERP_CUDA(cudaMemsetAsync(mine, 0, sizeof(erp_dmatch), ctx->stream));
     ERP_TRY(match_shard_dev(ctx, d_q_shard, lo, hi, d_t, nt, dim, ratio, cross_check, mine + 1, &mine->queryIdx));
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[1], ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[1]));
     // in place: rank r's slot is already at its position of the receive buffer
     ERP_NCCL(nccl().AllGather(mine, slots, (size_t)slot * sizeof(erp_dmatch), ncclInt8, ctx->comm->comm, ctx->stream));
     if (tc) ERP_CUDA(cudaMemsetAsync(sb.w, 0, W_WORDS_BYTES, ctx->stream));
     ERP_TRY(gather_slots_chain(ctx, slots, G, slot, nq_total, d_matches, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes,
                                width, height, b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[2], ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[2]));
     ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, nq_total, d_n_matches, seed, (uint64_t)hlo, hhi - hlo, S, metric, tau, tc, true,
                             d_mask ? d_mask : b.mask, d_result));
-    ERP_CUDA(cudaEventRecord(ctx->ev_stage[3], ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[3]));
     return ERP_OK;
+    });
 }
 
 namespace erp {

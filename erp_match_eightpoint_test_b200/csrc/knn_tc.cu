@@ -588,14 +588,14 @@ int knn2_tc(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, in
     p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s; p.cand_thr = cand_thr; p.qn = qn;
     p.tn_max_bits = reinterpret_cast<const unsigned*>(misc + 1);
 
-    if (ctx->tc_chunk == 0) ERP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if (ctx->tc_chunk == 0) ERP_CUDA(record_timing(ctx, ctx->ev_k0));
     switch (kch) {
     case 1: ERP_TRY(launch_tc<1>(ctx, mq, mt, p, grid)); break;
     case 2: ERP_TRY(launch_tc<2>(ctx, mq, mt, p, grid)); break;
     case 3: ERP_TRY(launch_tc<3>(ctx, mq, mt, p, grid)); break;
     default: ERP_TRY(launch_tc<4>(ctx, mq, mt, p, grid)); break;
     }
-    ERP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+    ERP_CUDA(record_timing(ctx, ctx->ev_k1));
 
     ERP_TRY(refine_launch(ctx, d_q, nq, d_t, nt, dim, n_lists, TOPK, KAPPA, cand, cand_s, cand_thr, reinterpret_cast<unsigned*>(misc),
                           d_idx2, d_dist2, d_d2, list));
