@@ -64,6 +64,8 @@ _SIGNATURES = {
                                  C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "erp_knn2_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int,
                                C.c_void_p, C.c_void_p]),
+    "erp_knn2_near_ties": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_float,
+                                     C.c_void_p, C.POINTER(C.c_int)]),
     "erp_knn2_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "erp_nn1_reverse_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "erp_match_filter_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -285,6 +287,18 @@ class Context:
         _check(lib().erp_knn2_raw(self._h, _ptr(q), q.shape[0], 4 * q.shape[1], _ptr(t), t.shape[0], 4 * t.shape[1],
                                   q.shape[1], _ptr(idx), _ptr(dist)))
         return idx, dist
+
+    def knn2_near_ties(self, q, t, rel_tol: float = 1e-6) -> np.ndarray:
+        """Per-query flags of erp_knn2_near_ties: bit 0 order of the two nearest, bit 1 identity of the second."""
+        q, t = _f32(q), _f32(t)
+        flags = np.zeros(max(q.shape[0], 1), np.uint8)
+        n = C.c_int(0)
+        _check(lib().erp_knn2_near_ties(self._h, _ptr(q), q.shape[0], q.strides[0] if q.shape[0] else 4 * q.shape[1],
+                                        _ptr(t), t.shape[0], t.strides[0] if t.shape[0] else 4 * t.shape[1], q.shape[1],
+                                        rel_tol, _ptr(flags), C.byref(n)))
+        flags = flags[: q.shape[0]]
+        assert int((flags != 0).sum()) == n.value
+        return flags
 
     # ---- matching (device buffers: torch tensors or raw pointers)
     def knn2_dev(self, d_q, nq, d_t, nt, dim, d_idx2, d_dist2, d_d2=None):

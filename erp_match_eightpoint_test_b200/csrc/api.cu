@@ -426,6 +426,41 @@ ERP_API int erp_knn2_raw(erp_ctx* ctx, const float* q, int nq, size_t q_stride_b
     return ERP_OK;
 }
 
+ERP_API int erp_knn2_near_ties(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
+                               const float* t, int nt, size_t t_stride_bytes, int dim, float rel_tol,
+                               uint8_t* flags, int* n_flagged)
+{
+    ERP_TRY(check_knn_args("erp_knn2_near_ties", ctx, nq, nt, dim));
+    ERP_ARG(n_flagged && rel_tol >= 0.f, ERP_E_ARG, "erp_knn2_near_ties: bad argument");
+    *n_flagged = 0;
+    if (nq == 0) return ERP_OK;
+    ERP_ARG(flags, ERP_E_ARG, "erp_knn2_near_ties: flags is null");
+    DeviceGuard g(ctx->device);
+    int st = ERP_OK;
+    int32_t* d_idx = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
+    float* d_dist = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
+    double* d_d2 = ctx->scratch<double>(S_D2, (size_t)nq * 2 + 2, &st);
+    int32_t* d_third = ctx->scratch<int32_t>(S_COUNTS, (size_t)nq + 1, &st);
+    uint8_t* d_flags = ctx->scratch<uint8_t>(S_MASK, (size_t)nq + 4, &st);
+    ERP_TRY(st);
+    // the engine's own exact 2-NN (indices + fp64 squared distances), then one exact counting pass
+    size_t row = (size_t)dim * sizeof(float);
+    ERP_ARG(q && t && q_stride_bytes >= row && t_stride_bytes >= row, ERP_E_ARG, "erp_knn2_near_ties: bad descriptor buffers");
+    float* dq = ctx->scratch<float>(S_Q, (size_t)nq * dim + 4, &st);
+    float* dt = ctx->scratch<float>(S_T, (size_t)nt * dim + 4, &st);
+    ERP_TRY(st);
+    ERP_TRY(upload_rows(ctx, dt, t, nt, row, t_stride_bytes));
+    ERP_TRY(upload_rows(ctx, dq, q, nq, row, q_stride_bytes));
+    ERP_TRY(erp_knn2_dev(ctx, dq, nq, dt, nt, dim, d_idx, d_dist, d_d2));
+    ERP_TRY(near_ties(ctx, dq, nq, dt, nt, dim, d_idx, d_d2, (double)rel_tol, d_third, d_flags));
+    int32_t n = 0;
+    ERP_CUDA(cudaMemcpyAsync(flags, d_flags, (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaMemcpyAsync(&n, d_third + nq, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_flagged = n;
+    return ERP_OK;
+}
+
 // ======================================================================================
 // geometry, host-pointer forms
 // ======================================================================================

@@ -222,6 +222,124 @@ int knn2_exact_rescan(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, 
 }
 
 // ---------------------------------------------------------------------------------------
+// near-tie report (diagnostic, not on the hot path).  The library's 2-NN is exact; an fp32 implementation of the
+// reference's matcher (cv::BFMatcher / FLANN compare fp32 distances, src/feature_matcher.cpp:45,52) may legitimately
+// return another index where two distances differ by less than its rounding error.  flags[q]:
+//   bit 0: |d1 - d0| <= rel_tol * d1                (the ORDER of the two nearest may differ)
+//   bit 1: some third train row has d <= d1 (1 + rel_tol)   (the second INDEX may differ)
+// d = exact L2 distance (fp64 chain of the engine).  Same tiling as knn2_exact_kernel: 64 queries x 64 train rows.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+near_tie_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int dim,
+                const int32_t* __restrict__ idx2, const double* __restrict__ d2, double rel_tol, int32_t* __restrict__ third_count)
+{
+    __shared__ __align__(16) double Qs[KC][PITCH];
+    __shared__ __align__(16) double Ts[KC][PITCH];
+    __shared__ int cnt[QT];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int q0 = blockIdx.x * QT;
+    const int per = ((nt + (int)gridDim.y - 1) / (int)gridDim.y + TT - 1) / TT * TT;
+    const int t_begin = min(nt, (int)blockIdx.y * per), t_end = min(nt, t_begin + per);
+    if (tid < QT) cnt[tid] = 0;
+    double lim[4];
+    int i0[4], i1[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int qr = q0 + ty * 4 + i;
+        lim[i] = -1.0; i0[i] = i1[i] = -1;
+        if (qr < nq && idx2[2 * qr + 1] >= 0) {
+            const double f = 1.0 + rel_tol;
+            lim[i] = d2[2 * qr + 1] * f * f;
+            i0[i] = idx2[2 * qr]; i1[i] = idx2[2 * qr + 1];
+        }
+    }
+    int mine[4] = {0, 0, 0, 0};
+    for (int t0 = t_begin; t0 < t_end; t0 += TT) {
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+        for (int kc = 0; kc < dim; kc += KC) {
+            __syncthreads();
+            for (int v = tid; v < QT * (KC / 4); v += 256) {
+                int row = v >> 3, c4 = v & 7, k = kc + c4 * 4;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                int qr = q0 + row;
+                if (qr < nq && k < dim) a = *reinterpret_cast<const float4*>(q + (size_t)qr * dim + k);
+                int tr = t0 + row;
+                if (tr < t_end && k < dim) b = *reinterpret_cast<const float4*>(t + (size_t)tr * dim + k);
+                Qs[c4 * 4 + 0][row] = (double)a.x; Qs[c4 * 4 + 1][row] = (double)a.y;
+                Qs[c4 * 4 + 2][row] = (double)a.z; Qs[c4 * 4 + 3][row] = (double)a.w;
+                Ts[c4 * 4 + 0][row] = (double)b.x; Ts[c4 * 4 + 1][row] = (double)b.y;
+                Ts[c4 * 4 + 2][row] = (double)b.z; Ts[c4 * 4 + 3][row] = (double)b.w;
+            }
+            __syncthreads();
+            const int klim = min(KC, dim - kc);
+#pragma unroll 4
+            for (int k = 0; k < klim; k++) {
+                double2 qa = *reinterpret_cast<const double2*>(&Qs[k][ty * 4]);
+                double2 qb = *reinterpret_cast<const double2*>(&Qs[k][ty * 4 + 2]);
+                double2 ta = *reinterpret_cast<const double2*>(&Ts[k][tx * 4]);
+                double2 tb = *reinterpret_cast<const double2*>(&Ts[k][tx * 4 + 2]);
+                double qv[4] = {qa.x, qa.y, qb.x, qb.y};
+                double tv[4] = {ta.x, ta.y, tb.x, tb.y};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        double diff = __dsub_rn(qv[i], tv[j]);
+                        acc[i][j] = __fma_rn(diff, diff, acc[i][j]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int tr = t0 + tx * 4 + j;
+            if (tr < t_end) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) mine[i] += (acc[i][j] <= lim[i] && tr != i0[i] && tr != i1[i]) ? 1 : 0;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (mine[i]) atomicAdd(&cnt[ty * 4 + i], mine[i]);
+    __syncthreads();
+    if (tid < QT && q0 + tid < nq && cnt[tid]) atomicAdd(&third_count[q0 + tid], cnt[tid]);
+}
+
+__global__ void near_tie_flags_kernel(const int32_t* __restrict__ idx2, const double* __restrict__ d2, const int32_t* __restrict__ third_count,
+                                      int nq, double rel_tol, uint8_t* __restrict__ flags, int32_t* __restrict__ n_flagged)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t f = 0;
+    if (i < nq && idx2[2 * i + 1] >= 0) {
+        const double a = sqrt(d2[2 * i]), b = sqrt(d2[2 * i + 1]);
+        if (b - a <= rel_tol * b) f |= 1;
+        if (third_count[i] > 0) f |= 2;
+    }
+    if (i < nq) flags[i] = f;
+    const int n = __reduce_add_sync(0xffffffffu, f ? 1 : 0);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(n_flagged, n);
+}
+
+int near_ties(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, const int32_t* d_idx2, const double* d_d2,
+              double rel_tol, int32_t* d_third /* nq + 1 */, uint8_t* d_flags)
+{
+    ERP_CUDA(cudaMemsetAsync(d_third, 0, sizeof(int32_t) * ((size_t)nq + 1), ctx->stream));
+    // few query blocks: split the train rows so that the machine is full
+    const int qb = cdiv(nq, QT);
+    int slices = 1;
+    if (qb < ctx->sm_count * 2) slices = max(1, min(cdiv(nt, TT), (ctx->sm_count * 2) / qb));
+    near_tie_kernel<<<dim3(qb, slices), 256, 0, ctx->stream>>>(d_q, nq, d_t, nt, dim, d_idx2, d_d2, rel_tol, d_third);
+    ERP_LAUNCH(ctx, "near_tie_kernel");
+    near_tie_flags_kernel<<<cdiv(nq, 256), 256, 0, ctx->stream>>>(d_idx2, d_d2, d_third, nq, rel_tol, d_flags, d_third + nq);
+    ERP_LAUNCH(ctx, "near_tie_flags_kernel");
+    return ERP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // ratio test + cross-check + compaction in ascending queryIdx (feature_matcher.cpp:50-56)
 // ---------------------------------------------------------------------------------------
 constexpr int FB = 1024;  // queries per filter block

@@ -125,6 +125,16 @@ int erp_knn2_raw(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
                  const float* t, int nt, size_t t_stride_bytes, int dim,
                  int32_t* idx2, float* dist2);
 
+/* Near-tie report (diagnostic; north_star: "bit-exact except for documented fp32 distance ties within 1e-6 relative").
+ * The 2-NN above is exact (fp64 distances); the reference compares fp32 distances (src/feature_matcher.cpp:45,52), so
+ * an fp32 matcher may legitimately return another index where two distances are closer than its rounding error.
+ * flags[i] for query i: bit 0 = the two nearest are within rel_tol of each other (|d1 - d0| <= rel_tol * d1: their
+ * ORDER may differ), bit 1 = a third train row is within rel_tol of the second (d <= d1 (1 + rel_tol): the second
+ * INDEX may differ).  Exact fp64 brute force over all pairs; flags: nq bytes, *n_flagged = how many are non-zero. */
+int erp_knn2_near_ties(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,
+                       const float* t, int nt, size_t t_stride_bytes, int dim, float rel_tol,
+                       uint8_t* flags, int* n_flagged);
+
 /* device-resident forms (dense rows: stride == dim * 4) */
 int erp_knn2_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim,
                  int32_t* d_idx2, float* d_dist2, double* d_d2 /* nq x 2 or NULL */);

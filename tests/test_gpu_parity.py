@@ -533,6 +533,75 @@ def test_cfg3_full_size_tensor_core_equals_exact_engine(ctx):
     a = ctx.ransac(l, r, seed=1, hyp_offset=0, H=400000)
     b = ctx.ransac(l, r, seed=1, hyp_offset=400000, H=600000)
     assert max(a["packed"], b["packed"]) == res["packed"]
+    # the same million hypotheses scored one by one with the fp32 chain (SIMT engine, 5e10 residuals): same packed winner,
+    # same mask -- the tensor-core search with exact pruning is checked at FULL size, not only through properties
+    ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+    full = ctx.ransac(l, r, seed=1, hyp_offset=0, H=1000000)
+    ctx.set_engine(binding.ENGINE_AUTO)
+    assert full["packed"] == res["packed"] and np.array_equal(full["mask"], res["mask"])
+    assert np.array_equal(full["E_refit"], res["E_refit"])
+
+
+def test_cfg2_full_size_against_cv2_bfmatcher_with_near_tie_report(ctx):
+    """configs[1] at full size against the third-party matcher itself: cv2.BFMatcher(NORM_L2).knnMatch(k=2) computes
+    and compares in fp32 (as src/feature_matcher.cpp:45,52 does); the device result is exact.  north_star: indices
+    bit-exact except for documented fp32 distance ties.  Every query on which cv2 returns another index must be in the
+    near-tie report (erp_knn2_near_ties); the report itself is checked against its definition on a sub-sample."""
+    cv2 = pytest.importorskip("cv2")
+    q, t, planted = synth.descriptor_pair(20000, 20000, 64, seed=synth.SEED_BASE + 1)
+    t[137] = t[12]; t[5] = t[12]; q[3] = t[12]                          # exact ties: lowest trainIdx first, on both sides
+    kn = cv2.BFMatcher(cv2.NORM_L2).knnMatch(q, t, k=2)
+    cidx = np.array([[m[0].trainIdx, m[1].trainIdx] for m in kn], np.int32)
+    cdist = np.array([[m[0].distance, m[1].distance] for m in kn], np.float32)
+    idx, dist = ctx.knn2_raw(q, t)
+    # fp32 accumulation of 64 terms: documented tolerance of the report = 64 * 2^-24 relative on the distance
+    tol = 64 * 2.0 ** -24
+    flags = ctx.knn2_near_ties(q, t, tol)
+    bad = np.nonzero((idx != cidx).any(1))[0]
+    print("cfg2 vs cv2.BFMatcher: %d of %d queries differ, %d flagged as near ties at rel_tol %.1e (%d at 1e-6)" %
+          (len(bad), len(q), (flags != 0).sum(), tol, (ctx.knn2_near_ties(q, t, 1e-6) != 0).sum()))
+    assert (flags[bad] != 0).all(), bad[flags[bad] == 0][:10]
+    assert len(bad) <= 20
+    ok = np.setdiff1d(np.arange(len(q)), bad)
+    assert np.abs(dist[ok].astype(np.float64) - cdist[ok]).max() <= 4e-6 * dist.max()      # cv2's distances are fp32 sums
+    # the report is what its definition says (numpy fp64, 256 queries incl. the planted ties)
+    sub = np.concatenate([np.arange(0, 20000, 80), bad[:6]]).astype(np.int64)
+    q64, t64 = q[sub].astype(np.float64), t.astype(np.float64)
+    for j, i in enumerate(sub):
+        d = np.sqrt(((t64 - q64[j]) ** 2).sum(1))
+        d0, d1 = d[idx[i, 0]], d[idx[i, 1]]
+        others = np.ones(len(t), bool)
+        others[idx[i]] = False
+        want = (1 if d1 - d0 <= tol * d1 else 0) | (2 if (d[others] <= d1 * (1 + tol)).any() else 0)
+        assert flags[i] == want, (i, flags[i], want)
+    assert flags[3] & 1 or flags[3] & 2                                                     # the planted triple tie is reported
+
+
+def test_one_product_engine_worst_case_rounding(ctx):
+    """Adversarial input for the 1xTF32 certificate (kappa = 1.05 * 2^-10): every component of every descriptor sits just
+    below a tf32 rounding midpoint (v0 + 2^-11 - 2^-18 with v0 a tf32 value close to 1), all positive and of nearly equal
+    norm, so BOTH operands of every product round down by almost 2^-11 and no error cancels; half of the queries are
+    exact copies of train rows (q.t = |t|^2).  The observed deviation approaches 2^-10 (|q|^2 + max|t|^2); the result
+    must still equal the fp64 engine bit for bit, with or without re-scans."""
+    rng = np.random.default_rng(7)
+    nq, nt = 3000, 5000
+    for dim in (64, 128):
+        def adversarial(n):
+            # tf32 values 1 + m / 1024 with small m, plus just under half a tf32 ulp: cvt.rna rounds DOWN by ~2^-11 relative
+            m = rng.integers(0, 64, size=(n, dim)).astype(np.float64)
+            return np.ascontiguousarray((1.0 + m / 1024.0 + 2.0 ** -11 - 2.0 ** -18).astype(np.float32))
+        t = adversarial(nt)
+        q = adversarial(nq)
+        q[: nq // 2] = t[rng.permutation(nt)[: nq // 2]]                 # exact copies: q.t = |t|^2, the error term is maximal
+        ctx.set_engine(binding.ENGINE_EXACT_SIMT)
+        eidx, edist = ctx.knn2_raw(q, t)
+        ctx.set_engine(binding.ENGINE_TCGEN05_1X)
+        idx, dist = ctx.knn2_raw(q, t)
+        st = ctx.last_knn_stats()
+        ctx.set_engine(binding.ENGINE_AUTO)
+        assert np.array_equal(idx, eidx) and np.array_equal(dist.view(np.uint32), edist.view(np.uint32))
+        print("worst-case rounding, D=%d: deviation %.3e = %.3f of 2^-10, %d re-scanned" % (dim, st["deviation"], st["deviation"] * 1024, st["rescanned"]))
+        assert 0.8 * 2.0 ** -10 < st["deviation"] <= 1.05 * 2.0 ** -10, st
 
 
 def test_cfg4_full_size_surf128_cross_check_properties(ctx):
