@@ -443,6 +443,17 @@ def run_pair(args, cfg, rig):
             t_e2e_match += b - a
             t_pair += c - b
     assert len(pm) == m and pres["packed"] == res["packed"], "host-buffer call disagrees with the device-resident call"
+    # the same match call on PAGEABLE buffers (what a cv::Mat is): staged through pinned chunks by the library
+    t_pageable = 0.0
+    if not strong:
+        gq, gt = np.array(pq), np.array(pt)
+        for it in range(4):
+            torch.cuda.synchronize()
+            a = time.perf_counter()
+            gm = ctx.knn2_match(gq, gt, RATIO, False)
+            if it > 0:
+                t_pageable += (time.perf_counter() - a) / 3
+        assert gm.tobytes() == mt.tobytes()
     t_e2e_match, t_pair = rig.max_over_ranks([t_e2e_match, t_pair])
     share = 1.0 / world if strong else 1.0
     h2d = int(pq.nbytes * share + pt.nbytes * share)
@@ -531,6 +542,7 @@ def run_pair(args, cfg, rig):
         "roofline": roof, "roofline_3xtf32": alt3, "roofline_scoring": score_roof,
         "e2e": {"value": units * args.steps / t_e2e_match, "unit": "dist-evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "match_ms": 1e3 * t_e2e_match / args.steps, "steps": args.steps,
+                "match_ms_pageable_source": 1e3 * t_pageable if t_pageable > 0 else None,
                 "api": "erp_knn2_match_dist (host buffers, per rank: its query rows + 1/N of the train rows up, NVLink all-gather)" if strong
                        else "erp_knn2_match (host buffers)",
                 "pair": {"ms": 1e3 * t_pair / args.steps, "dist_evals_per_s": units * args.steps / t_pair,

@@ -65,14 +65,14 @@ enum ScratchId {
 
 } // namespace erp
 
-namespace erp { struct Comm; struct GraphCache; }
+namespace erp { struct Comm; struct GraphCache; struct StagePool; }
 
 struct erp_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;             // host-buffer calls upload query chunks here while the previous chunk computes
-    cudaEvent_t ev_copy[8] = {};                    // "chunk c is on the device" (+ one fork event)
+    cudaEvent_t ev_copy[10] = {};                   // "chunk c is on the device" (0..6), fork events (7: chunked upload, 8: staged upload)
     int tc_chunk = 0;                               // > 0: later query chunk of one host call: train operand and statistics carry over
     int engine = ERP_ENGINE_AUTO;
     uint64_t launches = 0;
@@ -87,6 +87,7 @@ struct erp_ctx {
     bool capturing = false;
     uint64_t scratch_gen = 0;
     erp::GraphCache* graph = nullptr;
+    erp::StagePool* stage = nullptr;                // pinned staging of pageable host buffers (api.cu: upload_rows)
     std::vector<cudaEvent_t> ev_score;              // pairs around the scoring kernel launches of the last RANSAC call
     int n_ev_score = 0;                             // events used by that call
     erp::Buf dev[erp::S_COUNT_];
@@ -233,6 +234,8 @@ int pose_chain_tail(erp_ctx* ctx, const double* dl, const double* dr, const floa
 // touching the host again.  The first call with a key runs directly, the second is captured, the rest replay.
 int graph_run(erp_ctx* ctx, const void* key, size_t key_bytes, const std::function<int()>& body);
 void graph_release(erp_ctx* ctx);
+int upload_rows(erp_ctx* ctx, void* d_dst, const void* src, int rows, size_t row_bytes, size_t stride);
+void stage_release(erp_ctx* ctx);
 // multi-GPU (dist.cu)
 int comm_allreduce_best(erp_ctx* ctx, uint64_t* d_packed);
 void comm_release(erp_ctx* ctx);

@@ -291,29 +291,16 @@ static int upload_sharded(erp_ctx* ctx, const float* q, int lo, int hi, size_t q
     float* dq = ctx->scratch<float>(S_Q, (size_t)(hi - lo) * dim + 4, &st);
     float* dt = ctx->scratch<float>(S_T, (size_t)tcap * G * dim + 4, &st);
     ERP_TRY(st);
-    if (hi > lo) {
-        if (qs == row) ERP_CUDA(cudaMemcpyAsync(dq, reinterpret_cast<const char*>(q) + (size_t)lo * qs, row * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
-        else ERP_CUDA(cudaMemcpy2DAsync(dq, row, reinterpret_cast<const char*>(q) + (size_t)lo * qs, qs, row, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    ERP_TRY(upload_rows(ctx, dq, reinterpret_cast<const char*>(q) + (size_t)lo * qs, hi - lo, row, qs));
     const int t0 = rank * tcap < nt ? rank * tcap : nt, t1 = (rank + 1) * tcap < nt ? (rank + 1) * tcap : nt;
-    if (t1 > t0) {
-        float* dst = dt + (size_t)t0 * dim;
-        if (ts == row) ERP_CUDA(cudaMemcpyAsync(dst, reinterpret_cast<const char*>(t) + (size_t)t0 * ts, row * (t1 - t0), cudaMemcpyHostToDevice, ctx->stream));
-        else ERP_CUDA(cudaMemcpy2DAsync(dst, row, reinterpret_cast<const char*>(t) + (size_t)t0 * ts, ts, row, t1 - t0, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    ERP_TRY(upload_rows(ctx, dt + (size_t)t0 * dim, reinterpret_cast<const char*>(t) + (size_t)t0 * ts, t1 - t0, row, ts));
     if (G > 1)
         ERP_NCCL(nccl().AllGather(dt + (size_t)rank * tcap * dim, dt, (size_t)tcap * dim, ncclFloat, ctx->comm->comm, ctx->stream));
     *dq_out = dq; *dt_out = dt;
     return ERP_OK;
 }
 
-static int upload_xy(erp_ctx* ctx, float* d_dst, const void* src, int rows, size_t stride)
-{
-    if (rows == 0) return ERP_OK;
-    if (stride == 8) ERP_CUDA(cudaMemcpyAsync(d_dst, src, (size_t)8 * rows, cudaMemcpyHostToDevice, ctx->stream));
-    else ERP_CUDA(cudaMemcpy2DAsync(d_dst, 8, src, stride, 8, rows, cudaMemcpyHostToDevice, ctx->stream));
-    return ERP_OK;
-}
+static int upload_xy(erp_ctx* ctx, float* d_dst, const void* src, int rows, size_t stride) { return upload_rows(ctx, d_dst, src, rows, 8, stride); }
 
 } // namespace erp
 

@@ -21,8 +21,9 @@ void eight_point::find(int im_width, int im_height
                        , int match_size)
 {
     if (match_size > (int)key_left.size() || match_size > (int)key_right.size())
-        throw cv::Exception("eight_point::find: match_size exceeds the keypoint vectors");
+        CV_Error(cv::Error::StsBadArg, "eight_point::find: match_size exceeds the keypoint vectors");
     // KeyPoint.pt is the first member: stride sizeof(KeyPoint)
+    erp_host::Lock lock;
     erp_host::check(erp_find(erp_host::context(), im_width, im_height, key_left.data(), key_right.data(), sizeof(KeyPoint),
                              match_size, nullptr, 0, 0, R_vec_out.val, T_vec_out.val), "eight_point::find");
 }
@@ -35,6 +36,7 @@ void eight_point::eight_point_estimation(int im_width, int im_height
 {
     (void)im_width; (void)im_height;     // unused by the reference as well
     int v1 = 0, v2 = 0;
+    erp_host::Lock lock;
     erp_host::check(erp_eight_point_estimation(erp_host::context(), &key_point_left_rect[0].x, &key_point_right_rect[0].x, match_size,
                                                nullptr, R1_vec.val, R2_vec.val, T_vec.val, &v1, &v2), "eight_point::eight_point_estimation");
     R1_valid = v1 != 0;
@@ -48,6 +50,7 @@ void eight_point::initial_guess(int im_width, int im_height
 {
     (void)im_width; (void)im_height;
     const int H = 80, S = (int)(match_size * 0.25);      // src/eight_point.cpp:99,102
+    erp_host::Lock lock;
     erp_host::check(erp_initial_guess(erp_host::context(), &key_point_left_rect[0].x, &key_point_right_rect[0].x, match_size,
                                       nullptr, H, S, R_vec_out.val, T_vec_out.val, nullptr, nullptr, nullptr, nullptr),
                     "eight_point::initial_guess");
@@ -58,6 +61,7 @@ int eight_point::ransac(vector<Point3d>& l, vector<Point3d>& r, int match_size, 
 {
     erp_ransac_result res;
     if (inlier_mask) inlier_mask->resize(match_size);
+    erp_host::Lock lock;
     erp_host::check(erp_ransac(erp_host::context(), &l[0].x, &r[0].x, match_size, seed, 0, hypotheses, 8, ERP_METRIC_ALGEBRAIC,
                                0.002f, &res, inlier_mask ? inlier_mask->data() : nullptr), "eight_point::ransac");
     for (int i = 0; i < 9; i++) E_out[i] = res.E_refit[i];
@@ -71,6 +75,7 @@ int eight_point::ransac(int im_width, int im_height, vector<KeyPoint>& kl, vecto
 {
     erp_ransac_result res;
     if (inlier_mask) inlier_mask->resize(match_size);
+    erp_host::Lock lock;
     erp_host::check(erp_ransac_pixels(erp_host::context(), im_width, im_height, &kl[0].pt, &kr[0].pt, sizeof(KeyPoint), match_size,
                                       seed, 0, hypotheses, 8, ERP_METRIC_ALGEBRAIC, 0.002f, &res,
                                       inlier_mask ? inlier_mask->data() : nullptr), "eight_point::ransac");

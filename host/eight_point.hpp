@@ -12,6 +12,8 @@
 #include "debug_print.h"
 #include "erp_rotation.hpp"
 #include <opencv2/opencv.hpp>
+#include <algorithm>
+#include <numeric>      // the reference header pulls it in (src/eight_point.hpp:6): callers may lean on it
 #include <vector>
 
 class eight_point

@@ -27,25 +27,39 @@ cv::Vec3d erp_rotation::rot2eular(cv::Mat R)
 
 static void mat9(const cv::Mat& R, double* m)
 {
-    if (R.rows != 3 || R.cols != 3 || R.type() != CV_64FC1) throw cv::Exception("erp_rotation: rotation matrix must be 3x3 CV_64F");
+    if (R.rows != 3 || R.cols != 3 || R.type() != CV_64FC1) CV_Error(cv::Error::StsBadArg, "erp_rotation: rotation matrix must be 3x3 CV_64F");
     for (int i = 0; i < 9; i++) m[i] = R.at<double>(i / 3, i % 3);
 }
 
+// One pixel is fifteen lines of trigonometry: it stays on the host (the reference's callers invoke it per pixel from
+// OpenMP loops, src/spherical_surf.cpp:27-45,53-62 -- a device round trip each would be absurd).  Same operation order
+// as src/erp_rotation.cpp:66-92 and as rotate_pixels_kernel / the oracle, so the integer results agree:
+//   (row, col) -> colatitude, longitude -> bearing (OMAF axes: -sin cos, sin sin, cos) -> R * bearing -> back, truncated.
+// Whole images go through rotate_image (device).
 cv::Vec2i erp_rotation::rotate_pixel(const cv::Vec2i& in_vec, cv::Mat& rot_mat, int width, int height)
 {
     double m[9];
     mat9(rot_mat, m);
-    int in[2] = {in_vec[0], in_vec[1]}, out[2] = {0, 0};
-    erp_host::check(erp_rotate_pixels(erp_host::context(), in, 1, m, width, height, out), "erp_rotation::rotate_pixel");
-    return cv::Vec2i(out[0], out[1]);
+    const double colat = M_PI * in_vec[0] / height, lon = 2 * M_PI * in_vec[1] / width;
+    const double b[3] = {-std::sin(colat) * std::cos(lon), std::sin(colat) * std::sin(lon), std::cos(colat)};
+    double r[3];
+    for (int i = 0; i < 3; i++) r[i] = m[3 * i] * b[0] + m[3 * i + 1] * b[1] + m[3 * i + 2] * b[2];
+    const double colat_r = std::acos(r[2]);
+    double lon_r = std::atan2(r[1], -r[0]);
+    if (lon_r < 0) lon_r += M_PI * 2;
+    cv::Vec2i px;
+    px[0] = (int)(height * colat_r / M_PI);
+    px[1] = (int)(width * lon_r / (2 * M_PI));
+    return px;
 }
 
 cv::Mat erp_rotation::rotate_image(const cv::Mat& im, cv::Mat& rot_mat)
 {
-    if (im.type() != CV_8UC3) throw cv::Exception("erp_rotation::rotate_image: CV_8UC3 image expected");
+    if (im.type() != CV_8UC3) CV_Error(cv::Error::StsBadArg, "erp_rotation::rotate_image: CV_8UC3 image expected");
     double m[9];
     mat9(rot_mat, m);
     cv::Mat out(im.rows, im.cols, im.type());
+    erp_host::Lock lock;
     erp_host::check(erp_rotate_image(erp_host::context(), im.data, im.cols, im.rows, im.step, m, out.data, out.step),
                     "erp_rotation::rotate_image");
     return out;

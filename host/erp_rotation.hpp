@@ -1,8 +1,8 @@
 // erp_rotation.hpp -- drop-in for the reference's src/erp_rotation.hpp:9-19 (same class, same four members).
 //
 //   eular2rot, rot2eular    host arithmetic, src/erp_rotation.cpp:14-63
-//   rotate_pixel            src/erp_rotation.cpp:66-92   -> erp_rotate_pixels (one pixel per call = one device round
-//                           trip: loops over pixels should use the batched C entry point instead)
+//   rotate_pixel            src/erp_rotation.cpp:66-92   host arithmetic as well: the callers invoke it per pixel from
+//                           OpenMP loops; thread safe, no CUDA (batches: erp_rotate_pixels / erp_crop_rotated_image)
 //   rotate_image            src/erp_rotation.cpp:94-122  -> erp_rotate_image (inverse-mapped nearest-neighbour warp)
 #pragma once
 #include <cmath>

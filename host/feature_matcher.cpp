@@ -34,7 +34,7 @@ vector<KeyPoint> feature_matcher::detect_key_point(const Mat &image)
     return key_point;
 #else
     (void)image;
-    throw cv::Exception("feature_matcher::detect_key_point needs OpenCV xfeatures2d (SURF); this build uses the type shim");
+    CV_Error(cv::Error::StsNotImplemented, "feature_matcher::detect_key_point needs OpenCV xfeatures2d (SURF); this build uses the type shim");
 #endif
 }
 
@@ -46,7 +46,7 @@ Mat feature_matcher::comput_descriptor(const Mat &image, vector<KeyPoint> &key_p
     return d;
 #else
     (void)image; (void)key_point;
-    throw cv::Exception("feature_matcher::comput_descriptor needs OpenCV xfeatures2d (SURF); this build uses the type shim");
+    CV_Error(cv::Error::StsNotImplemented, "feature_matcher::comput_descriptor needs OpenCV xfeatures2d (SURF); this build uses the type shim");
 #endif
 }
 
@@ -55,34 +55,59 @@ Mat feature_matcher::comput_descriptor(const Mat &image, vector<KeyPoint> &key_p
 vector<DMatch> feature_matcher::match_two_image(const Mat &descriptor1, const Mat &descriptor2)
 {
     if (descriptor1.type() != CV_32FC1 || descriptor2.type() != CV_32FC1)
-        throw cv::Exception("match_two_image: descriptors must be CV_32F single channel");
+        CV_Error(cv::Error::StsBadArg, "match_two_image: descriptors must be CV_32F single channel");
     if (descriptor1.rows > 0 && descriptor1.cols != descriptor2.cols)
-        throw cv::Exception("match_two_image: descriptor dimensions differ");
+        CV_Error(cv::Error::StsBadArg, "match_two_image: descriptor dimensions differ");
     vector<DMatch> good(descriptor1.rows > 0 ? descriptor1.rows : 0);
     int n = 0;
     static_assert(sizeof(DMatch) == sizeof(erp_dmatch), "cv::DMatch and erp_dmatch must share a layout");
-    int st = erp_knn2_match(erp_host::context(),
-                            descriptor1.ptr<float>(0), descriptor1.rows, descriptor1.step,
-                            descriptor2.ptr<float>(0), descriptor2.rows, descriptor2.step,
-                            descriptor1.cols, ratio_thresh, cross_check ? 1 : 0,
-                            reinterpret_cast<erp_dmatch*>(good.data()), &n);
+    int st;
+    {
+        erp_host::Lock lock;
+        if (erp_group* grp = erp_host::group())      // $ERP_B200_DEVICES: query rows per GPU, train set all-gathered over NVLink
+            st = erp_group_knn2_match(grp, descriptor1.ptr<float>(0), descriptor1.rows, descriptor1.step,
+                                      descriptor2.ptr<float>(0), descriptor2.rows, descriptor2.step,
+                                      descriptor1.cols, ratio_thresh, cross_check ? 1 : 0,
+                                      reinterpret_cast<erp_dmatch*>(good.data()), &n);
+        else
+            st = erp_knn2_match(erp_host::context(),
+                                descriptor1.ptr<float>(0), descriptor1.rows, descriptor1.step,
+                                descriptor2.ptr<float>(0), descriptor2.rows, descriptor2.step,
+                                descriptor1.cols, ratio_thresh, cross_check ? 1 : 0,
+                                reinterpret_cast<erp_dmatch*>(good.data()), &n);
+    }
     // the reference throws cv::Exception out of knnMatch on malformed input (e.g. < 2 train rows)
-    if (st != ERP_OK) throw cv::Exception(string("match_two_image: ") + erp_last_error());
+    if (st != ERP_OK) CV_Error(cv::Error::StsBadArg, string("match_two_image: ") + erp_last_error());
     good.resize(n);
-    last_matches_ = good;
     return good;
 }
 
+// The overlap picture of src/feature_matcher.cpp:61-84: left view in one channel, right view in another, and one
+// coloured segment per correspondence from its left to its right position (key_left[i] <-> key_right[i]: the callers
+// pass the GATHERED keypoints, src/spherical_surf.cpp:173).  Drawing needs OpenCV's imgproc: real builds only.
 Mat feature_matcher::draw_match(const Mat& im_left, const Mat& im_right, const vector<KeyPoint>& key_left, const vector<KeyPoint>& key_right)
 {
 #ifndef ERP_OPENCV_COMPAT
-    Mat out;
-    drawMatches(im_left, key_left, im_right, key_right, last_matches_, out, Scalar::all(-1), Scalar::all(-1), vector<char>(),
-                DrawMatchesFlags::NOT_DRAW_SINGLE_POINTS);
-    return out;
+    Mat gray_left, gray_right;
+    cvtColor(im_left, gray_left, COLOR_RGB2GRAY);
+    cvtColor(im_right, gray_right, COLOR_RGB2GRAY);
+    vector<Mat> planes;
+    planes.push_back(gray_left);
+    planes.push_back(gray_right);
+    planes.push_back(Mat::zeros(im_left.rows, im_left.cols, CV_8UC1));
+    Mat overlap;
+    merge(planes, overlap);
+    const size_t n = key_left.size() < key_right.size() ? key_left.size() : key_right.size();
+    for (size_t i = 0; i < n; i++) {
+        // hue ramp over the matches, as the reference colours them
+        Mat hsv(1, 1, CV_8UC3, Scalar(i * (180.0 / (double)n), 180, 150)), bgr;
+        cvtColor(hsv, bgr, COLOR_HSV2BGR);
+        line(overlap, key_left[i].pt, key_right[i].pt, Scalar(bgr.data[0], bgr.data[1], bgr.data[2]), 5);
+    }
+    return overlap;
 #else
     (void)im_left; (void)im_right; (void)key_left; (void)key_right;
-    throw cv::Exception("feature_matcher::draw_match needs OpenCV features2d; this build uses the type shim");
+    CV_Error(cv::Error::StsNotImplemented, "feature_matcher::draw_match needs OpenCV imgproc; this build uses the type shim");
 #endif
 }
 
@@ -97,5 +122,5 @@ void feature_matcher::do_all(const Mat &im_left, const Mat &im_right, vector<Key
     left_key.resize(m.size());
     right_key.resize(m.size());
     for (size_t i = 0; i < m.size(); i++) { left_key[i] = kl[m[i].queryIdx]; right_key[i] = kr[m[i].trainIdx]; }
-    match_output = draw_match(im_left, im_right, kl, kr);
+    match_output = draw_match(im_left, im_right, left_key, right_key);
 }

@@ -4,7 +4,7 @@
 //                     the B200: exact brute-force 2-NN instead of the approximate FLANN KD-tree
 //   detect_key_point, comput_descriptor, draw_match, do_all
 //                     SURF and drawing are not on the accelerated path: they forward to OpenCV (xfeatures2d) when the
-//                     build has it, and throw cv::Exception with the type shim of this image
+//                     build has it, and raise cv::Exception (CV_Error) with the type shim of this image
 //
 // Objects are default-constructible and cheap (the reference builds one per call, src/spherical_surf.cpp:96): the CUDA
 // context lives in a per-thread cache (erp_host_context.hpp), not in the object.
@@ -45,7 +45,7 @@ public:
     std::vector<cv::DMatch> match_two_image(const cv::Mat &descriptor1,
                                             const cv::Mat &descriptor2);
 
-    // side-by-side rendering of the last match result
+    // overlap picture: left / right view in two colour channels, one coloured segment per pair key_left[i] -> key_right[i]
     cv::Mat draw_match(const cv::Mat& im_left,
                        const cv::Mat& im_right,
                        const std::vector<cv::KeyPoint>& key_left,
@@ -73,5 +73,4 @@ private:
     cv::Ptr<cv::Feature2D> surf_describe_;
 #endif
     bool extended_ = false;
-    std::vector<cv::DMatch> last_matches_;   // what draw_match renders, as in the reference
 };

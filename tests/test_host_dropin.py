@@ -82,6 +82,82 @@ def test_extrinsic_log_format_and_round_trip(tmp_path):
     assert np.allclose(back[:3], r, rtol=1e-5) and np.allclose(back[3:], t, rtol=1e-5)      # six significant digits
 
 
+REFERENCE = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference checkout exists only in the build container")
+def test_reference_callers_compile_and_link_unchanged(tmp_path):
+    """north_star: "automatic.cpp and the test mains link against it unchanged".  The reference's own callers
+    (src/automatic.cpp, src/spherical_surf.cpp + .hpp: everything that is NOT replaced) are copied to a scratch
+    directory at test time -- next to the reference's headers they would include those instead of the drop-in's -- and
+    compiled + linked, unmodified, against host/*.hpp, liberp_host.a and liberp_b200.so (OpenCV: the type shim; the
+    only thing this image cannot provide is image codecs, so the binary is linked, not run on images)."""
+    _build()
+    import shutil
+    for f in ("automatic.cpp", "spherical_surf.cpp", "spherical_surf.hpp"):
+        shutil.copy(os.path.join(REFERENCE, f), tmp_path / f)
+    exe = tmp_path / "automatic.out"
+    cmd = ["g++", "-std=c++11", "-O1", "-fopenmp", "-w", f"-I{tmp_path}", f"-I{HOST}", f"-I{HOST}/compat", f"-I{ROOT}/include",
+           str(tmp_path / "automatic.cpp"), str(tmp_path / "spherical_surf.cpp"), os.path.join(HOST, "_build", "liberp_host.a"),
+           f"-L{ROOT}/erp_match_eightpoint_test_b200/lib", "-lerp_b200", f"-Wl,-rpath,{ROOT}/erp_match_eightpoint_test_b200/lib",
+           "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    # the classes the callers use resolve to the drop-in's objects
+    syms = subprocess.run(["nm", "-C", str(exe)], capture_output=True, text=True).stdout
+    for name in ("feature_matcher::match_two_image", "eight_point::find", "erp_rotation::rotate_pixel", "erp_rotation::rotate_image",
+                 "spherical_surf::do_all"):
+        assert name in syms, name
+    usage = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert usage.returncode == 0 and "usage:" in usage.stdout
+    # the other mains and manual.cpp need highgui (windows, mouse callbacks): GUI, out of scope; their use of the replaced
+    # classes is the same member set (checked by the symbol list of test_host_classes_build...)
+
+
+def test_rotate_pixel_loops_run_on_the_host(tmp_path):
+    """erp_rotation::rotate_pixel per pixel from an OpenMP loop (what spherical_surf::crop_rotated_image does,
+    src/spherical_surf.cpp:27-45) at the reference's image size: plain host arithmetic, no CUDA context (this test has
+    no GPU), same integers as the oracle, and the whole 5376 x 672 strip well under a second per core-second budget."""
+    _build()
+    exe = os.path.join(HOST, "_build", "strip_main")
+    W, H = 5376, 2688
+    for pitch in (45.0, -90.0):
+        out = tmp_path / "map.bin"
+        r = subprocess.run([exe, str(W), str(H), str(pitch), str(out)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        sec = float(r.stdout.split()[0])
+        got = np.fromfile(out, np.int32).reshape(-1, 2)
+        rows = H // 4
+        rc = np.stack(np.meshgrid(np.arange(H * 3 // 8, H * 3 // 8 + rows), np.arange(W), indexing="ij"), -1).reshape(-1, 2).astype(np.int32)
+        want = O.rotate_pixels(rc, O.eular2rot([0.0, float(np.float32(np.pi * pitch / 180.0)), 0.0]), W, H)     # Vec3f angle, as the callers pass it
+        assert np.array_equal(got, want)
+        threads = int(r.stdout.split()[-2])
+        assert sec * threads < 8.0, r.stdout          # ~0.1 us of trigonometry per pixel and thread; a device round trip would be ~20 us
+
+
+@pytest.mark.gpu
+def test_reference_strip_loop_equals_the_device_strip(tmp_path):
+    """The same host loop fills a strip from a real-sized image; erp_crop_rotated_image (device) picks the same pixels
+    up to the documented libm boundary cases (a mapped coordinate within an ulp of an integer: CUDA libm vs glibc; the
+    45-degree strips put many pixel centres on such boundaries, tests/test_gpu_image.py uses the same 2 % bar)."""
+    _build()
+    exe = os.path.join(HOST, "_build", "strip_main")
+    W, H = 5376, 2688
+    rng = np.random.default_rng(3)
+    im = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    img = tmp_path / "im.bin"
+    im.tofile(img)
+    r = subprocess.run([exe, str(W), str(H), "45", str(tmp_path / "map.bin"), str(img), str(tmp_path / "strip.bin")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    sec = float(r.stdout.split()[0])
+    assert sec < 1.0, r.stdout
+    differ = int(r.stdout.splitlines()[-1].split()[4])
+    assert differ <= 2e-2 * (H // 4) * W, r.stdout
+    strip = np.fromfile(tmp_path / "strip.bin", np.uint8).reshape(H // 4, W, 3)
+    assert np.array_equal(strip, O.crop_rotated_image(im, 45.0))
+
+
 @pytest.mark.gpu
 def test_dropin_driver_matches_oracle(tmp_path):
     _build()
