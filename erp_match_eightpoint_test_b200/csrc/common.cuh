@@ -59,7 +59,7 @@ enum ScratchId {
     S_TC_Q, S_TC_T, S_TC_QN, S_TC_TN, S_TC_CAND, S_TC_LIST, S_TC_MISC,
     S_RS_IDX, S_RS_DIST, S_RS_D2, S_RS_PARTIAL,
     S_SC_E, S_SC_E2, S_SC_K, S_SC_MISC, S_SC_BOUNDS, S_SC_LIST,
-    S_IMG_IN, S_IMG_OUT, S_RESULT, S_GATHER, S_XCHG,
+    S_IMG_IN, S_IMG_OUT, S_RESULT, S_GATHER, S_XCHG, S_TC_ROWTHR,
     S_COUNT_
 };
 

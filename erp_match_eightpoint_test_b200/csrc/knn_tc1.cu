@@ -139,7 +139,12 @@ struct Tc1Params {
     int32_t* cand_idx;        // nq x lists x F_TOPK, pre-set to -1
     float* cand_s;
     float* cand_thr;          // nq x lists: lower bound of the approximate score of every non-candidate
+    int32_t* row_thr;         // nq ordered-int keys (or null): the lowest threshold any segment of the row has published
 };
+
+// monotone float <-> int key (scores may be negative), so that atomicMin orders thresholds
+__device__ __forceinline__ int32_t thr_key(float f) { const int32_t k = __float_as_int(f); return k >= 0 ? k : k ^ 0x7fffffff; }
+__device__ __forceinline__ float key_thr(int32_t k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 template <int KCH>   // k chunks of 32 floats: dpad = 32 * KCH
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -321,15 +326,39 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             float floor_thr[F_SUB];
 #pragma unroll
             for (int sub = 0; sub < F_SUB; sub++) floor_thr[sub] = INFINITY;
+            // A query row cut into several segments is scanned by several CTAs at once, each starting cold.  Any threshold
+            // one of them has reached (second best so far + slack) bounds the row's exact two nearest for ALL of them, so
+            // the segments publish theirs (atomicMin on an ordered key) and fold the others' in every few tiles: the row
+            // then warms up once, not once per segment.  Racy on purpose: every published value is a valid bound, and
+            // floor_thr -- the lowest threshold ever in force -- is what the list's certificate bound is built from.
+            const bool seed = SHARE && p.row_thr != nullptr;
+            float published[F_SUB];
+#pragma unroll
+            for (int sub = 0; sub < F_SUB; sub++) published[sub] = INFINITY;
             if (SHARE) {
                 // every epilogue warp has left the previous query rows before their thresholds are replaced
                 asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
 #pragma unroll
-                for (int sub = 0; sub < F_SUB; sub++) thr_sh[sub * F_BM + row] = INFINITY;
+                for (int sub = 0; sub < F_SUB; sub++) {
+                    const int qrow = (qp * F_SUB + sub) * F_BM + row;
+                    float g = INFINITY;
+                    if (seed && qrow < p.nq) g = key_thr(*reinterpret_cast<volatile int32_t*>(p.row_thr + qrow));
+                    thr_sh[sub * F_BM + row] = g;
+                }
                 asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_THREADS) : "memory");
             }
             for (int tt = t0; tt < t1; tt++, tt_n++) {
                 const uint32_t nb = tt_n & 1;
+                // every fourth tile: fetch the row's published bound now, use it after this tile's scan
+                const bool sync_thr = seed && ((tt - t0) & 3) == 3;
+                int32_t fetched[F_SUB];
+                if (sync_thr) {
+#pragma unroll
+                    for (int sub = 0; sub < F_SUB; sub++) {
+                        const int qrow = (qp * F_SUB + sub) * F_BM + row;
+                        fetched[sub] = qrow < p.nq ? *reinterpret_cast<volatile int32_t*>(p.row_thr + qrow) : 0x7f7f7f7f;
+                    }
+                }
                 if (!FOLD) mbar_wait(&nfull[nb], (tt_n >> 1) & 1);
                 const float4* tn4 = reinterpret_cast<const float4*>(tn_smem + nb * F_BN + cg * F_EPI_COLS);
                 const int colbase = tt * F_BN + cg * F_EPI_COLS;
@@ -374,10 +403,23 @@ knn2_tc1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&nempty[nb]);
                 }
+                if (sync_thr) {
+#pragma unroll
+                    for (int sub = 0; sub < F_SUB; sub++) {
+                        const int qrow = (qp * F_SUB + sub) * F_BM + row;
+                        if (qrow >= p.nq) continue;
+                        const float mine = floor_thr[sub];
+                        if (mine < published[sub]) { atomicMin(p.row_thr + qrow, thr_key(mine)); published[sub] = mine; }
+                        const float g = key_thr(fetched[sub]);
+                        volatile float* rt = thr_sh + sub * F_BM + row;
+                        if (g < *rt) *rt = g;
+                    }
+                }
             }
 #pragma unroll
             for (int sub = 0; sub < F_SUB; sub++) {
                 const int qg = (qp * F_SUB + sub) * F_BM + row;
+                if (seed && qg < p.nq && floor_thr[sub] < published[sub]) atomicMin(p.row_thr + qg, thr_key(floor_thr[sub]));
                 if (qg < p.nq) {
                     const size_t l = ((size_t)qg * p.n_seg + seg) * F_EPI_GROUPS + cg;
 #pragma unroll
@@ -457,7 +499,12 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     float* qn = ctx->scratch<float>(S_TC_QN, (size_t)nq + 8, &st);
     int32_t* list = ctx->scratch<int32_t>(S_TC_LIST, (size_t)nq + 8, &st);
     int32_t* misc = ctx->scratch<int32_t>(S_TC_MISC, 8, &st);
+    // rows cut into segments exchange their thresholds (see the kernel): 12.5k x 100k (one rank of an 8-way split, 5 segments
+    // per row) 0.308 -> 0.260 ms, 25k x 100k 0.519 -> 0.474, 100k x 100k (2 segments) 1.759 -> 1.731
+    static const int seed_from = [] { const char* e = getenv("ERP_B200_SEED_SEGS"); return e ? atoi(e) : 2; }();     // experiments: 99 = never
+    int32_t* row_thr = n_seg >= seed_from ? ctx->scratch<int32_t>(S_TC_ROWTHR, (size_t)nq + 8, &st) : nullptr;
     ERP_TRY(st);
+    if (row_thr) ERP_CUDA(cudaMemsetAsync(row_thr, 0x7f, sizeof(int32_t) * (size_t)nq, ctx->stream));
     float* cand_s = reinterpret_cast<float*>(cand + (size_t)nq * n_lists * F_TOPK);
     float* cand_thr = cand_s + (size_t)nq * n_lists * F_TOPK;
     ERP_CUDA(cudaMemsetAsync(cand_thr, 0x7f, (size_t)nq * n_lists * sizeof(float), ctx->stream));              // ~3.4e38: "unbounded"
@@ -478,6 +525,7 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     p.nq = nq; p.nt = nt; p.n_qpairs = n_qpairs; p.n_ttiles = n_ttiles; p.units_per_cta = (int)L; p.n_seg = n_seg;
     p.tn = tn; p.cand_idx = cand; p.cand_s = cand_s; p.cand_thr = cand_thr; p.qn = qn;
     p.tn_max_bits = reinterpret_cast<const unsigned*>(misc + 1);
+    p.row_thr = row_thr;
 
     if (ctx->tc_chunk == 0) ERP_CUDA(record_timing(ctx, ctx->ev_k0));
     switch (kch) {
