@@ -244,7 +244,7 @@ int gather_bearings_chain(erp_ctx* ctx, const erp_dmatch* d_matches, int n_cap, 
                           float* d_l4, float* d_r4, float* Ks, int32_t* w);
 int gather_slots_chain(erp_ctx* ctx, const erp_dmatch* d_slots, int n_ranks, int slot_records, int n_cap, erp_dmatch* d_out,
                        int32_t* d_n_out, const void* d_left_xy, const void* d_right_xy, size_t stride, int W, int H,
-                       double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w);
+                       double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w, uint32_t* ctl, const uint32_t* slot_flag);
 int bearings_pair_chain(erp_ctx* ctx, const void* d_left_xy, const void* d_right_xy, size_t stride, int n, int W, int H,
                         double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w);
 

@@ -19,6 +19,8 @@
 
 namespace erp {
 
+constexpr int PEER_MAX = 64;
+
 // ------------------------------------------------------------------------------------------ NCCL at run time
 struct NcclApi {
     void* handle = nullptr;
@@ -70,16 +72,68 @@ static int need_nccl()
         }                                                                                           \
     } while (0)
 
+// ------------------------------------------------------------------------------------------ peer-memory exchange
+// The two exchange steps of a sharded pair are tiny (<= 1.6 MB of match records, 8 bytes of best model) and sit on the
+// critical path between kernels a few microseconds long: through NCCL they cost ~35 us each on this pool (plus the
+// occasional millisecond when a proxy thread is descheduled).  Every rank therefore owns a WINDOW of device memory that
+// all its peers map (cudaIpc* between processes, peer access inside one process) and the exchange is done by the
+// library's own kernels over NVLink: a rank STORES its match slot / best word straight into every peer's window and
+// then raises a per-source epoch flag there; consumers spin on flags in their own memory.  No kernel ever waits for
+// something a peer has not been able to issue yet (every rank pushes before it waits), the epochs live on the device
+// (a replayed CUDA graph advances them like a direct call), and spins are bounded (a protocol error traps instead of
+// hanging the GPU).  NCCL stays for what is bandwidth bound or rare: the train-set all-gather of host-buffer calls,
+// the cross-check reduction, and the window set-up itself.
+struct WindowLayout {                     // byte offsets inside a window
+    static constexpr size_t CTL = 0;             // uint32[64]: [0] epoch of the slot exchange, [1] of the best exchange, [2] ticket
+    static constexpr size_t SLOT_FLAG = 256;     // uint32[64]: epoch of the last slot pushed by rank r
+    static constexpr size_t BEST_FLAG = 512;     // uint32[64]
+    static constexpr size_t BEST = 768;          // uint64[64]: packed best model of rank r
+    static constexpr size_t SLOTS = 2048;        // erp_dmatch[nranks][slot_records]
+};
+struct WindowPtrs { uint8_t* peer[PEER_MAX]; };  // kernel argument: rank r's window as seen from this device
+
+struct LocalClique {                      // one process, several devices (erp_group): pointers travel through host memory
+    int n = 0;
+    std::atomic<int> arrived{0}, phase{0};
+    void* win[PEER_MAX] = {};
+    int ok[PEER_MAX] = {};
+    void barrier()
+    {
+        const int p = phase.load();
+        if (arrived.fetch_add(1) + 1 == n) { arrived.store(0); phase.store(p + 1); }
+        else while (phase.load() == p) std::this_thread::yield();
+    }
+};
+
 struct Comm {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer window
+    uint8_t* win = nullptr;
+    size_t win_bytes = 0;
+    WindowPtrs ptrs = {};
+    bool opened[PEER_MAX] = {};          // cudaIpcOpenMemHandle mappings to close
+    bool peer_failed = false;            // set once: stay on NCCL
+    LocalClique* clique = nullptr;       // shared by the contexts of an erp_group (owned by the group)
 };
+
+static void window_close(Comm* c)
+{
+    for (int r = 0; r < c->nranks && r < PEER_MAX; r++) {
+        if (c->opened[r] && c->ptrs.peer[r]) cudaIpcCloseMemHandle(c->ptrs.peer[r]);
+        c->opened[r] = false;
+        c->ptrs.peer[r] = nullptr;
+    }
+}
 
 void comm_release(erp_ctx* ctx)
 {
     if (!ctx->comm) return;
-    if (ctx->comm->comm && nccl().handle) nccl().CommDestroy(ctx->comm->comm);
-    delete ctx->comm;
+    Comm* c = ctx->comm;
+    window_close(c);
+    if (c->win) cudaFree(c->win);
+    if (c->comm && nccl().handle) nccl().CommDestroy(c->comm);
+    delete c;
     ctx->comm = nullptr;
 }
 
@@ -93,9 +147,151 @@ static inline void shard_range(int n, int rank, int world, int* lo, int* hi)
     *hi = *lo + base + (rank < rem ? 1 : 0);
 }
 
+// Collective: a window of at least `need` bytes on every rank, mapped by every rank.  Every rank of the clique calls it
+// with the same size from the same call; returns null when the peer path is not available (then NCCL carries the
+// exchange).  Growing re-does the set-up (host synchronisation: once per problem size, not per call).
+static Comm* window_ensure(erp_ctx* ctx, size_t need)
+{
+    Comm* c = ctx->comm;
+    static const bool off = [] { const char* e = getenv("ERP_B200_PEER"); return e && atoi(e) == 0; }();
+    if (off || !c || c->peer_failed || c->nranks > PEER_MAX) return nullptr;
+    if (c->win && c->win_bytes >= need) return c;
+    if (ctx->capturing) return nullptr;                       // never during a capture: the first (direct) call sizes it
+    const int G = c->nranks, rank = c->rank;
+    size_t bytes = need < (size_t)(8 << 20) ? (size_t)(8 << 20) : need + need / 2;
+    int good = 1;
+    cudaStreamSynchronize(ctx->stream);
+    if (c->clique) {
+        // ---- one process: plain pointers, peer access was enabled when the group was made
+        c->clique->barrier();                                 // nobody still uses the old windows
+        if (c->win) { cudaFree(c->win); c->win = nullptr; }
+        if (cudaMalloc(&c->win, bytes) != cudaSuccess || cudaMemset(c->win, 0, WindowLayout::SLOTS) != cudaSuccess) { cudaGetLastError(); good = 0; }
+        c->clique->win[rank] = c->win;
+        c->clique->ok[rank] = good;
+        c->clique->barrier();
+        for (int r = 0; r < G; r++) { good &= c->clique->ok[r]; c->ptrs.peer[r] = static_cast<uint8_t*>(c->clique->win[r]); }
+        c->clique->barrier();                                 // everyone has read the table before it can change again
+    } else {
+        // ---- one process per GPU: cudaIpc handles, exchanged with NCCL
+        int st = ERP_OK;
+        uint8_t* xh = ctx->scratch<uint8_t>(S_GATHER, (size_t)G * 128 + 64, &st);
+        if (st != ERP_OK) { c->peer_failed = true; return nullptr; }
+        window_close(c);
+        int32_t* flag = reinterpret_cast<int32_t*>(xh + (size_t)G * 128);
+        // barrier: every rank has dropped its mappings before anyone frees the memory behind them
+        if (nccl().AllReduce(flag, flag, 1, ncclInt32, ncclMin, c->comm, ctx->stream) != ncclSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) good = 0;
+        if (c->win) { cudaFree(c->win); c->win = nullptr; }
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof mine);
+        if (cudaMalloc(&c->win, bytes) != cudaSuccess || cudaMemset(c->win, 0, WindowLayout::SLOTS) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine, c->win) != cudaSuccess) { cudaGetLastError(); good = 0; }
+        static_assert(sizeof(cudaIpcMemHandle_t) <= 128, "handle size");
+        std::vector<uint8_t> all((size_t)G * 128, 0);
+        cudaMemcpy(xh + (size_t)rank * 128, &mine, sizeof mine, cudaMemcpyHostToDevice);
+        if (nccl().AllGather(xh + (size_t)rank * 128, xh, 128, ncclInt8, c->comm, ctx->stream) != ncclSuccess ||
+            cudaMemcpyAsync(all.data(), xh, all.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); good = 0; }
+        for (int r = 0; r < G && good; r++) {
+            if (r == rank) { c->ptrs.peer[r] = c->win; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + (size_t)r * 128, sizeof h);
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+            c->ptrs.peer[r] = static_cast<uint8_t*>(p);
+            c->opened[r] = true;
+        }
+        // all or nothing: a rank that could not map a peer sends everybody back to NCCL
+        int32_t mine_ok = good;
+        cudaMemcpy(flag, &mine_ok, sizeof mine_ok, cudaMemcpyHostToDevice);
+        if (nccl().AllReduce(flag, flag, 1, ncclInt32, ncclMin, c->comm, ctx->stream) != ncclSuccess ||
+            cudaMemcpyAsync(&mine_ok, flag, sizeof mine_ok, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); mine_ok = 0; }
+        good = mine_ok;
+    }
+    ctx->scratch_gen++;                                       // a cached graph holds window pointers
+    if (!good) {
+        window_close(c);
+        if (c->win) { cudaFree(c->win); c->win = nullptr; }
+        c->win_bytes = 0;
+        c->peer_failed = true;
+        return nullptr;
+    }
+    c->win_bytes = bytes;
+    return c;
+}
+
+__device__ __forceinline__ void spin_until(const volatile uint32_t* flag, uint32_t epoch)
+{
+    if ((int32_t)(*flag - epoch) >= 0) return;
+    const long long t0 = clock64();
+    while ((int32_t)(*flag - epoch) < 0) {
+        __nanosleep(40);
+        if (clock64() - t0 > 8000000000LL) __trap();          // ~4 s: a peer never arrived
+    }
+}
+
+// my match slot (header + records) into every peer's window, then the epoch flag of this rank on every peer
+__global__ void __launch_bounds__(256)
+push_slots_kernel(WindowPtrs w, int G, int rank, int slot_records)
+{
+    __shared__ int last;
+    uint8_t* local = w.peer[rank];
+    const int4* mine = reinterpret_cast<const int4*>(local + WindowLayout::SLOTS) + (size_t)rank * slot_records;
+    const uint32_t epoch = reinterpret_cast<volatile uint32_t*>(local + WindowLayout::CTL)[0] + 1;
+    int n = mine[0].x;                                         // header: the count the filter wrote
+    n = n < 0 ? 0 : (n < slot_records - 1 ? n : slot_records - 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) {
+        const int4 rec = mine[i];
+        for (int p = 0; p < G; p++)
+            if (p != rank) (reinterpret_cast<int4*>(w.peer[p] + WindowLayout::SLOTS) + (size_t)rank * slot_records)[i] = rec;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<uint32_t*>(local + WindowLayout::CTL) + 2, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if (threadIdx.x < G) reinterpret_cast<volatile uint32_t*>(w.peer[threadIdx.x] + WindowLayout::SLOT_FLAG)[rank] = epoch;
+    if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(local + WindowLayout::CTL)[2] = 0;
+}
+
+// the single small reduction of north_star: every rank stores its packed best into every window, waits for the others'
+// and keeps the maximum (count, then lowest hypothesis id).  One block.
+__global__ void __launch_bounds__(PEER_MAX)
+xchg_best_kernel(WindowPtrs w, int G, int rank, unsigned long long* __restrict__ packed)
+{
+    __shared__ unsigned long long red[PEER_MAX];
+    uint8_t* local = w.peer[rank];
+    const uint32_t epoch = reinterpret_cast<volatile uint32_t*>(local + WindowLayout::CTL)[1] + 1;
+    const int r = threadIdx.x;
+    const unsigned long long mine = *packed;
+    unsigned long long v = 0;
+    if (r < G) {
+        reinterpret_cast<volatile unsigned long long*>(w.peer[r] + WindowLayout::BEST)[rank] = mine;
+        __threadfence_system();
+        reinterpret_cast<volatile uint32_t*>(w.peer[r] + WindowLayout::BEST_FLAG)[rank] = epoch;
+        spin_until(reinterpret_cast<volatile uint32_t*>(local + WindowLayout::BEST_FLAG) + r, epoch);
+        __threadfence_system();
+        v = reinterpret_cast<volatile unsigned long long*>(local + WindowLayout::BEST)[r];
+    }
+    red[r] = v;
+    __syncthreads();
+    if (r == 0) {
+        for (int i = 1; i < G; i++) v = red[i] > v ? red[i] : v;
+        *packed = v;
+        reinterpret_cast<volatile uint32_t*>(local + WindowLayout::CTL)[1] = epoch;
+    }
+}
+
 int comm_allreduce_best(erp_ctx* ctx, uint64_t* d_packed)
 {
     if (comm_size(ctx) == 1) return ERP_OK;
+    if (Comm* c = window_ensure(ctx, WindowLayout::SLOTS)) {
+        xchg_best_kernel<<<1, PEER_MAX, 0, ctx->stream>>>(c->ptrs, c->nranks, c->rank, reinterpret_cast<unsigned long long*>(d_packed));
+        ERP_LAUNCH(ctx, "xchg_best_kernel");
+        return ERP_OK;
+    }
     // the packed word is < 2^63 (counts are < 2^31), unsigned max orders (count, then lowest id)
     ERP_NCCL(nccl().AllReduce(d_packed, d_packed, 1, ncclUint64, ncclMax, ctx->comm->comm, ctx->stream));
     return ERP_OK;
@@ -247,11 +443,13 @@ ERP_API int erp_pair_pose_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_
     shard_range(H_total, rank, G, &hlo, &hhi);
     ERP_ARG(hi == lo || d_q_shard, ERP_E_ARG, "erp_pair_pose_dist_dev: null query shard");
     const uint64_t key[] = {(uint64_t)(uintptr_t)d_q_shard, (uint64_t)(uintptr_t)d_t, (uint64_t)(uintptr_t)d_left_xy, (uint64_t)(uintptr_t)d_right_xy, (uint64_t)(uintptr_t)d_matches, (uint64_t)(uintptr_t)d_n_matches, (uint64_t)(uintptr_t)d_mask, (uint64_t)(uintptr_t)d_result, (uint64_t)nq_total, (uint64_t)nt, (uint64_t)dim, (uint64_t)cross_check, (uint64_t)width, (uint64_t)height, (uint64_t)H_total, (uint64_t)S, (uint64_t)metric, (uint64_t)__builtin_bit_cast(uint32_t, ratio), (uint64_t)__builtin_bit_cast(uint32_t, tau), (uint64_t)seed, (uint64_t)kp_stride_bytes};      // every argument, no padding bytes
-    return graph_run(ctx, key, sizeof key, [&]() -> int {
-    // slots of the match exchange: [header | up to cap records] per rank
+    // slots of the match exchange: [header | up to cap records] per rank, in the peer window when there is one
     const int cap = cdiv(nq_total, G), slot = cap + 1;
+    Comm* win = window_ensure(ctx, WindowLayout::SLOTS + (size_t)slot * G * sizeof(erp_dmatch));
+    return graph_run(ctx, key, sizeof key, [&]() -> int {
     int st = ERP_OK;
-    erp_dmatch* slots = ctx->scratch<erp_dmatch>(S_XCHG, (size_t)slot * G, &st);
+    erp_dmatch* slots = win ? reinterpret_cast<erp_dmatch*>(win->win + WindowLayout::SLOTS)
+                            : ctx->scratch<erp_dmatch>(S_XCHG, (size_t)slot * G, &st);
     PoseBuffers b;
     ERP_TRY(pose_chain_buffers(ctx, nq_total, &b));
     const bool tc = ransac_uses_tc(ctx, hhi - hlo, nq_total, metric);
@@ -264,11 +462,19 @@ ERP_API int erp_pair_pose_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_
     ERP_CUDA(cudaMemsetAsync(mine, 0, sizeof(erp_dmatch), ctx->stream));
     ERP_TRY(match_shard_dev(ctx, d_q_shard, lo, hi, d_t, nt, dim, ratio, cross_check, mine + 1, &mine->queryIdx));
     ERP_CUDA(record_timing(ctx, ctx->ev_stage[1]));
-    // in place: rank r's slot is already at its position of the receive buffer
-    ERP_NCCL(nccl().AllGather(mine, slots, (size_t)slot * sizeof(erp_dmatch), ncclInt8, ctx->comm->comm, ctx->stream));
+    if (win) {
+        // peer stores over NVLink + epoch flags; the gather below waits for the flags of all ranks
+        push_slots_kernel<<<cdiv(slot, 256), 256, 0, ctx->stream>>>(win->ptrs, G, rank, slot);
+        ERP_LAUNCH(ctx, "push_slots_kernel");
+    } else {
+        // in place: rank r's slot is already at its position of the receive buffer
+        ERP_NCCL(nccl().AllGather(mine, slots, (size_t)slot * sizeof(erp_dmatch), ncclInt8, ctx->comm->comm, ctx->stream));
+    }
     if (tc) ERP_CUDA(cudaMemsetAsync(sb.w, 0, W_WORDS_BYTES, ctx->stream));
     ERP_TRY(gather_slots_chain(ctx, slots, G, slot, nq_total, d_matches, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes,
-                               width, height, b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
+                               width, height, b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w,
+                               win ? reinterpret_cast<uint32_t*>(win->win + WindowLayout::CTL) : nullptr,
+                               win ? reinterpret_cast<uint32_t*>(win->win + WindowLayout::SLOT_FLAG) : nullptr));
     ERP_CUDA(record_timing(ctx, ctx->ev_stage[2]));
     ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, nq_total, d_n_matches, seed, (uint64_t)hlo, hhi - hlo, S, metric, tau, tc, true,
                             d_mask ? d_mask : b.mask, d_result));
@@ -408,6 +614,7 @@ ERP_API int erp_knn2_match_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq
 // one process, several devices: contexts + clique + one worker thread per device
 // ======================================================================================
 struct erp_group {
+    erp::LocalClique clique;              // host-side rendezvous of the peer windows (one process: no cudaIpc)
     std::vector<erp_ctx*> ctx;
     std::vector<std::thread> workers;
     std::mutex mu;
@@ -499,9 +706,25 @@ ERP_API int erp_group_create(const int* devices, int ndev, erp_group** out)
             erp_group_destroy(g);
             return ERP_E_NCCL;
         }
+        // peer access for the windows (dist.cu: peer-memory exchange); without it the exchange stays on NCCL
+        bool p2p = true;
+        for (int i = 0; i < ndev && p2p; i++) {
+            DeviceGuard dg(devices[i]);
+            for (int j = 0; j < ndev && p2p; j++) {
+                if (i == j) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) { p2p = false; break; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) p2p = false;
+                cudaGetLastError();
+            }
+        }
+        g->clique.n = ndev;
         for (int i = 0; i < ndev; i++) {
             Comm* c = new Comm();
             c->comm = comms[i]; c->nranks = ndev; c->rank = i;
+            c->clique = &g->clique;
+            c->peer_failed = !p2p;
             g->ctx[i]->comm = c;
         }
     }

@@ -79,14 +79,32 @@ __global__ void gather_slots_kernel(const erp_dmatch* __restrict__ slots, int n_
                                     erp_dmatch* __restrict__ out, int32_t* __restrict__ n_out,
                                     const char* __restrict__ lxy, const char* __restrict__ rxy, size_t stride,
                                     int W, int H, double* __restrict__ l3, double* __restrict__ r3,
-                                    float4* __restrict__ l4, float4* __restrict__ r4, float* __restrict__ Ks, int32_t* __restrict__ w)
+                                    float4* __restrict__ l4, float4* __restrict__ r4, float* __restrict__ Ks, int32_t* __restrict__ w,
+                                    uint32_t* __restrict__ ctl, const uint32_t* __restrict__ slot_flag)
 {
     __shared__ int prefix[GATHER_MAX_RANKS + 1];
+    __shared__ int last;
+    // peer-memory exchange (dist.cu): the slots were stored into this rank's window by its peers, each followed by the
+    // peer's epoch flag; epoch = ctl[0] + 1, advanced by the last block of this kernel
+    uint32_t epoch = 0;
+    if (ctl) {
+        epoch = *reinterpret_cast<volatile uint32_t*>(ctl) + 1;
+        if (threadIdx.x < n_ranks) {
+            const volatile uint32_t* f = slot_flag + threadIdx.x;
+            const long long t0 = clock64();
+            while ((int32_t)(*f - epoch) < 0) {
+                __nanosleep(40);
+                if (clock64() - t0 > 8000000000LL) __trap();       // a peer never arrived
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int r = 0; r < n_ranks; r++) {
             prefix[r] = acc;
-            int c = slots[(size_t)r * slot_records].queryIdx;
+            int c = __ldcg(reinterpret_cast<const int*>(slots + (size_t)r * slot_records));
             acc += c < 0 ? 0 : (c < slot_records - 1 ? c : slot_records - 1);
         }
         prefix[n_ranks] = acc < n_cap ? acc : n_cap;
@@ -99,7 +117,9 @@ __global__ void gather_slots_kernel(const erp_dmatch* __restrict__ slots, int n_
     if (i < n) {
         int r = 0;
         while (r + 1 < n_ranks && prefix[r + 1] <= i) r++;
-        const erp_dmatch m = slots[(size_t)r * slot_records + 1 + (i - prefix[r])];
+        const int4 raw = __ldcg(reinterpret_cast<const int4*>(slots + (size_t)r * slot_records + 1 + (i - prefix[r])));
+        erp_dmatch m;
+        m.queryIdx = raw.x; m.trainIdx = raw.y; m.imgIdx = raw.z; m.distance = __int_as_float(raw.w);
         out[i] = m;
         double x, y, z;
         pixel_to_bearing(reinterpret_cast<const float*>(lxy + (size_t)m.queryIdx * stride), W, H, x, y, z);
@@ -112,6 +132,13 @@ __global__ void gather_slots_kernel(const erp_dmatch* __restrict__ slots, int n_
         r4[i] = rf;
     }
     if (Ks) prep_k_slot(i, n, lf, rf, Ks, w);
+    if (ctl) {
+        // every block has read the epoch and the slots: the last one to finish advances the epoch
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(ctl + 3, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last && threadIdx.x == 0) { ctl[3] = 0; *reinterpret_cast<volatile uint32_t*>(ctl) = epoch; }
+    }
 }
 
 // the same for keypoint pairs that are already gathered (erp_ransac_pixels): slot i of both views
@@ -988,12 +1015,12 @@ int gather_bearings_chain(erp_ctx* ctx, const erp_dmatch* d_matches, int n_cap, 
 
 int gather_slots_chain(erp_ctx* ctx, const erp_dmatch* d_slots, int n_ranks, int slot_records, int n_cap, erp_dmatch* d_out,
                        int32_t* d_n_out, const void* d_left_xy, const void* d_right_xy, size_t stride, int W, int H,
-                       double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w)
+                       double* d_l3, double* d_r3, float* d_l4, float* d_r4, float* Ks, int32_t* w, uint32_t* ctl, const uint32_t* slot_flag)
 {
     if (n_ranks > GATHER_MAX_RANKS) { set_error("more than %d ranks", GATHER_MAX_RANKS); return ERP_E_LIMIT; }
     gather_slots_kernel<<<max(1, cdiv(n_cap, 256)), 256, 0, ctx->stream>>>(d_slots, n_ranks, slot_records, n_cap, d_out, d_n_out,
                                                                           (const char*)d_left_xy, (const char*)d_right_xy, stride, W, H,
-                                                                          d_l3, d_r3, (float4*)d_l4, (float4*)d_r4, Ks, w);
+                                                                          d_l3, d_r3, (float4*)d_l4, (float4*)d_r4, Ks, w, ctl, slot_flag);
     ERP_LAUNCH(ctx, "gather_slots_kernel");
     return ERP_OK;
 }
