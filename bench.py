@@ -146,16 +146,25 @@ def tf32_measured():
     return None
 
 
-def sass_stamp(kernel_substr):
-    """sha1 of the kernel's SASS in the shipped library: roofline.traffic is an ncu constant taken for ONE build of the
-    kernel; a different stamp in profiles/roofline_traffic.json means the constant is stale."""
+def sass_stamp(kernel_substr, variant="ILi2"):
+    """sha1 of the kernel's SASS in the shipped library (D = 64 instantiation): roofline.traffic is an ncu constant taken
+    for ONE build of the kernel; a different stamp in profiles/roofline_traffic.json means the constant is stale."""
+    import re
+
     lib = os.path.join(ROOT, "erp_match_eightpoint_test_b200", "lib", "liberp_b200.so")
     try:
-        out = subprocess.run(["cuobjdump", "-sass", "-fun", kernel_substr, lib], capture_output=True, text=True, timeout=60).stdout
+        out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=120).stdout
     except (OSError, subprocess.TimeoutExpired):
         return None
-    code = "\n".join(l.split("*/")[1].strip() if "*/" in l else l.strip() for l in out.splitlines() if "/*0" in l)
-    return hashlib.sha1(code.encode()).hexdigest()[:12] if code else None
+    code, on = [], False
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            on = kernel_substr in m.group(1) and variant in m.group(1)
+            continue
+        if on and "/*0" in line:
+            code.append(re.sub(r"/\*[0-9a-fx ]+\*/", "", line).strip())       # opcode text only: addresses and encodings dropped
+    return hashlib.sha1("\n".join(code).encode()).hexdigest()[:12] if code else None
 
 
 # --------------------------------------------------------------------------------------------
@@ -330,7 +339,7 @@ def distance_roofline(rig, cfg, stats, k_ms, nq_kernel, nt, dim, clocks, workloa
         traffic = tr.get(engine + ":" + workload)      # dram bytes per launch (ncu --set full)
         stamp = tr.get(engine + ":sass")
     if engine.startswith("tcgen05"):
-        stamp_now = sass_stamp("knn2_tc1_kernel" if engine == "tcgen05_1xtf32" else "knn2_tc_kernel")
+        stamp_now = sass_stamp("knn2_tc1_kernelILi" if engine == "tcgen05_1xtf32" else "knn2_tc_kernelILi", "ILi%dE" % ((dim + 31) // 32))
     roof = {"bound": "tensor", "kernel": "distance tiles + fused top-k (" + engine + ")", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_sass_stamp": {"captured": stamp, "this_build": stamp_now,

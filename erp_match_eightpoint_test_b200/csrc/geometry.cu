@@ -455,17 +455,77 @@ __device__ void decompose_pose(const M3& Ec, float* pose)
     pose[11] = 0.f;
 }
 
-// rank-2 projection (eight_point.cpp:45-50: SVD, sigma3 <- 0, recompose), optional pose
+// rank-2 projection (eight_point.cpp:45-50: SVD, sigma3 <- 0, recompose), optional pose.
+// U diag(s1, s2, 0) V^T = E - (E v3) v3^T with v3 the right singular vector of the smallest singular value, i.e. the
+// eigenvector of M = E^T E for its smallest eigenvalue.  A full one-sided Jacobi SVD (hypot, sqrt and two divisions per
+// rotation, ~15 rotations) was 40 % of the minimal-sample solver; here the eigenvalue comes from Newton's iteration on
+// the characteristic cubic started at 0 (monotone from below: the cubic is increasing and concave up to its first
+// root) and v3 from the largest cross product of two rows of M - lambda I: ~150 flops, one square root.  The result is
+// the same matrix to working precision; a (numerically) double smallest singular value falls back to the SVD.
+__device__ __forceinline__ bool rank2_project_fast(const M3& E, M3& Ec)
+{
+    double m[6];                                  // M = E^T E, upper triangle: 00 01 02 11 12 22
+    m[0] = E.v[0] * E.v[0] + E.v[3] * E.v[3] + E.v[6] * E.v[6];
+    m[1] = E.v[0] * E.v[1] + E.v[3] * E.v[4] + E.v[6] * E.v[7];
+    m[2] = E.v[0] * E.v[2] + E.v[3] * E.v[5] + E.v[6] * E.v[8];
+    m[3] = E.v[1] * E.v[1] + E.v[4] * E.v[4] + E.v[7] * E.v[7];
+    m[4] = E.v[1] * E.v[2] + E.v[4] * E.v[5] + E.v[7] * E.v[8];
+    m[5] = E.v[2] * E.v[2] + E.v[5] * E.v[5] + E.v[8] * E.v[8];
+    const double tr = m[0] + m[3] + m[5];
+    if (!(tr > 0.0) || !(tr < INFINITY)) return false;
+    // f(x) = x^3 - c2 x^2 + c1 x - c0, roots = eigenvalues
+    const double c2 = tr;
+    const double c1 = (m[0] * m[3] - m[1] * m[1]) + (m[0] * m[5] - m[2] * m[2]) + (m[3] * m[5] - m[4] * m[4]);
+    const double dE = det3(E), c0 = dE * dE;
+    double x = 0.0;
+    for (int it = 0; it < 12; it++) {
+        const double f = ((x - c2) * x + c1) * x - c0, df = (3.0 * x - 2.0 * c2) * x + c1;
+        if (!(df > 0.0)) return false;            // the two smallest eigenvalues (nearly) coincide
+        const double step = f / df;
+        x -= step;
+        if (fabs(step) <= 1e-17 * tr) break;
+    }
+    if (!(x >= 0.0)) x = 0.0;
+    // rows of A = M - x I
+    const double a00 = m[0] - x, a11 = m[3] - x, a22 = m[5] - x;
+    const double r0[3] = {a00, m[1], m[2]}, r1[3] = {m[1], a11, m[4]}, r2[3] = {m[2], m[4], a22};
+    double c[3][3];
+    c[0][0] = r0[1] * r1[2] - r0[2] * r1[1]; c[0][1] = r0[2] * r1[0] - r0[0] * r1[2]; c[0][2] = r0[0] * r1[1] - r0[1] * r1[0];
+    c[1][0] = r0[1] * r2[2] - r0[2] * r2[1]; c[1][1] = r0[2] * r2[0] - r0[0] * r2[2]; c[1][2] = r0[0] * r2[1] - r0[1] * r2[0];
+    c[2][0] = r1[1] * r2[2] - r1[2] * r2[1]; c[2][1] = r1[2] * r2[0] - r1[0] * r2[2]; c[2][2] = r1[0] * r2[1] - r1[1] * r2[0];
+    double n[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) n[k] = c[k][0] * c[k][0] + c[k][1] * c[k][1] + c[k][2] * c[k][2];
+    const int best = n[0] >= n[1] ? (n[0] >= n[2] ? 0 : 2) : (n[1] >= n[2] ? 1 : 2);
+    const double nb = best == 0 ? n[0] : (best == 1 ? n[1] : n[2]);
+    // |r_i x r_j| ~ (l1 - l3)(l2 - l3): a tiny value means the smallest eigenvalue is not isolated
+    if (!(nb > 1e-12 * tr * tr * tr * tr)) return false;
+    const double inv = 1.0 / sqrt(nb);
+    double v[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) v[k] = (best == 0 ? c[0][k] : (best == 1 ? c[1][k] : c[2][k])) * inv;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double w = E.v[3 * i] * v[0] + E.v[3 * i + 1] * v[1] + E.v[3 * i + 2] * v[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) Ec.v[3 * i + j] = E.v[3 * i + j] - w * v[j];
+    }
+    return true;
+}
+
 template <bool WANT_POSE>
 __device__ __forceinline__ void finish_hypothesis(const M3& E, double* __restrict__ Eout, float* __restrict__ pose)
 {
-    double w[3];
-    M3 U, Vt;
-    svd3(E, w, U, Vt);
-    M3 UD;
+    M3 Ec;
+    if (!rank2_project_fast(E, Ec)) {
+        double w[3];
+        M3 U, Vt;
+        svd3(E, w, U, Vt);
+        M3 UD;
 #pragma unroll
-    for (int i = 0; i < 3; i++) { UD.v[3 * i] = U.v[3 * i] * w[0]; UD.v[3 * i + 1] = U.v[3 * i + 1] * w[1]; UD.v[3 * i + 2] = 0.0; }
-    M3 Ec = mul3(UD, Vt);
+        for (int i = 0; i < 3; i++) { UD.v[3 * i] = U.v[3 * i] * w[0]; UD.v[3 * i + 1] = U.v[3 * i + 1] * w[1]; UD.v[3 * i + 2] = 0.0; }
+        Ec = mul3(UD, Vt);
+    }
 #pragma unroll
     for (int k = 0; k < 9; k++) Eout[k] = Ec.v[k];
     if (WANT_POSE) decompose_pose(Ec, pose);
@@ -776,6 +836,7 @@ __device__ void refit_inverse_iteration(const double* Gp /* packed upper triangl
 #pragma unroll
         for (int i = 0; i < 9; i++) x[i] *= s;
     }
+    double prev = INFINITY;
     for (int it = 0; it < 24; it++) {
         double y[9];
 #pragma unroll
@@ -800,7 +861,9 @@ __device__ void refit_inverse_iteration(const double* Gp /* packed upper triangl
         double diff = 0.0;
 #pragma unroll
         for (int i = 0; i < 9; i++) { const double v = y[i] * s; diff = fmax(diff, fabs(v - x[i])); x[i] = v; }
-        if (diff < 4e-15) break;
+        // converged, or at the rounding floor of the solves (the change no longer shrinks)
+        if (diff < 1e-14 || (it > 0 && diff >= 0.5 * prev)) break;
+        prev = diff;
     }
     M3 E;
 #pragma unroll

@@ -75,14 +75,29 @@ __host__ __device__ constexpr int f_smem(int kch) { return f_sub(kch) * kch * F_
 
 // rows -> tf32-rounded rows (dpad floats), optional norms (+inf padding) and their maximum
 // LPR lanes own one row (4 floats per lane and pass); a warp covers 32 / LPR rows
+// one operand of a prep launch: rows x, scaled, rounded into out; norms (+inf padding up to n_pad), their maximum, and the
+// 8-float norm operand rows when aug is given
+struct RoundJob {
+    const float* x; int n; float scale; float* out; float* norm; int n_pad; unsigned* max_bits; float* aug; int blocks;
+};
+
+// both operands of a search in ONE launch: blocks [0, a.blocks) round the queries, the rest the train rows
 template <int LPR>
 __global__ void __launch_bounds__(256)
-round_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
-             float* __restrict__ out, float* __restrict__ norm, int n_pad, unsigned* __restrict__ max_bits, float* __restrict__ aug)
+round_kernel(const RoundJob a, const RoundJob b, int dim, int dpad)
 {
     constexpr int RPW = 32 / LPR;
+    const bool second = (int)blockIdx.x >= a.blocks;
+    const RoundJob& j = second ? b : a;
+    const float* __restrict__ x = j.x;
+    float* __restrict__ out = j.out;
+    float* __restrict__ norm = j.norm;
+    float* __restrict__ aug = j.aug;
+    unsigned* __restrict__ max_bits = j.max_bits;
+    const int n = j.n, n_pad = j.n_pad;
+    const float scale = j.scale;
     const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
-    const int row = (blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + sub;
+    const int row = (((int)blockIdx.x - (second ? a.blocks : 0)) * 8 + (threadIdx.x >> 5)) * RPW + sub;
     double acc = 0.0;
     if (row < n) {
         for (int k = l * 4; k < dpad; k += LPR * 4) {
@@ -114,16 +129,17 @@ round_kernel(const float* __restrict__ x, int n, int dim, int dpad, float scale,
     }
 }
 
-static int launch_prep(erp_ctx* ctx, const float* x, int n, int dim, int dpad, float scale, float* out, float* norm, int n_pad,
-                       unsigned* max_bits, float* aug = nullptr)
+static int launch_prep(erp_ctx* ctx, RoundJob a, RoundJob b, int dim, int dpad)
 {
     // 8 / 16 / 32 lanes per row for dpad = 32 / 64 / (96, 128)
     const int lpr = dpad <= 32 ? 8 : dpad <= 64 ? 16 : 32;
     const int rows_per_block = 8 * (32 / lpr);
-    const int grid = cdiv(n_pad, rows_per_block);
-    if (lpr == 8) round_kernel<8><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits, aug);
-    else if (lpr == 16) round_kernel<16><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits, aug);
-    else round_kernel<32><<<grid, 256, 0, ctx->stream>>>(x, n, dim, dpad, scale, out, norm, n_pad, max_bits, aug);
+    a.blocks = cdiv(a.n_pad, rows_per_block);
+    b.blocks = b.x ? cdiv(b.n_pad, rows_per_block) : 0;
+    const int grid = a.blocks + b.blocks;
+    if (lpr == 8) round_kernel<8><<<grid, 256, 0, ctx->stream>>>(a, b, dim, dpad);
+    else if (lpr == 16) round_kernel<16><<<grid, 256, 0, ctx->stream>>>(a, b, dim, dpad);
+    else round_kernel<32><<<grid, 256, 0, ctx->stream>>>(a, b, dim, dpad);
     ERP_LAUNCH(ctx, "round_kernel");
     return ERP_OK;
 }
@@ -511,10 +527,11 @@ int knn2_tc1(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, i
     ERP_TRY(tc_misc_begin(ctx, misc));
     ERP_CUDA(cudaMemsetAsync(cand, 0xFF, (size_t)nq * n_lists * F_TOPK * sizeof(int32_t), ctx->stream));
 
-    ERP_TRY(launch_prep(ctx, d_q, nq, dim, dpad, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3)));
     float* aug = tn + (size_t)n_ttiles * F_BN;
-    if (ctx->tc_chunk == 0)
-        ERP_TRY(launch_prep(ctx, d_t, nt, dim, dpad, 1.0f, ts, tn, n_ttiles * F_BN, reinterpret_cast<unsigned*>(misc + 1), f_fold(kch) ? aug : nullptr));
+    RoundJob jq = {d_q, nq, -2.0f, qs, qn, nq, reinterpret_cast<unsigned*>(misc + 3), nullptr, 0};
+    RoundJob jt = {ctx->tc_chunk == 0 ? d_t : nullptr, nt, 1.0f, ts, tn, n_ttiles * F_BN, reinterpret_cast<unsigned*>(misc + 1),
+                   f_fold(kch) ? aug : nullptr, 0};
+    ERP_TRY(launch_prep(ctx, jq, jt, dim, dpad));
 
     CUtensorMap mq, mt;
     ERP_TRY(make_map(&mq, qs, nq, dpad, F_BM));

@@ -108,14 +108,34 @@ score_kernel(const double* __restrict__ E, int H, const float4* __restrict__ l4,
 }
 
 // Exact counts of a LIST of hypotheses (the contenders of the tensor-core search: a few hundred of a million) and their
-// packed best, algebraic residual.  Roles are transposed with respect to score_kernel: a thread owns one hypothesis (its
-// nine coefficients in registers), a block stages a slice of correspondences as Kronecker products in shared memory
-// and every thread walks it with broadcast reads -- no cross-thread reduction per hypothesis, full instruction-level
-// parallelism across correspondences, and many small blocks (tile x slice) so that a short list still fills the machine.
-// Same fma chain as everywhere else: counts are bit-exact.
-constexpr int SL_HYPS = 128;       // hypotheses per block (threads)
-constexpr int SL_CORR = 256;       // correspondences per block
-__global__ void __launch_bounds__(SL_HYPS)
+// packed best, algebraic residual.  Roles are transposed with respect to score_kernel: a thread owns TWO hypotheses (their
+// coefficients interleaved in packed fp32x2 registers), a block stages a slice of correspondences as Kronecker products
+// in shared memory and every thread walks it with broadcast reads -- no cross-thread reduction per hypothesis, full
+// instruction-level parallelism across correspondences, and many small blocks (tile x slice) so that a short list still
+// fills the machine.  mul.rn.f32x2 / fma.rn.f32x2 round each half like the scalar instructions: the fma chain is the
+// one used everywhere else and counts are bit-exact.
+constexpr int SL_THREADS = 64;              // threads per block
+constexpr int SL_HYPS = 2 * SL_THREADS;     // hypotheses per block
+constexpr int SL_CORR = 256;                // correspondences per block
+__device__ __forceinline__ unsigned long long pack2(float a, float b)
+{
+    unsigned long long p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(a), "f"(b));
+    return p;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__global__ void __launch_bounds__(SL_THREADS)
 score_list_kernel(const double* __restrict__ E, int H_cap, const int32_t* __restrict__ hlist, const int32_t* __restrict__ hlist_len,
                   const float4* __restrict__ l4, const float4* __restrict__ r4, int m_cap, const int32_t* __restrict__ m_dev, float tau,
                   int32_t* __restrict__ counts, int32_t* __restrict__ tile_done, unsigned long long* __restrict__ best,
@@ -127,7 +147,7 @@ score_list_kernel(const double* __restrict__ E, int H_cap, const int32_t* __rest
     if ((int)blockIdx.x * SL_HYPS >= H) return;
     const int m = dev_len(m_dev, m_cap);
     const int c0 = blockIdx.y * SL_CORR, n = max(0, min(SL_CORR, m - c0));
-    for (int i = threadIdx.x; i < n; i += SL_HYPS) {
+    for (int i = threadIdx.x; i < n; i += SL_THREADS) {
         float k[9];
         kron9(l4[c0 + i], r4[c0 + i], k);
         *reinterpret_cast<float4*>(&ks[i][0]) = make_float4(k[0], k[1], k[2], k[3]);
@@ -136,21 +156,29 @@ score_list_kernel(const double* __restrict__ E, int H_cap, const int32_t* __rest
     }
     __syncthreads();
     for (int h0 = blockIdx.x * SL_HYPS; h0 < H; h0 += gridDim.x * SL_HYPS) {
-        const int h = h0 + threadIdx.x;
-        float e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (h < H) scale_E(E + (size_t)hlist[h] * 9, e);
-        int cnt = 0;
+        const int ha = h0 + 2 * threadIdx.x, hb = ha + 1;
+        float ea[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, eb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (ha < H) scale_E(E + (size_t)hlist[ha] * 9, ea);
+        if (hb < H) scale_E(E + (size_t)hlist[hb] * 9, eb);
+        unsigned long long e2[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) e2[i] = pack2(ea[i], eb[i]);
+        int cnt_a = 0, cnt_b = 0;
 #pragma unroll 4
         for (int i = 0; i < n; i++) {
             const float4 k0 = *reinterpret_cast<const float4*>(&ks[i][0]), k1 = *reinterpret_cast<const float4*>(&ks[i][4]);
             const float k8 = ks[i][8];
-            float res = __fmul_rn(e[0], k0.x);
-            res = __fmaf_rn(e[1], k0.y, res); res = __fmaf_rn(e[2], k0.z, res); res = __fmaf_rn(e[3], k0.w, res);
-            res = __fmaf_rn(e[4], k1.x, res); res = __fmaf_rn(e[5], k1.y, res); res = __fmaf_rn(e[6], k1.z, res);
-            res = __fmaf_rn(e[7], k1.w, res); res = __fmaf_rn(e[8], k8, res);
-            cnt += fabsf(res) < tau ? 1 : 0;
+            unsigned long long res = mul2(e2[0], pack2(k0.x, k0.x));
+            res = fma2(e2[1], pack2(k0.y, k0.y), res); res = fma2(e2[2], pack2(k0.z, k0.z), res); res = fma2(e2[3], pack2(k0.w, k0.w), res);
+            res = fma2(e2[4], pack2(k1.x, k1.x), res); res = fma2(e2[5], pack2(k1.y, k1.y), res); res = fma2(e2[6], pack2(k1.z, k1.z), res);
+            res = fma2(e2[7], pack2(k1.w, k1.w), res); res = fma2(e2[8], pack2(k8, k8), res);
+            float ra, rb;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(res));
+            cnt_a += fabsf(ra) < tau ? 1 : 0;
+            cnt_b += fabsf(rb) < tau ? 1 : 0;
         }
-        if (h < H && cnt) atomicAdd(&counts[h], cnt);
+        if (ha < H && cnt_a) atomicAdd(&counts[ha], cnt_a);
+        if (hb < H && cnt_b) atomicAdd(&counts[hb], cnt_b);
         // the block that completes a hypothesis tile (last of its gridDim.y slices) merges the tile's packed best
         __threadfence();
         __syncthreads();
@@ -159,10 +187,15 @@ score_list_kernel(const double* __restrict__ E, int H_cap, const int32_t* __rest
         if (last_slice) {
             __threadfence();
             unsigned long long b = 0;
-            if (h < H) {
-                const int c = *reinterpret_cast<volatile int32_t*>(&counts[h]);
-                const unsigned long long id = hyp0 + (unsigned long long)hlist[h];
-                b = ((unsigned long long)(uint32_t)c << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)id);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int h = ha + u;
+                if (h < H) {
+                    const int c = *reinterpret_cast<volatile int32_t*>(&counts[h]);
+                    const unsigned long long id = hyp0 + (unsigned long long)hlist[h];
+                    const unsigned long long pk = ((unsigned long long)(uint32_t)c << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)id);
+                    b = pk > b ? pk : b;
+                }
             }
             for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_down_sync(0xffffffffu, b, o); b = y > b ? y : b; }
             if ((threadIdx.x & 31) == 0 && b) atomicMax(best, b);
@@ -264,7 +297,7 @@ int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d
     // the list is usually short (cfg3: ~900 contenders = 7 hypothesis tiles): tile x slice blocks of 128 threads
     // (score_kernel in list mode took 100 us for them, this kernel 20)
     dim3 grid(min(tiles, 32), max(1, cdiv(m_cap, SL_CORR)));
-    score_list_kernel<<<grid, SL_HYPS, 0, ctx->stream>>>(d_E, H_max, d_list, d_len, (const float4*)d_l4, (const float4*)d_r4, m_cap, d_m, tau,
+    score_list_kernel<<<grid, SL_THREADS, 0, ctx->stream>>>(d_E, H_max, d_list, d_len, (const float4*)d_l4, (const float4*)d_r4, m_cap, d_m, tau,
                                                         d_counts, d_counts + H_max, (unsigned long long*)d_best, (unsigned long long)hyp0);
     ERP_LAUNCH(ctx, "score_list_kernel");
     return ERP_OK;

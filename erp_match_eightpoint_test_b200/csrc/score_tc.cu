@@ -327,9 +327,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
 }
 
 // ---- the small kernels between the passes ------------------------------------------------------
-// After pass A: the hypothesis with the largest bound (lowest index on ties) is scored exactly over ALL correspondences
-// -> L*, a lower bound of the best count; the last block to finish the arg-max does it (1024 threads: ~50 correspondences
-// each) and plans passes B and C.  Its packed (count, ~id) is merged into *best like any other exact count.
+// After pass A: L* = a lower bound of the best exact count.  ANY hypothesis' exact count is one; the best-looking
+// hypotheses give the tightest.  Every block scores the hypothesis with the largest bound among its own (1024 threads,
+// ~50 correspondences each, four in flight) exactly over ALL correspondences -- the globally best-looking one is among
+// them, so L* is at least what scoring that one alone would give -- and merges its packed (count, ~id) into *best
+// like any other exact count.  The last block to finish takes the maximum and plans passes B and C.
 constexpr int AP_THREADS = 1024;
 __global__ void __launch_bounds__(AP_THREADS)
 argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__ E, const float4* __restrict__ l4,
@@ -339,8 +341,9 @@ argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__
     __shared__ unsigned long long wbest[AP_THREADS / 32];
     __shared__ int wsum[AP_THREADS / 32];
     __shared__ float Es[9];
-    __shared__ int last;
+    __shared__ int first_sh, last;
     const int H = w[W_DYN_A], lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int m = w[W_M];
     unsigned long long b = 0;
     for (int h = blockIdx.x * AP_THREADS + threadIdx.x; h < H; h += gridDim.x * AP_THREADS) {
         unsigned long long v = ((unsigned long long)(uint32_t)upper[h] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)h);
@@ -351,46 +354,51 @@ argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < AP_THREADS / 32; i++) b = wbest[i] > b ? wbest[i] : b;
-        atomicMax(reinterpret_cast<unsigned long long*>(w + W_AMAX), b);
-        __threadfence();
-        last = atomicAdd(w + W_DONE, 1) == (int)gridDim.x - 1;
+        // a block whose range is empty (H < its first index) has nothing to score
+        first_sh = b ? (int)(0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull)) : -1;
+        if (first_sh >= 0) scale_E(E + (size_t)first_sh * 9, Es);
     }
     __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const unsigned long long amax = *reinterpret_cast<volatile unsigned long long*>(w + W_AMAX);
-    const int first = (int)(0xFFFFFFFFu - (uint32_t)(amax & 0xFFFFFFFFull));
-    const int m = w[W_M];
-    if (threadIdx.x == 0) scale_E(E + (size_t)first * 9, Es);
-    __syncthreads();
-    float e[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) e[i] = Es[i];
+    const int first = first_sh;
     int cnt = 0;
-    // four correspondences in flight per thread: the loop is a chain of L2 round trips otherwise
-    for (int c = threadIdx.x; c < m; c += 4 * AP_THREADS) {
-        float4 l[4], r[4];
+    if (first >= 0) {
+        float e[9];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int cu = c + u * AP_THREADS;
-            l[u] = cu < m ? l4[cu] : make_float4(0.f, 0.f, 0.f, 0.f);
-            r[u] = cu < m ? r4[cu] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < 9; i++) e[i] = Es[i];
+        // four correspondences in flight per thread: the loop is a chain of L2 round trips otherwise
+        for (int c = threadIdx.x; c < m; c += 4 * AP_THREADS) {
+            float4 l[4], r[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            float k[9];
-            kron9(l[u], r[u], k);
-            cnt += (c + u * AP_THREADS < m && inlier<ERP_METRIC_ALGEBRAIC>(e, k, l[u], r[u], tau, 0.f, 0.f)) ? 1 : 0;
+            for (int u = 0; u < 4; u++) {
+                const int cu = c + u * AP_THREADS;
+                l[u] = cu < m ? l4[cu] : make_float4(0.f, 0.f, 0.f, 0.f);
+                r[u] = cu < m ? r4[cu] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float k[9];
+                kron9(l[u], r[u], k);
+                cnt += (c + u * AP_THREADS < m && inlier<ERP_METRIC_ALGEBRAIC>(e, k, l[u], r[u], tau, 0.f, 0.f)) ? 1 : 0;
+            }
         }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) wsum[wid] = cnt;
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    int lstar = 0;
-    for (int i = 0; i < AP_THREADS / 32; i++) lstar += wsum[i];
-    w[W_LSTAR] = lstar; w[W_FIRST] = first;
-    if (H > 0) atomicMax(best, ((unsigned long long)(uint32_t)lstar << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(hyp0 + (unsigned long long)first)));
+    if (threadIdx.x == 0) {
+        int exact = 0;
+        for (int i = 0; i < AP_THREADS / 32; i++) exact += wsum[i];
+        if (first >= 0) {
+            atomicMax(best, ((unsigned long long)(uint32_t)exact << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)(hyp0 + (unsigned long long)first)));
+            atomicMax(w + W_LSTAR, exact);
+        }
+        __threadfence();
+        last = atomicAdd(w + W_DONE, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    const int lstar = *reinterpret_cast<volatile int32_t*>(w + W_LSTAR);
     // pass B extends the bounds to tile ct1: far enough that a hypothesis with nothing so far can no longer reach L*
     // (correspondences a discarded hypothesis may still be missing: m - seen < L*  <=>  seen > m - L*)
     const int n0 = w[W_N0], n_ct = w[W_NCT];

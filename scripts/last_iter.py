@@ -14,7 +14,7 @@ for f in sys.argv[1:]:
         v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(r[iU], v)
         out.append((r[iN][:60], v))
     idx = [i for i, (n, v) in enumerate(out) if "round_kernel" in n]
-    start = idx[-2] if len(idx) >= 2 else 0
+    start = idx[-1] if idx else 0
     print(f, "last iteration:")
     tot = 0
     for n, v in out[start:]:
