@@ -86,6 +86,58 @@ def test_group_match_with_cross_check_min_reduce(single, G, dim):
         assert few.tobytes() == O.match(q[:3], t, -1.0, True).tobytes()
 
 
+@pytest.mark.parametrize("peer", ["1", "0"])
+@pytest.mark.timeout(600)
+def test_one_process_per_gpu_clique_equals_single_gpu(single, tmp_path, peer):
+    """The torchrun layout (one process per GPU, erp_comm_init): peer windows mapped with cudaIpc (peer = 1) or NCCL
+    collectives (peer = 0).  Rank 0's records, winner, mask and refit equal the single-GPU call bit for bit."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    G = min(n_devices(), 8)
+    if G < 2:
+        pytest.skip("2 devices needed")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = tmp_path / "mp.npz"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ERP_B200_PEER=peer)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={G}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "tests", "mp_worker.py"), str(out)],
+                       capture_output=True, text=True, timeout=540, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    z = np.load(out)
+    for tag, (nq, nt, H, cross, seed) in {"tc": (6001, 7003, 60001, False, 41), "cross": (6001, 7003, 60001, True, 41), "simt": (1501, 1999, 2049, False, 43)}.items():
+        q, t, left, right = scene_pair(nq, nt, 64, 4096, 2048, seed)
+        wm, want = single.pair_pose(q, t, left, right, 4096, 2048, ratio=0.3, cross_check=cross, seed=7, H=H)
+        assert z[tag + "_matches"].tobytes() == wm.tobytes() == z[tag + "_parts"].tobytes()
+        assert int(z[tag + "_packed"]) == want["packed"]
+        assert np.array_equal(z[tag + "_mask"], want["mask"]) and np.array_equal(z[tag + "_E_refit"], want["E_refit"])
+
+
+def test_dropin_classes_fan_out_over_erp_b200_devices(tmp_path):
+    """The C++ classes with $ERP_B200_DEVICES naming several GPUs: feature_matcher::match_two_image splits the query
+    rows inside the call (erp_group); the driver's output file equals the one-GPU run byte for byte."""
+    import os
+    import subprocess
+    import test_host_dropin as hd
+    if n_devices() < 2:
+        pytest.skip("2 devices needed")
+    hd._build()
+    q, t, lxy, rxy, W, H = hd._scene()
+    inp = tmp_path / "in.bin"
+    hd._write_input(inp, q, t, lxy, rxy, W, H)
+    outs = []
+    for devs in ("0", ",".join(str(i) for i in range(min(n_devices(), 4)))):
+        out = tmp_path / ("out_%d.bin" % len(devs))
+        r = subprocess.run([hd.EXE, str(inp), str(out)], capture_output=True, text=True, timeout=300, env=dict(os.environ, ERP_B200_DEVICES=devs))
+        assert r.returncode == 0, r.stderr
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1]
+
+
 def test_pair_pose_dev_keeps_the_match_count_on_the_device(single):
     """erp_pair_pose (one call, no host synchronisation between matcher and pose) against the oracle end to end."""
     q, t, left, right = scene_pair(5000, 6000, 64, 4096, 2048, 61)
