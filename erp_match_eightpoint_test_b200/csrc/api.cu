@@ -273,7 +273,7 @@ ERP_API int erp_ctx_last_score_stats(erp_ctx* ctx, int64_t out[6])
     for (int i = 0; i < 6; i++) out[i] = 0;
     if (!ctx->sc_misc_dev) return ERP_OK;
     DeviceGuard g(ctx->device);
-    int32_t w[24];
+    int32_t w[W_WORDS];
     ERP_CUDA(cudaMemcpyAsync(w, ctx->sc_misc_dev, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
     ERP_CUDA(cudaStreamSynchronize(ctx->stream));
     out[0] = w[W_DYN_A];       // hypotheses of the chunk

@@ -205,16 +205,16 @@ int knn2_exact_rescan(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, 
 // final result copy waits for the host
 constexpr int RANSAC_CHUNK = 1 << 20;
 struct ScoreTcBuffers { float *Es, *Es2, *Ks; int32_t *w, *upper, *list; };
-struct Min8Fused { float* Es = nullptr; float big = 0.f; int32_t* upper = nullptr; int32_t* w = nullptr; };
+struct Min8Fused { float* Es = nullptr; float big = 0.f; int32_t* upper = nullptr; int32_t* w = nullptr; int metric = 0; float tau = 0.f, sin_tau = 0.f; };
 int score_tc_buffers(erp_ctx* ctx, int H, int m_cap, ScoreTcBuffers* b);
 int score_tc_prepare(erp_ctx* ctx, const ScoreTcBuffers& b, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m);
 int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap,
-                    float tau, uint64_t hyp0, bool es_ready, int32_t* d_counts_scratch, uint64_t* d_best);
+                    int metric, float tau, uint64_t hyp0, bool es_ready, int32_t* d_counts_scratch, uint64_t* d_best);
 float score_tc_big(float tau);
 int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau,
                   uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best);
 int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,
-                    const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau, uint64_t hyp0,
+                    const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, int metric, float tau, uint64_t hyp0,
                     int32_t* d_counts, uint64_t* d_best);
 bool score_tc_preferred(int H, int m);
 bool ransac_uses_tc(erp_ctx* ctx, int H, int m_cap, int metric);
@@ -225,7 +225,7 @@ int ransac_finish(erp_ctx* ctx, const double* d_l3, const double* d_r3, const fl
                   const int32_t* d_m, uint64_t seed, const uint64_t* d_packed, int S, int metric, float tau,
                   uint8_t* d_mask, erp_ransac_result* d_result);
 struct PoseBuffers { double *l3, *r3; float *l4, *r4; uint8_t* mask; erp_ransac_result* res; };
-constexpr size_t W_WORDS_BYTES = 24 * sizeof(int32_t);     // == W_WORDS (score_common.cuh)
+constexpr size_t W_WORDS_BYTES = 28 * sizeof(int32_t);     // == W_WORDS (score_common.cuh)
 int pose_chain_buffers(erp_ctx* ctx, int m_cap, PoseBuffers* b);
 int pose_chain_tail(erp_ctx* ctx, const double* dl, const double* dr, const float* dl4, const float* dr4, int m_cap, const int32_t* d_m,
                     uint64_t seed, uint64_t hyp_offset, int H, int S, int metric, float tau, bool k_ready, bool reduce,

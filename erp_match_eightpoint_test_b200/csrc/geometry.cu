@@ -704,7 +704,9 @@ min8_kernel(const double* __restrict__ l3, const double* __restrict__ r3, int m_
     if (fused.Es) {
         float e[9];
         scale_E(Eout + (size_t)h * 9, e);
-        write_e_row(e, fused.big, fused.Es + (size_t)h * 32);
+        RowScale rs;
+        rs.metric = fused.metric; rs.tau = fused.tau; rs.sin_tau = fused.sin_tau;
+        write_e_row(e, fused.big, fused.Es + (size_t)h * 32, row_gain(e, rs, fused.w));
         fused.upper[h] = 0; fused.upper[(size_t)H + h] = 0;
     }
 }

@@ -289,11 +289,28 @@ int score_launch(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, cons
 
 // exact counts of the listed hypotheses, their packed best merged into *d_best by the same launch
 int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,
-                    const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau, uint64_t hyp0,
+                    const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, int metric, float tau, uint64_t hyp0,
                     int32_t* d_counts /* H_max + H_max / 128 + 1, scratch */, uint64_t* d_best)
 {
+    static_assert(SL_HYPS == TH, "one ticket per 128 hypotheses in both list kernels");
     const int tiles = cdiv(H_max, SL_HYPS);
     ERP_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * ((size_t)H_max + tiles), ctx->stream));
+    if (metric != ERP_METRIC_ALGEBRAIC) {
+        // Sampson / angular: the bound is looser, the list is long (thousands): score_kernel in list mode, hypothesis
+        // tiles x correspondence slices, the packed best merged by the last slice of a tile
+        float tau2, sin2;
+        thresholds(tau, tau2, sin2);
+        int msplit = max(1, min(cdiv(m_cap, SC_THREADS * 4), 24));
+        dim3 grid(min(tiles, 1024), msplit);
+        if (metric == ERP_METRIC_SAMPSON)
+            score_kernel<ERP_METRIC_SAMPSON, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m_cap, d_m, tau, tau2, sin2,
+                                                                                    d_counts, d_list, d_len, (unsigned long long*)d_best, (unsigned long long)hyp0, d_counts + H_max);
+        else
+            score_kernel<ERP_METRIC_ANGULAR, 4><<<grid, SC_THREADS, 0, ctx->stream>>>(d_E, H_max, (const float4*)d_l4, (const float4*)d_r4, m_cap, d_m, tau, tau2, sin2,
+                                                                                    d_counts, d_list, d_len, (unsigned long long*)d_best, (unsigned long long)hyp0, d_counts + H_max);
+        ERP_LAUNCH(ctx, "score_kernel(list)");
+        return ERP_OK;
+    }
     // the list is usually short (cfg3: ~900 contenders = 7 hypothesis tiles): tile x slice blocks of 128 threads
     // (score_kernel in list mode took 100 us for them, this kernel 20)
     dim3 grid(min(tiles, 32), max(1, cdiv(m_cap, SL_CORR)));
@@ -326,9 +343,9 @@ int mask_launch(erp_ctx* ctx, const double* d_E9, const float* d_l4, const float
 bool ransac_uses_tc(erp_ctx* ctx, int H, int m_cap, int metric)
 {
     const int n = H < RANSAC_CHUNK ? H : RANSAC_CHUNK;
-    return metric == ERP_METRIC_ALGEBRAIC &&
-           (ctx->engine == ERP_ENGINE_TCGEN05 || ctx->engine == ERP_ENGINE_TCGEN05_1X ||
-            (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m_cap)));
+    (void)metric;       // all three residuals: Sampson / angular through a per-hypothesis bound (score_common.cuh: row_gain)
+    return ctx->engine == ERP_ENGINE_TCGEN05 || ctx->engine == ERP_ENGINE_TCGEN05_1X ||
+           (ctx->engine == ERP_ENGINE_AUTO && score_tc_preferred(n, m_cap));
 }
 
 // Hypotheses [hyp_offset, hyp_offset + H): sample, solve, score, packed best into *d_packed (max-merged: the caller
@@ -353,6 +370,7 @@ int ransac_search(erp_ctx* ctx, const double* d_l3, const double* d_r3, const fl
         ERP_TRY(score_tc_buffers(ctx, chunk, m_cap, &b));
         if (!k_ready) ERP_TRY(score_tc_prepare(ctx, b, d_l4, d_r4, m_cap, d_m));
         fused.Es = b.Es; fused.big = score_tc_big(tau); fused.upper = b.upper; fused.w = b.w;
+        fused.metric = metric; fused.tau = tau; fused.sin_tau = (float)sin((double)tau);
     }
     for (int h0 = 0; h0 < H; h0 += CH) {
         int n = H - h0 < CH ? H - h0 : CH;
@@ -363,7 +381,7 @@ int ransac_search(erp_ctx* ctx, const double* d_l3, const double* d_r3, const fl
             ERP_TRY(gram_batch(ctx, d_l3, d_r3, m_cap, d_m, nullptr, n, S, seed, hyp_offset + h0, nullptr, G));
             ERP_TRY(solve_batch(ctx, G, n, E, nullptr));
         }
-        if (tc) ERP_TRY(score_tc_search(ctx, b, E, n, d_l4, d_r4, m_cap, tau, hyp_offset + h0, S == 8, counts, d_packed));
+        if (tc) ERP_TRY(score_tc_search(ctx, b, E, n, d_l4, d_r4, m_cap, metric, tau, hyp_offset + h0, S == 8, counts, d_packed));
         else {
             cudaEvent_t e0, e1;
             ERP_TRY(score_event(ctx, &e0));

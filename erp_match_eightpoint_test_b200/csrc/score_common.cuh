@@ -47,12 +47,13 @@ __device__ __forceinline__ void scale_E(const double* __restrict__ E, float* __r
 // One 128-byte row (32 floats) per hypothesis / correspondence carries the three 3xTF32 products of the 9-term dot:
 //     hypothesis     [ Eh_hi(9) | Eh_hi(9) | Eh_lo(9) | 0 x 5 ]   (times a power of two, see score_tc.cu)
 //     correspondence [ K_hi(9)  | K_lo(9)  | K_hi(9)  | 0 x 5 ]
-__device__ __forceinline__ void write_e_row(const float e[9], float big, float* __restrict__ row)
+__device__ __forceinline__ void write_e_row(const float e[9], float big, float* __restrict__ row, float gain = 1.f)
 {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        const float hi = tf32_rna(e[i]), lo = tf32_rna(__fsub_rn(e[i], hi));
+        const float eg = __fmul_rn(e[i], gain);
+        const float hi = tf32_rna(eg), lo = tf32_rna(__fsub_rn(eg, hi));
         v[i] = hi * big; v[9 + i] = hi * big; v[18 + i] = lo * big;       // exact: power of two
     }
 #pragma unroll
@@ -90,10 +91,11 @@ constexpr int SC_N0 = 8;          // tiles of pass A
 
 // int32 words every pass reads from device memory (no length of the search ever visits the host)
 enum ScoreWords {
-    W_KMAX = 0, W_M = 1, W_NCT = 2, W_N0 = 3,                // set once per call by the correspondence prep
-    W_AMAX = 4 /* 2 words */, W_DONE = 6, W_LEN1 = 7, W_LENF = 8, W_LSTAR = 9, W_REMAIN = 10, W_FIRST = 11,
-    W_DYN_A = 12, W_DYN_B = 16, W_DYN_C = 20,                // { rows of the A matrix, first tile, end tile, m }
-    W_WORDS = 24, W_CHUNK0 = 4                               // words [W_CHUNK0, W_WORDS) are reset per hypothesis chunk
+    // set once per call by the correspondence prep: max |l||r|, m, tiles, pass-A tiles, max (|l|^2 + |r|^2), max |r|^2 (float bits)
+    W_KMAX = 0, W_M = 1, W_NCT = 2, W_N0 = 3, W_RMAX = 4, W_RRMAX = 5,
+    W_AMAX = 6 /* 2 words */, W_DONE = 8, W_LEN1 = 9, W_LENF = 10, W_LSTAR = 11, W_REMAIN = 12,
+    W_DYN_A = 16, W_DYN_B = 20, W_DYN_C = 24,                // { rows of the A matrix, first tile, end tile, m }
+    W_WORDS = 28, W_CHUNK0 = 6                               // words [W_CHUNK0, W_WORDS) are reset per hypothesis chunk
 };
 static_assert(W_WORDS * sizeof(int32_t) == W_WORDS_BYTES, "common.cuh: W_WORDS_BYTES");
 
@@ -110,9 +112,46 @@ __device__ __forceinline__ void prep_k_slot(int c, int m, float4 l, float4 r, fl
     if (c < m) nrm = write_k_row(l, r, Ks + (size_t)c * 32);
     else if (c < ((m + SC_TILE - 1) / SC_TILE) * SC_TILE) zero_row(Ks + (size_t)c * 32);
     // non-negative floats (inf, NaN included) order like their bit patterns
-    unsigned b = __float_as_uint(nrm);
+    const float rr = c < m ? r.x * r.x + r.y * r.y + r.z * r.z : 0.f, ll = c < m ? l.x * l.x + l.y * l.y + l.z * l.z : 0.f;
+    unsigned b = __float_as_uint(nrm), b1 = __float_as_uint(ll + rr), b2 = __float_as_uint(rr);
     b = __reduce_max_sync(__activemask(), b);
-    if ((threadIdx.x & 31) == 0 && b > *reinterpret_cast<volatile unsigned*>(w + W_KMAX)) atomicMax(reinterpret_cast<unsigned*>(w + W_KMAX), b);
+    b1 = __reduce_max_sync(__activemask(), b1);
+    b2 = __reduce_max_sync(__activemask(), b2);
+    if ((threadIdx.x & 31) == 0) {
+        if (b > *reinterpret_cast<volatile unsigned*>(w + W_KMAX)) atomicMax(reinterpret_cast<unsigned*>(w + W_KMAX), b);
+        if (b1 > *reinterpret_cast<volatile unsigned*>(w + W_RMAX)) atomicMax(reinterpret_cast<unsigned*>(w + W_RMAX), b1);
+        if (b2 > *reinterpret_cast<volatile unsigned*>(w + W_RRMAX)) atomicMax(reinterpret_cast<unsigned*>(w + W_RRMAX), b2);
+    }
+}
+
+// Sampson and angular residual tests depend on the pair (h, c) through |E r|^2 and |E^T l|^2, which the residual GEMM
+// does not produce.  For the BOUND they are replaced by their maximum over unit-ish bearings:
+//     Sampson  res^2 < tau^2 (|E r|^2 + |E^T l|^2) <= tau^2 s1^2 (|r|^2 + |l|^2)    =>  |res| < T_h = tau  s1 sqrt(max_c (|l|^2 + |r|^2))
+//     angular  res^2 < sin^2(tau) |E r|^2          <= sin^2(tau) s1^2 |r|^2         =>  |res| < T_h = sin(tau) s1 sqrt(max_c |r|^2)
+// with s1 the largest singular value of the scaled E.  T_h is a per-HYPOTHESIS threshold: its operand row is scaled by
+// g_h = tau / max(T_h, tau) <= 1 and the kernel keeps its single threshold tau (+ band).  The count is then an upper
+// bound of the exact count (score_kernel / the oracle) -- looser than for the algebraic test, so more contenders are
+// re-scored exactly, but the winner is the same.  (1 + 1e-5) absorbs the fp32 roundings of the exact test.
+struct RowScale { int metric = ERP_METRIC_ALGEBRAIC; float tau = 0.f, sin_tau = 0.f; };
+__device__ __forceinline__ float row_gain(const float e[9], const RowScale& rs, const int32_t* __restrict__ w)
+{
+    if (rs.metric == ERP_METRIC_ALGEBRAIC) return 1.f;
+    double m[6] = {0, 0, 0, 0, 0, 0};                        // E^T E, upper triangle
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double a = e[3 * i], b = e[3 * i + 1], c = e[3 * i + 2];
+        m[0] += a * a; m[1] += a * b; m[2] += a * c; m[3] += b * b; m[4] += b * c; m[5] += c * c;
+    }
+    const double t = m[0] + m[3] + m[5];
+    const double c1 = (m[0] * m[3] - m[1] * m[1]) + (m[0] * m[5] - m[2] * m[2]) + (m[3] * m[5] - m[4] * m[4]);
+    const double disc = t * t - 4.0 * c1;
+    // largest eigenvalue of a rank-2 E^T E; the Frobenius bound t covers everything else (NaN included)
+    double s1sq = 0.5 * (t + sqrt(disc > 0.0 ? disc : 0.0)) * (1.0 + 1e-6) + 1e-9 * t;
+    if (!(s1sq < t)) s1sq = t;
+    const float R = __uint_as_float((unsigned)w[rs.metric == ERP_METRIC_SAMPSON ? W_RMAX : W_RRMAX]);
+    const double T = (double)(rs.metric == ERP_METRIC_SAMPSON ? rs.tau : rs.sin_tau) * sqrt(s1sq * (double)R) * (1.0 + 1e-5);
+    if (!(T < (double)INFINITY)) return 0.f;                 // non-finite input: residual 0, always counted
+    return T > (double)rs.tau ? (float)((double)rs.tau / T) : 1.f;
 }
 
 } // namespace erp

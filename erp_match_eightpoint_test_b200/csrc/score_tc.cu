@@ -51,14 +51,14 @@ constexpr float S_KAPPA = 1.0f / 65536.0f;
 // row i of Es = split scaled E of hypothesis i; also clears the two bound arrays and publishes pass A's shape
 // (the minimal-sample solver does the same in its own epilogue, geometry.cu: min8_kernel)
 __global__ void prep_e_kernel(const double* __restrict__ E, int H, float* __restrict__ Es /* H x 32 */, float big,
-                              int32_t* __restrict__ upper /* 2 x H */, int32_t* __restrict__ w)
+                              int32_t* __restrict__ upper /* 2 x H */, int32_t* __restrict__ w, const RowScale rs)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h == 0) { w[W_DYN_A] = H; w[W_DYN_A + 1] = 0; w[W_DYN_A + 2] = w[W_N0]; w[W_DYN_A + 3] = w[W_M]; }
     if (h >= H) return;
     float e[9];
     scale_E(E + (size_t)h * 9, e);
-    write_e_row(e, big, Es + (size_t)h * 32);
+    write_e_row(e, big, Es + (size_t)h * 32, row_gain(e, rs, w));
     upper[h] = 0; upper[(size_t)H + h] = 0;
 }
 
@@ -333,9 +333,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant
 // them, so L* is at least what scoring that one alone would give -- and merges its packed (count, ~id) into *best
 // like any other exact count.  The last block to finish takes the maximum and plans passes B and C.
 constexpr int AP_THREADS = 1024;
+template <int METRIC>
 __global__ void __launch_bounds__(AP_THREADS)
 argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__ E, const float4* __restrict__ l4,
-                   const float4* __restrict__ r4, float tau, unsigned long long hyp0, int32_t* __restrict__ w,
+                   const float4* __restrict__ r4, float tau, float tau2, float sin2, unsigned long long hyp0, int32_t* __restrict__ w,
                    unsigned long long* __restrict__ best)
 {
     __shared__ unsigned long long wbest[AP_THREADS / 32];
@@ -378,7 +379,7 @@ argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__
             for (int u = 0; u < 4; u++) {
                 float k[9];
                 kron9(l[u], r[u], k);
-                cnt += (c + u * AP_THREADS < m && inlier<ERP_METRIC_ALGEBRAIC>(e, k, l[u], r[u], tau, 0.f, 0.f)) ? 1 : 0;
+                cnt += (c + u * AP_THREADS < m && inlier<METRIC>(e, k, l[u], r[u], tau, tau2, sin2)) ? 1 : 0;
             }
         }
     }
@@ -509,13 +510,17 @@ int score_tc_prepare(erp_ctx* ctx, const ScoreTcBuffers& b, const float* d_l4, c
 // in place (score_tc_prepare, or the fused gather of geometry.cu) and the per-chunk words are clear; es_ready: the
 // hypothesis operand and the cleared bounds are in place too (min8_kernel wrote them).
 int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap,
-                    float tau, uint64_t hyp0, bool es_ready, int32_t* d_counts_scratch, uint64_t* d_best)
+                    int metric, float tau, uint64_t hyp0, bool es_ready, int32_t* d_counts_scratch, uint64_t* d_best)
 {
     const float big = score_tc_big(tau);
+    const double sd = sin((double)tau);
+    const float tau2 = tau * tau, sin2 = (float)(sd * sd);
+    RowScale rs;
+    rs.metric = metric; rs.tau = tau; rs.sin_tau = (float)sd;
     int32_t* w = b.w;
     int32_t *upper = b.upper, *upper2 = b.upper + H, *survivors = b.list, *contenders = b.list + H;
     if (!es_ready) {
-        prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, b.Es, big, upper, w);
+        prep_e_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_E, H, b.Es, big, upper, w, rs);
         ERP_LAUNCH(ctx, "prep_e_kernel");
     }
     CUtensorMap me, me2, mk;
@@ -528,9 +533,15 @@ int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, in
     // pass A: every hypothesis, the first n0 correspondence tiles
     p.dyn = w + W_DYN_A; p.upper = upper;
     ERP_TRY(launch_score_tc(ctx, me, mk, p));
-    argmax_plan_kernel<<<min(cdiv(H, AP_THREADS), ctx->sm_count), AP_THREADS, 0, ctx->stream>>>(
-        upper, d_E, (const float4*)d_l4, (const float4*)d_r4, tau, (unsigned long long)hyp0, w, (unsigned long long*)d_best);
-    ERP_LAUNCH(ctx, "argmax_plan_kernel");
+    {
+        const int grid = min(cdiv(H, AP_THREADS), ctx->sm_count);
+        const float4 *l4 = (const float4*)d_l4, *r4 = (const float4*)d_r4;
+        unsigned long long* bp = (unsigned long long*)d_best;
+        if (metric == ERP_METRIC_ALGEBRAIC) argmax_plan_kernel<ERP_METRIC_ALGEBRAIC><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp);
+        else if (metric == ERP_METRIC_SAMPSON) argmax_plan_kernel<ERP_METRIC_SAMPSON><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp);
+        else argmax_plan_kernel<ERP_METRIC_ANGULAR><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp);
+        ERP_LAUNCH(ctx, "argmax_plan_kernel");
+    }
     // pass B: every hypothesis, tiles [n0, ct1)
     p.dyn = w + W_DYN_B;
     ERP_TRY(launch_score_tc(ctx, me, mk, p));
@@ -542,7 +553,7 @@ int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, in
     final_select_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(upper, upper2, survivors, w, contenders);
     ERP_LAUNCH(ctx, "final_select_kernel");
     ctx->sc_misc_dev = w;
-    return score_list_best(ctx, d_E, H, contenders, w + W_LENF, d_l4, d_r4, m_cap, w + W_M, tau, hyp0, d_counts_scratch, d_best);
+    return score_list_best(ctx, d_E, H, contenders, w + W_LENF, d_l4, d_r4, m_cap, w + W_M, metric, tau, hyp0, d_counts_scratch, d_best);
 }
 
 // stand-alone form (arbitrary E matrix, host or device m)
@@ -552,7 +563,7 @@ int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, con
     ScoreTcBuffers b;
     ERP_TRY(score_tc_buffers(ctx, H, m_cap, &b));
     ERP_TRY(score_tc_prepare(ctx, b, d_l4, d_r4, m_cap, d_m));
-    return score_tc_search(ctx, b, d_E, H, d_l4, d_r4, m_cap, tau, hyp0, false, d_counts_scratch, d_best);
+    return score_tc_search(ctx, b, d_E, H, d_l4, d_r4, m_cap, ERP_METRIC_ALGEBRAIC, tau, hyp0, false, d_counts_scratch, d_best);
 }
 
 } // namespace erp

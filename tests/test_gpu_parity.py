@@ -301,35 +301,41 @@ def test_host_call_with_query_chunks_equals_single_call(tmp_path):
                                       (1500, 100, 0.002), (40000, 2500, 0.0005),
                                       # the power-of-two scaling of the counting epilogue at both ends of its range
                                       (3000, 3000, 0.5), (2000, 1000, 4.0), (3000, 3000, 1e-9)])
-def test_tensor_core_best_search_is_exact(ctx, scene, H, m, tau):
+@pytest.mark.parametrize("metric", [0, 1, 2])
+def test_tensor_core_best_search_is_exact(ctx, scene, H, m, tau, metric):
     """score_tc.cu bounds every hypothesis' inlier count with a 3xTF32 residual GEMM and re-scores the
     contenders exactly: winner, count (the packed word) and inlier mask must equal the all-SIMT path
-    and the oracle, also when residuals crowd the threshold or tau is below the band width."""
+    and the oracle, also when residuals crowd the threshold or tau is below the band width.  Sampson (1) and
+    angular (2) residuals go through a per-hypothesis bound (tau s1 sqrt(max(|l|^2 + |r|^2)), sin(tau) s1 max|r|)."""
     kp, l, r = scene
     rng = np.random.default_rng(H + m)
     ll = np.concatenate([l, l[rng.integers(0, len(l), max(0, m - len(l)))]])[:m]
     rr = np.concatenate([r, r[rng.integers(0, len(r), max(0, m - len(r)))]])[:m]
+    if metric and tau > 1.0:
+        tau = 1.0                                           # an angle: sin(tau) stops growing at pi / 2
     ctx.set_engine(binding.ENGINE_EXACT_SIMT)
-    simt = ctx.ransac(ll, rr, seed=4, hyp_offset=10, H=H, S=8, metric=0, tau=tau)
+    simt = ctx.ransac(ll, rr, seed=4, hyp_offset=10, H=H, S=8, metric=metric, tau=tau)
     ctx.set_engine(binding.ENGINE_TCGEN05)
-    tc = ctx.ransac(ll, rr, seed=4, hyp_offset=10, H=H, S=8, metric=0, tau=tau)
+    tc = ctx.ransac(ll, rr, seed=4, hyp_offset=10, H=H, S=8, metric=metric, tau=tau)
     ctx.set_engine(binding.ENGINE_AUTO)
     assert tc["packed"] == simt["packed"]
     assert np.array_equal(tc["mask"], simt["mask"]) and tc["count"] == simt["count"]
     if H * m <= 2 * 10 ** 6:
-        assert tc["packed"] == O.ransac(ll, rr, seed=4, hyp0=10, H=H, S=8, metric=0, tau=tau)["packed"]
+        assert tc["packed"] == O.ransac(ll, rr, seed=4, hyp0=10, H=H, S=8, metric=metric, tau=tau)["packed"]
 
 
 @pytest.mark.parametrize("m,outliers,H", [(20000, 0.3, 30000), (20000, 0.85, 30000), (6000, 0.5, 50000), (2048, 0.3, 20000)])
-def test_tensor_core_best_search_with_pruning(ctx, m, outliers, H):
+@pytest.mark.parametrize("metric", [0, 1, 2])
+def test_tensor_core_best_search_with_pruning(ctx, m, outliers, H, metric):
     """Three-pass progressive pruning (bounds on a prefix, exact L*, survivors only for the rest): the
-    winner must not depend on it, for high and low inlier ratios (pruning switches itself off)."""
+    winner must not depend on it, for high and low inlier ratios (pruning switches itself off), for all three residuals."""
     kp = synth.keypoint_pair(m, 8192, 4096, outlier_frac=outliers, seed=m + H)
     l, r = O.bearings(kp["left_xy"], 8192, 4096), O.bearings(kp["right_xy"], 8192, 4096)
     ctx.set_engine(binding.ENGINE_EXACT_SIMT)
-    simt = ctx.ransac(l, r, seed=9, hyp_offset=0, H=H, S=8, metric=0, tau=0.002)
+    simt = ctx.ransac(l, r, seed=9, hyp_offset=0, H=H, S=8, metric=metric, tau=0.002)
     ctx.set_engine(binding.ENGINE_TCGEN05)
-    tc = ctx.ransac(l, r, seed=9, hyp_offset=0, H=H, S=8, metric=0, tau=0.002)
+    tc = ctx.ransac(l, r, seed=9, hyp_offset=0, H=H, S=8, metric=metric, tau=0.002)
+    print("metric %d: search stats %s" % (metric, ctx.last_score_stats()))
     ctx.set_engine(binding.ENGINE_AUTO)
     assert tc["packed"] == simt["packed"] and tc["count"] == simt["count"]
     assert np.array_equal(tc["mask"], simt["mask"])
