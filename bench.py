@@ -247,7 +247,7 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "2nn_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tm + tr) / args.steps, "higher_is_better": True,
         "scaling": scaling_of(args), "vs_baseline": None, "dtype": "f32 data, f64 accumulate", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "engine": "CPU oracle port of the reference path (OpenMP)", "sample": s["sample"]},
+        "config": workload_config(cfg), "run": {"engine": "CPU oracle port of the reference path (OpenMP)", "sample": s["sample"]},
         "ransac_hyps_per_s": hyps_s,
         "cpu_baseline": {"value": value, "unit": "dist-evals/s", "cores": s["cores"], "kind": "port", "sample": s["sample"],
                          "ransac_hyps_per_s": hyps_s},
@@ -258,6 +258,16 @@ def run_reference(args, cfg):
 
 def scaling_of(args):
     return args.scaling or "strong"
+
+
+def workload_config(cfg):
+    """What defines the workload -- identical in both arms (the driver compares `config`); how an arm ran it (engine,
+    sharding, the CPU arm's bounded sample) goes under `run`."""
+    c = {"workload": cfg["desc"], "nq": cfg["nq"], "nt": cfg["nt"], "dim": cfg["dim"], "hyps": cfg["hyps"], "cross_check": cfg["cross"],
+         "ratio": RATIO, "tau": TAU, "sample_size": SAMPLE, "image": [cfg["W"], cfg["H"]]}
+    if "pairs" in cfg:
+        c["pairs"] = cfg["pairs"]
+    return c
 
 
 # --------------------------------------------------------------------------------------------
@@ -542,10 +552,10 @@ def run_pair(args, cfg, rig):
         "dtype": ("f32 data; TF32 tiles (certified) + f64 exact refine" if engine == "tcgen05_1xtf32" else
                   "f32 data; 3xTF32 tiles + f64 refine" if engine.startswith("tcgen05") else "f32 data; f64 direct-form accumulate"),
         "data": "synthetic",
-        "config": {"workload": cfg["desc"], "engine": engine, "nq_per_gpu": nq, "nt": nt, "dim": dim,
-                   "hyps_per_gpu": hyps_rank, "correspondences": m, "sample_size": SAMPLE, "ratio": RATIO, "tau": TAU,
-                   "l2": "flushed between timed steps (256 MiB write)", "sharding": sharding,
-                   "api": "erp_pair_pose_dist_dev" if strong else "erp_pair_pose_dev"},
+        "config": workload_config(cfg),
+        "run": {"engine": engine, "nq_per_gpu": nq, "hyps_per_gpu": hyps_rank, "correspondences": m,
+                "l2": "flushed between timed steps (256 MiB write)", "sharding": sharding,
+                "api": "erp_pair_pose_dist_dev" if strong else "erp_pair_pose_dev"},
         "match_ms": t_match / args.steps, "exchange_gather_ms": t_xchg / args.steps, "ransac_ms": t_ransac / args.steps,
         "ransac_hyps_per_s": args.steps * hyps_total / (t_ransac * 1e-3),
         "step_dist_evals_per_s": args.steps * units / (t_step * 1e-3),
@@ -656,11 +666,11 @@ def run_match(args, cfg, rig):
         "metric": "2nn_dist_evals_per_s", "value": args.steps * units / (t_match * 1e-3), "unit": "dist-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_match / args.steps, "higher_is_better": True,
         "scaling": scaling_of(args), "vs_baseline": None, "dtype": "f32 data; TF32 tiles (certified) + f64 exact refine", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "engine": engine, "nq_per_gpu": nq, "nt": nt, "dim": dim, "ratio": RATIO, "cross_check": True,
-                   "l2": "flushed between timed steps (256 MiB write)",
-                   "sharding": ("query rows per rank; per-train nearest query: ncclAllReduce(min) of d2, then of the query id"
-                                if strong else ("one GPU" if world == 1 else "one descriptor set pair per rank, no collective")),
-                   "dist_evals": "forward + reverse search = 2 x nq x nt per step", "api": "erp_knn2_match_dist_dev"},
+        "config": workload_config(cfg),
+        "run": {"engine": engine, "nq_per_gpu": nq, "l2": "flushed between timed steps (256 MiB write)",
+                "sharding": ("query rows per rank; per-train nearest query: ncclAllReduce(min) of d2, then of the query id"
+                             if strong else ("one GPU" if world == 1 else "one descriptor set pair per rank, no collective")),
+                "dist_evals": "forward + reverse search = 2 x nq x nt per step", "api": "erp_knn2_match_dist_dev"},
         "match_ms": t_match / args.steps, "roofline": roof,
         "e2e": {"value": units * e2e_steps / t_e2e, "unit": "dist-evals/s", "h2d_bytes_per_step": int((pq.nbytes + pt.nbytes) * share),
                 "d2h_bytes_per_step": int(len(mt) * 16 + 4), "match_ms": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
@@ -759,11 +769,11 @@ def run_video(args, cfg, rig):
         "metric": "2nn_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 data; TF32 tiles (certified) + f64 exact refine", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "engine": engine, "pairs": pairs, "pairs_per_gpu": len(mine), "distinct_pairs_cycled": cfg["distinct"],
-                   "nq": cfg["nq"], "nt": cfg["nt"], "dim": cfg["dim"], "hyps_per_pair": cfg["hyps"], "host_threads_per_gpu": n_threads,
-                   "l2": "inputs stream from pinned host memory: every pair is a fresh 10.6 MB upload",
-                   "sharding": "frame pairs round-robin per rank, no collective; every call moves its inputs from host memory, so "
-                               "value and e2e coincide"},
+        "config": workload_config(cfg),
+        "run": {"engine": engine, "pairs_per_gpu": len(mine), "distinct_pairs_cycled": cfg["distinct"], "host_threads_per_gpu": n_threads,
+                "l2": "inputs stream from pinned host memory: every pair is a fresh 10.6 MB upload",
+                "sharding": "frame pairs round-robin per rank, no collective; every call moves its inputs from host memory, so "
+                            "value and e2e coincide"},
         "pairs_per_s": args.steps * pairs / (t_ms * 1e-3), "ms_per_pair": t_ms / args.steps / len(mine),
         "ransac_hyps_per_s": args.steps * pairs * cfg["hyps"] / (t_ms * 1e-3),
         "roofline": roof, "e2e": e2e, "gpu_launches": int(launches_all), "clocks": clocks, "cpu_baseline": cpu,
