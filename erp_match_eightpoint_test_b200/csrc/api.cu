@@ -206,9 +206,9 @@ ERP_API void erp_ctx_destroy(erp_ctx* ctx)
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     for (cudaEvent_t e : ctx->ev_stage) if (e) cudaEventDestroy(e);
+    comm_release(ctx);
     graph_release(ctx);
     stage_release(ctx);
-    comm_release(ctx);
     for (cudaEvent_t e : ctx->ev_score) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

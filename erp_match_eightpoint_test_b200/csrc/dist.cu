@@ -129,6 +129,7 @@ static void window_close(Comm* c)
 void comm_release(erp_ctx* ctx)
 {
     if (!ctx->comm) return;
+    graph_release(ctx);                  // a cached graph holds this clique's communicator and window pointers
     Comm* c = ctx->comm;
     window_close(c);
     if (c->win) cudaFree(c->win);

@@ -138,6 +138,28 @@ def test_dropin_classes_fan_out_over_erp_b200_devices(tmp_path):
     assert outs[0] == outs[1]
 
 
+def test_graph_cache_follows_the_arguments(single):
+    """The device-resident pair call is captured into a CUDA graph on its second use and replayed afterwards; a call with
+    other arguments (seed, hypotheses, metric, sizes) must never replay a stale graph.  Interleaved calls against the oracle."""
+    q, t, left, right = scene_pair(3000, 3500, 64, 4096, 2048, 71)
+    om = O.match(q, t, 0.3, False)
+    l, r = O.bearings(left[om["queryIdx"]], 4096, 2048), O.bearings(right[om["trainIdx"]], 4096, 2048)
+    q2, t2, left2, right2 = scene_pair(2000, 3500, 64, 4096, 2048, 72)
+    om2 = O.match(q2, t2, 0.3, False)
+    l2, r2 = O.bearings(left2[om2["queryIdx"]], 4096, 2048), O.bearings(right2[om2["trainIdx"]], 4096, 2048)
+    want = {}
+    for key, (seed, H, metric) in {"a": (5, 3000, 0), "b": (6, 3000, 0), "c": (5, 4000, 1)}.items():
+        want[key] = O.ransac(l, r, seed=seed, hyp0=0, H=H, metric=metric)["packed"]
+    want["d"] = O.ransac(l2, r2, seed=5, hyp0=0, H=3000)["packed"]
+    args = {"a": (q, t, left, right, 5, 3000, 0), "b": (q, t, left, right, 6, 3000, 0), "c": (q, t, left, right, 5, 4000, 1),
+            "d": (q2, t2, left2, right2, 5, 3000, 0)}
+    for key in "aaabbacccaddaab":
+        qq, tt, ll, rr, seed, H, metric = args[key]
+        m, res = single.pair_pose(qq, tt, ll, rr, 4096, 2048, ratio=0.3, seed=seed, H=H, metric=metric)
+        assert res["packed"] == want[key], key
+        assert m.tobytes() == (om2 if key == "d" else om).tobytes()
+
+
 def test_pair_pose_dev_keeps_the_match_count_on_the_device(single):
     """erp_pair_pose (one call, no host synchronisation between matcher and pose) against the oracle end to end."""
     q, t, left, right = scene_pair(5000, 6000, 64, 4096, 2048, 61)
