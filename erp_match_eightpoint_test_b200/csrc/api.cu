@@ -407,9 +407,8 @@ ERP_API int erp_knn2_match_dev(erp_ctx* ctx, const float* d_q, int nq, const flo
 // Host-buffer 2-NN: the train set and the first query chunk are uploaded, then every further query chunk travels
 // (on its own stream) while the previous one is searched.  Rows are independent, so the result does not depend on
 // the cut; the train-side operands are prepared by the first chunk only.  Chunks: $ERP_B200_HOST_CHUNKS (1..7).
-// Measured on cfg3 (100k x 100k, pinned source): 1 chunk 3.85 ms, 2 chunks 3.90, 4 chunks 4.27, 6 chunks 6.07 -- the
-// shorter per-chunk kernels (more list segments per row, more tails) lose more than the hidden copy gains, so the
-// default is ONE chunk and the knob stays for larger query sets / slower links.
+// Round 1 measured chunking as a loss on cfg3 (1 chunk 3.85 ms, 2 chunks 3.90, 4 chunks 4.27: shorter kernels, more list
+// segments per row, more tails); with round 2's finer segments and threshold exchange three chunks win for large inputs.
 static int host_chunks(int nq, int nt)
 {
     static int forced = -1;
@@ -419,8 +418,9 @@ static int host_chunks(int nq, int nt)
         if (forced < 0 || forced > 7) forced = 0;
     }
     if (forced) return forced;
-    (void)nq; (void)nt;
-    return 1;
+    // round 2 (eight segments per query row + threshold exchange keep short chunks efficient): 100k x 100k from pinned
+    // memory 3.42 ms with one chunk, 3.32 / 3.24 / 3.35 with 2 / 3 / 4 (scripts/e2e_chunks.py); small inputs: one chunk
+    return (double)nq * (double)nt >= 4.0e9 ? 3 : 1;
 }
 static int knn2_host(erp_ctx* ctx, const float* q, int nq, size_t qs, const float* t, int nt, size_t ts, int dim,
                      int32_t* d_idx2, float* d_dist2)
