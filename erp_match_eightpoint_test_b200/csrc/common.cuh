@@ -211,8 +211,6 @@ int score_tc_prepare(erp_ctx* ctx, const ScoreTcBuffers& b, const float* d_l4, c
 int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap,
                     int metric, float tau, uint64_t hyp0, bool es_ready, int32_t* d_counts_scratch, uint64_t* d_best);
 float score_tc_big(float tau);
-int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau,
-                  uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best);
 int score_list_best(erp_ctx* ctx, const double* d_E, int H_max, const int32_t* d_list, const int32_t* d_len,
                     const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, int metric, float tau, uint64_t hyp0,
                     int32_t* d_counts, uint64_t* d_best);

@@ -93,7 +93,7 @@ constexpr int SC_N0 = 8;          // tiles of pass A
 enum ScoreWords {
     // set once per call by the correspondence prep: max |l||r|, m, tiles, pass-A tiles, max (|l|^2 + |r|^2), max |r|^2 (float bits)
     W_KMAX = 0, W_M = 1, W_NCT = 2, W_N0 = 3, W_RMAX = 4, W_RRMAX = 5,
-    W_AMAX = 6 /* 2 words */, W_DONE = 8, W_LEN1 = 9, W_LENF = 10, W_LSTAR = 11, W_REMAIN = 12,
+    W_AMAX = 6 /* 2 words */, W_DONE = 8, W_LENF = 10, W_LSTAR = 11, W_REMAIN = 12,
     W_DYN_A = 16, W_DYN_B = 20, W_DYN_C = 24,                // { rows of the A matrix, first tile, end tile, m }
     W_WORDS = 28, W_CHUNK0 = 6                               // words [W_CHUNK0, W_WORDS) are reset per hypothesis chunk
 };

@@ -556,14 +556,4 @@ int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, in
     return score_list_best(ctx, d_E, H, contenders, w + W_LENF, d_l4, d_r4, m_cap, w + W_M, metric, tau, hyp0, d_counts_scratch, d_best);
 }
 
-// stand-alone form (arbitrary E matrix, host or device m)
-int score_tc_best(erp_ctx* ctx, const double* d_E, int H, const float* d_l4, const float* d_r4, int m_cap, const int32_t* d_m, float tau,
-                  uint64_t hyp0, int32_t* d_counts_scratch, uint64_t* d_best)
-{
-    ScoreTcBuffers b;
-    ERP_TRY(score_tc_buffers(ctx, H, m_cap, &b));
-    ERP_TRY(score_tc_prepare(ctx, b, d_l4, d_r4, m_cap, d_m));
-    return score_tc_search(ctx, b, d_E, H, d_l4, d_r4, m_cap, ERP_METRIC_ALGEBRAIC, tau, hyp0, false, d_counts_scratch, d_best);
-}
-
 } // namespace erp

@@ -81,3 +81,24 @@ def test_sample_table_argument_errors():
     with pytest.raises(erp.ErpError) as ei:
         erp.libstdcxx_sample_table(10, 2, 11)
     assert ei.value.status == binding.E_ARG
+
+
+def test_shard_range_is_the_python_helper():
+    """erp_shard_range (what the library cuts query rows and hypothesis ids with) == sharding.shard_range (what the gloo
+    tests of the host logic use): contiguous, ordered, sizes differing by at most one."""
+    from erp_match_eightpoint_test_b200 import sharding
+    for n in (0, 1, 7, 100, 100003, 1000000):
+        for w in (1, 2, 3, 8, 64):
+            parts = [erp.shard_range(n, r, w) for r in range(w)]
+            assert parts == [sharding.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    with pytest.raises(erp.ErpError):
+        erp.shard_range(10, 3, 3)
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_devices():
+    if erp.lib().erp_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(erp.ErpError) as ei:
+        erp.Group([0, 1])
+    assert ei.value.status in (binding.E_NO_DEVICE, binding.E_NCCL)
