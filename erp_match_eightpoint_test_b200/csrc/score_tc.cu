@@ -337,7 +337,7 @@ template <int METRIC>
 __global__ void __launch_bounds__(AP_THREADS)
 argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__ E, const float4* __restrict__ l4,
                    const float4* __restrict__ r4, float tau, float tau2, float sin2, unsigned long long hyp0, int32_t* __restrict__ w,
-                   unsigned long long* __restrict__ best)
+                   unsigned long long* __restrict__ best, int slack_div, int slack_tiles)
 {
     __shared__ unsigned long long wbest[AP_THREADS / 32];
     __shared__ int wsum[AP_THREADS / 32];
@@ -404,7 +404,7 @@ argmax_plan_kernel(const int32_t* __restrict__ upper, const double* __restrict__
     // (correspondences a discarded hypothesis may still be missing: m - seen < L*  <=>  seen > m - L*)
     const int n0 = w[W_N0], n_ct = w[W_NCT];
     long need = (long)m - lstar;
-    need += need / 8 + 2 * SN_ROWS;                        // slack: bad hypotheses still collect a few inliers
+    need += need / slack_div + slack_tiles * SN_ROWS;       // slack: bad hypotheses still collect a few inliers
     int ct1 = (int)((need + SN_ROWS - 1) / SN_ROWS);
     if (ct1 < n0) ct1 = n0;
     if (ct1 > n_ct || lstar * 4 < m) ct1 = n_ct;           // weak best model: pruning cannot pay, finish in pass B
@@ -535,11 +535,13 @@ int score_tc_search(erp_ctx* ctx, const ScoreTcBuffers& b, const double* d_E, in
     ERP_TRY(launch_score_tc(ctx, me, mk, p));
     {
         const int grid = min(cdiv(H, AP_THREADS), ctx->sm_count);
+        static const int slack_div = [] { const char* e = getenv("ERP_B200_PRUNE_DIV"); return e && atoi(e) > 0 ? atoi(e) : 16; }();
+        static const int slack_tiles = [] { const char* e = getenv("ERP_B200_PRUNE_TILES"); return e ? atoi(e) : 2; }();
         const float4 *l4 = (const float4*)d_l4, *r4 = (const float4*)d_r4;
         unsigned long long* bp = (unsigned long long*)d_best;
-        if (metric == ERP_METRIC_ALGEBRAIC) argmax_plan_kernel<ERP_METRIC_ALGEBRAIC><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp);
-        else if (metric == ERP_METRIC_SAMPSON) argmax_plan_kernel<ERP_METRIC_SAMPSON><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp);
-        else argmax_plan_kernel<ERP_METRIC_ANGULAR><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp);
+        if (metric == ERP_METRIC_ALGEBRAIC) argmax_plan_kernel<ERP_METRIC_ALGEBRAIC><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp, slack_div, slack_tiles);
+        else if (metric == ERP_METRIC_SAMPSON) argmax_plan_kernel<ERP_METRIC_SAMPSON><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp, slack_div, slack_tiles);
+        else argmax_plan_kernel<ERP_METRIC_ANGULAR><<<grid, AP_THREADS, 0, ctx->stream>>>(upper, d_E, l4, r4, tau, tau2, sin2, hyp0, w, bp, slack_div, slack_tiles);
         ERP_LAUNCH(ctx, "argmax_plan_kernel");
     }
     // pass B: every hypothesis, tiles [n0, ct1)
