@@ -352,7 +352,8 @@ def distance_roofline(rig, cfg, stats, k_ms, nq_kernel, nt, dim, clocks, workloa
         stamp_now = sass_stamp("knn2_tc1_kernelILi" if engine == "tcgen05_1xtf32" else "knn2_tc_kernelILi", "ILi%dE" % ((dim + 31) // 32))
     roof = {"bound": "tensor", "kernel": "distance tiles + fused top-k (" + engine + ")", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_sass_stamp": {"captured": stamp, "this_build": stamp_now,
+            # the stamp belongs to the captured instantiation: compared only where a constant exists for this workload
+            "traffic_sass_stamp": None if traffic is None else {"captured": stamp, "this_build": stamp_now,
                                    "stale": (stamp is not None and stamp_now is not None and stamp != stamp_now)},
             "kernel_ms": k_ms,
             "peak_from": f"{pk['src']} bf16 {pk['bf16']} TFLOP/s / 2 (tf32)" + ("" if div == 1.0 else " / 3 (3xTF32)")

@@ -278,7 +278,7 @@ class Context:
         _check(lib().erp_knn2_match(self._h, _ptr(q), q.shape[0], q.strides[0] if q.shape[0] else 4 * q.shape[1],
                                     _ptr(t), t.shape[0], t.strides[0] if t.shape[0] else 4 * t.shape[1], q.shape[1],
                                     ratio, int(cross_check), _ptr(out), C.byref(n)))
-        return out[: n.value].copy()
+        return out[: n.value]          # a view of this call's own array: only the pages the records touched are resident
 
     def knn2_raw(self, q, t):
         q, t = _f32(q), _f32(t)
@@ -464,7 +464,7 @@ class Context:
         _check(lib().erp_knn2_match_dist(self._h, _ptr(q), q.shape[0], q.strides[0] if q.shape[0] else 4 * q.shape[1],
                                          _ptr(t), t.shape[0], t.strides[0] if t.shape[0] else 4 * t.shape[1], q.shape[1],
                                          ratio, int(cross_check), _ptr(out), C.byref(n)))
-        return out[: n.value].copy()
+        return out[: n.value]
 
     def knn2_match_dist_dev(self, d_q_shard, nq_total, d_t, nt, dim, ratio, cross_check, d_out, d_n_out):
         _check(lib().erp_knn2_match_dist_dev(self._h, _ptr(d_q_shard), nq_total, _ptr(d_t), nt, dim, ratio, int(cross_check),
@@ -629,4 +629,4 @@ class Group:
         _check(lib().erp_group_knn2_match(self._h, _ptr(q), q.shape[0], q.strides[0] if q.shape[0] else 4 * q.shape[1],
                                           _ptr(t), t.shape[0], t.strides[0] if t.shape[0] else 4 * t.shape[1], q.shape[1],
                                           ratio, int(cross_check), _ptr(out), C.byref(n)))
-        return out[: n.value].copy()
+        return out[: n.value]

@@ -4,6 +4,10 @@
 
 #include <stdarg.h>
 
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 namespace erp {
@@ -51,18 +55,70 @@ int mask_launch(erp_ctx*, const double*, const float*, const float*, int, int, f
 // driver's own pageable path is a single-threaded version of the same and was 2.2x slower for the 51 MB of cfg3.
 constexpr size_t STAGE_CHUNK = 1 << 20;          // bytes per pinned slot
 constexpr size_t STAGE_MIN_BYTES = 4 << 20;      // below this the driver's path is fine
+// The helper threads live as long as the context: starting three threads per upload (and their first CUDA call) cost
+// ~0.3 ms per call, more than the copy itself for one query chunk (scripts/stage_probe.py).
 struct StagePool {
-    static constexpr int THREADS = 4, SLOTS = 2;
+    static constexpr int THREADS = 8, SLOTS = 2;      // THREADS: upper bound; `threads` of them are used
+    int threads = 4;                                  // $ERP_B200_STAGE_THREADS (1..8); thread 0 is the caller
     cudaStream_t stream[THREADS] = {};
     cudaEvent_t ev[THREADS][SLOTS] = {};
     uint8_t* pinned = nullptr;
     bool ok = false;
+    // job hand-off: the caller publishes `job`, bumps `seq`; every helper runs job(t) once per seq
+    std::thread helpers[THREADS - 1];
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    const std::function<void(int)>* job = nullptr;
+    uint64_t seq = 0;
+    int pending = 0;
+    bool quit = false;
+
+    void helper_main(int t, int device)
+    {
+        cudaSetDevice(device);
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_job.wait(lk, [&] { return quit || seq != seen; });
+                if (quit) return;
+                seen = seq; j = job;
+            }
+            (*j)(t);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    // runs work(t) for t = 0 .. threads-1 (0 on the calling thread) and returns when all are done
+    void run(const std::function<void(int)>& work)
+    {
+        if (threads > 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            job = &work; pending = threads - 1; seq++;
+        }
+        if (threads > 1) cv_job.notify_all();
+        work(0);
+        if (threads > 1) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return pending == 0; });
+            job = nullptr;
+        }
+    }
 };
 
 void stage_release(erp_ctx* ctx)
 {
     StagePool* p = ctx->stage;
     if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->quit = true;
+    }
+    p->cv_job.notify_all();
+    for (auto& h : p->helpers) if (h.joinable()) h.join();
     for (int t = 0; t < StagePool::THREADS; t++) {
         if (p->stream[t]) { cudaStreamSynchronize(p->stream[t]); cudaStreamDestroy(p->stream[t]); }
         for (int s = 0; s < StagePool::SLOTS; s++) if (p->ev[t][s]) cudaEventDestroy(p->ev[t][s]);
@@ -76,15 +132,19 @@ static StagePool* stage_pool(erp_ctx* ctx)
 {
     if (ctx->stage) return ctx->stage->ok ? ctx->stage : nullptr;
     StagePool* p = ctx->stage = new StagePool();
+    if (const char* e = getenv("ERP_B200_STAGE_THREADS")) { const int n = atoi(e); if (n >= 1 && n <= StagePool::THREADS) p->threads = n; }
     bool ok = cudaMallocHost(&p->pinned, STAGE_CHUNK * StagePool::THREADS * StagePool::SLOTS) == cudaSuccess;
-    for (int t = 0; t < StagePool::THREADS && ok; t++) {
+    for (int t = 0; t < p->threads && ok; t++) {
         ok = cudaStreamCreateWithFlags(&p->stream[t], cudaStreamNonBlocking) == cudaSuccess;
         for (int s = 0; s < StagePool::SLOTS && ok; s++) ok = cudaEventCreateWithFlags(&p->ev[t][s], cudaEventDisableTiming) == cudaSuccess;
     }
     if (!ok) cudaGetLastError();
+    if (ok) for (int t = 1; t < p->threads; t++) p->helpers[t - 1] = std::thread(&StagePool::helper_main, p, t, ctx->device);
     p->ok = ok;
     return ok ? p : nullptr;
 }
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static bool is_pageable(const void* p)
 {
@@ -104,13 +164,12 @@ int upload_rows(erp_ctx* ctx, void* d_dst, const void* src, int rows, size_t row
         return ERP_OK;
     }
     // the staged copies must not overtake work already queued on the target buffer
+    const double t_begin = now_s();
     ERP_CUDA(cudaEventRecord(ctx->ev_copy[8], ctx->stream));
-    const int T = StagePool::THREADS;
+    const int T = pool->threads;
     const int rows_per_chunk = (int)(STAGE_CHUNK / row_bytes);
     std::atomic<int> failed{0};
-    const int device = ctx->device;
-    auto work = [&](int t) {
-        cudaSetDevice(device);
+    const std::function<void(int)> work = [&](int t) {
         const int r0 = (int)((long long)rows * t / T), r1 = (int)((long long)rows * (t + 1) / T);
         if (cudaStreamWaitEvent(pool->stream[t], ctx->ev_copy[8], 0) != cudaSuccess) { failed = 1; return; }
         int slot = 0;
@@ -126,14 +185,12 @@ int upload_rows(erp_ctx* ctx, void* d_dst, const void* src, int rows, size_t row
                 cudaEventRecord(pool->ev[t][slot], pool->stream[t]) != cudaSuccess) { failed = 1; return; }
         }
     };
-    std::thread helpers[StagePool::THREADS - 1];
-    for (int t = 1; t < T; t++) helpers[t - 1] = std::thread(work, t);
-    work(0);
-    for (int t = 1; t < T; t++) helpers[t - 1].join();
+    pool->run(work);
     if (failed) { set_error("staged upload failed: %s", cudaGetErrorString(cudaGetLastError())); return ERP_E_CUDA; }
     // the context stream continues after the last DMA of every helper stream
     for (int t = 0; t < T; t++)
         for (int s = 0; s < StagePool::SLOTS; s++) ERP_CUDA(cudaStreamWaitEvent(ctx->stream, pool->ev[t][s], 0));
+    if (getenv("ERP_B200_STAGE_TRACE")) fprintf(stderr, "[stage] %zu bytes staged by %d threads, host %.3f ms\n", total, T, 1e3 * (now_s() - t_begin));
     return ERP_OK;
 }
 
@@ -406,10 +463,15 @@ ERP_API int erp_knn2_match_dev(erp_ctx* ctx, const float* d_q, int nq, const flo
 
 // Host-buffer 2-NN: the train set and the first query chunk are uploaded, then every further query chunk travels
 // (on its own stream) while the previous one is searched.  Rows are independent, so the result does not depend on
-// the cut; the train-side operands are prepared by the first chunk only.  Chunks: $ERP_B200_HOST_CHUNKS (1..7).
-// Round 1 measured chunking as a loss on cfg3 (1 chunk 3.85 ms, 2 chunks 3.90, 4 chunks 4.27: shorter kernels, more list
-// segments per row, more tails); with round 2's finer segments and threshold exchange three chunks win for large inputs.
-static int host_chunks(int nq, int nt)
+// the cut; the train-side operands are prepared by the first chunk only.
+//
+// The cut (scripts/stage_probe.py prints the device timeline of a call; cfg3, 100k x 100k x 64): a chunk's search costs
+// ~0.10 ms + 17.5 us per 1000 rows, the train set must be complete before anything starts (0.47 ms pinned, ~1 ms staged
+// from pageable memory), and after the first chunk the call is search bound.  So the FIRST chunk is short -- it only has
+// to cover the upload of the second -- and the number of chunks small: two from pinned memory (5/32 + 27/32), three from
+// pageable memory where the staging is slower than the search (1/8 + 3/8 + 1/2).  $ERP_B200_HOST_CHUNKS = 1..7 forces a
+// count (a short first chunk, then even ones).  Small inputs: one chunk.
+static int chunk_bounds(int nq, int nt, bool pageable, int (&bounds)[9])
 {
     static int forced = -1;
     if (forced < 0) {
@@ -417,10 +479,21 @@ static int host_chunks(int nq, int nt)
         forced = e ? atoi(e) : 0;
         if (forced < 0 || forced > 7) forced = 0;
     }
-    if (forced) return forced;
-    // round 2 (eight segments per query row + threshold exchange keep short chunks efficient): 100k x 100k from pinned
-    // memory 3.42 ms with one chunk, 3.32 / 3.24 / 3.35 with 2 / 3 / 4 (scripts/e2e_chunks.py); small inputs: one chunk
-    return (double)nq * (double)nt >= 4.0e9 ? 3 : 1;
+    auto round256 = [](long long v) { return (int)((v + 255) / 256 * 256); };
+    int n = 0;
+    bounds[0] = 0;
+    auto cut = [&](int r) { if (r > bounds[n] && r < nq) bounds[++n] = r; };
+    if (forced > 1) {
+        const int first = forced > 2 ? round256(cdiv(nq, 2 * forced)) : 0;
+        cut(first);
+        const int rows = round256(cdiv(nq - bounds[n], forced - n));
+        for (int r = bounds[n] + rows; r < nq; r += rows) cut(r);
+    } else if (forced == 0 && (double)nq * (double)nt >= 4.0e9) {
+        if (pageable) { cut(round256(nq / 8)); cut(round256(nq / 2)); }
+        else cut(round256((long long)nq * 5 / 32));
+    }
+    bounds[++n] = nq;
+    return n;
 }
 static int knn2_host(erp_ctx* ctx, const float* q, int nq, size_t qs, const float* t, int nt, size_t ts, int dim,
                      int32_t* d_idx2, float* d_dist2)
@@ -432,30 +505,57 @@ static int knn2_host(erp_ctx* ctx, const float* q, int nq, size_t qs, const floa
     float* dq = ctx->scratch<float>(S_Q, (size_t)nq * dim + 4, &st);
     float* dt = ctx->scratch<float>(S_T, (size_t)nt * dim + 4, &st);
     ERP_TRY(st);
-    int chunks = host_chunks(nq, nt);
-    int rows = cdiv(cdiv(nq, chunks), 256) * 256;
-    chunks = cdiv(nq, rows);
+    int bounds[9];
+    const int chunks = chunk_bounds(nq, nt, is_pageable(q), bounds);
     // fork: the copy stream starts after whatever the context stream still has queued
     ERP_CUDA(cudaEventRecord(ctx->ev_copy[7], ctx->stream));
     ERP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
     cudaStream_t main_stream = ctx->stream;
-    ctx->stream = ctx->copy_stream;                 // upload_rows enqueues on ctx->stream
-    int rc = upload_rows(ctx, dt, t, nt, row, ts);
-    for (int c = 0; c < chunks && rc == ERP_OK; c++) {
-        const int r0 = c * rows, n = nq - r0 < rows ? nq - r0 : rows;
-        rc = upload_rows(ctx, dq + (size_t)r0 * dim, reinterpret_cast<const char*>(q) + (size_t)r0 * qs, n, row, qs);
-        if (rc == ERP_OK && cudaEventRecord(ctx->ev_copy[c], ctx->copy_stream) != cudaSuccess) rc = ERP_E_CUDA;
-    }
-    ctx->stream = main_stream;
-    ERP_TRY(rc);
+    // upload_rows enqueues on ctx->stream; it must point at the context's own stream again on EVERY exit path
+    struct StreamSwap {
+        erp_ctx* c; cudaStream_t main;
+        void to_copy() { c->stream = c->copy_stream; }
+        void to_main() { c->stream = main; }
+        ~StreamSwap() { c->stream = main; }
+    } sw{ctx, main_stream};
     // tc_chunk > 0 tells the tensor engines that the train operand of this call is already prepared: it must not
     // survive this function on ANY exit path (a stale value would make the next call reuse old train data)
     struct ChunkReset { erp_ctx* c; ~ChunkReset() { c->tc_chunk = 0; } } reset{ctx};
+    // $ERP_B200_STAGE_TRACE: device-side timeline of the call (uploads on the copy stream, searches on the context stream)
+    const bool trace = getenv("ERP_B200_STAGE_TRACE") != nullptr;
+    cudaEvent_t tr[20] = {};
+    int n_tr = 0;
+    auto mark = [&](cudaStream_t s) { if (trace && n_tr < 20 && cudaEventCreate(&tr[n_tr]) == cudaSuccess) cudaEventRecord(tr[n_tr++], s); };
+    mark(ctx->copy_stream);
+    sw.to_copy();
+    int rc = upload_rows(ctx, dt, t, nt, row, ts);
+    mark(ctx->copy_stream);
+    // chunk c's search is enqueued as soon as chunk c is on its way: a pageable source blocks this thread while the
+    // staging threads copy chunk c + 1, and the device searches chunk c meanwhile (pinned sources never block here)
     for (int c = 0; c < chunks && rc == ERP_OK; c++) {
-        const int r0 = c * rows, n = nq - r0 < rows ? nq - r0 : rows;
+        const int r0 = bounds[c], n = bounds[c + 1] - r0;
+        sw.to_copy();
+        rc = upload_rows(ctx, dq + (size_t)r0 * dim, reinterpret_cast<const char*>(q) + (size_t)r0 * qs, n, row, qs);
+        if (rc == ERP_OK && cudaEventRecord(ctx->ev_copy[c], ctx->copy_stream) != cudaSuccess) rc = ERP_E_CUDA;
+        mark(ctx->copy_stream);
+        sw.to_main();
+        if (rc != ERP_OK) break;
         ERP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[c], 0));
+        mark(ctx->stream);
         ctx->tc_chunk = c;
+        const double t_enq = now_s();
         rc = erp_knn2_dev(ctx, dq + (size_t)r0 * dim, n, dt, nt, dim, d_idx2 + 2 * (size_t)r0, d_dist2 + 2 * (size_t)r0, nullptr);
+        mark(ctx->stream);
+        if (trace) fprintf(stderr, "[stage] chunk %d: search of %d rows enqueued in %.3f ms (host)\n", c, n, 1e3 * (now_s() - t_enq));
+    }
+    if (trace && n_tr > 0) {
+        // marks: 0 fork, 1 train up, then per chunk { upload done (copy stream), search start, search end (context stream) }
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        fprintf(stderr, "[stage] device timeline (ms after the fork):");
+        for (int i = 1; i < n_tr; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, tr[0], tr[i]); fprintf(stderr, " %.3f", ms); }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < n_tr; i++) cudaEventDestroy(tr[i]);
     }
     return rc;
 }
@@ -485,11 +585,25 @@ ERP_API int erp_knn2_match(erp_ctx* ctx, const float* q, int nq, size_t q_stride
     }
     ERP_TRY(erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n));
     int32_t n = 0;
-    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n > 0) {
-        ERP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t cap_bytes = sizeof(erp_dmatch) * (size_t)nq;
+    if (cap_bytes <= (size_t)(8u << 20)) {
+        // one round trip: the count and the record array (capacity nq) land in a pinned bounce buffer together, then the
+        // n records are copied out.  Waiting for the count first costs a second synchronisation, and a pageable `out`
+        // the driver's staged copy on top.
+        uint8_t* h = ctx->host_scratch<uint8_t>(0, cap_bytes + 16, &st);
+        ERP_TRY(st);
+        ERP_CUDA(cudaMemcpyAsync(h, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaMemcpyAsync(h + 16, d_out, cap_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(&n, h, sizeof n);
+        if (n > 0) memcpy(out, h + 16, sizeof(erp_dmatch) * (size_t)n);
+    } else {
+        ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (n > 0) {
+            ERP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+            ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
     }
     *n_out = n;
     return ERP_OK;

@@ -284,7 +284,7 @@ def test_host_call_with_query_chunks_equals_single_call(tmp_path):
     """)
     import os
     outs = {}
-    for chunks in ("1", "3"):
+    for chunks in ("1", "3", "7"):                   # 3 and 7: a short first chunk, then even ones (api.cu: knn2_host)
         env = dict(os.environ, ERP_B200_HOST_CHUNKS=chunks)
         base = str(tmp_path / f"c{chunks}")
         r = subprocess.run([sys.executable, "-c", code, base], env=env, capture_output=True, text=True, timeout=300,
@@ -293,8 +293,9 @@ def test_host_call_with_query_chunks_equals_single_call(tmp_path):
         outs[chunks] = base
     for eng in (binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X):
         for what in ("idx", "dist", "m"):
-            a, b = np.load(outs["1"] + f"_{what}{eng}.npy"), np.load(outs["3"] + f"_{what}{eng}.npy")
-            assert a.tobytes() == b.tobytes(), (eng, what)
+            a = np.load(outs["1"] + f"_{what}{eng}.npy")
+            for chunks in ("3", "7"):
+                assert a.tobytes() == np.load(outs[chunks] + f"_{what}{eng}.npy").tobytes(), (eng, what, chunks)
 
 
 @pytest.mark.parametrize("H,m,tau", [(5000, 3000, 0.002), (129, 257, 0.002), (20000, 777, 0.01), (3000, 3000, 1e-5),
