@@ -526,6 +526,11 @@ def test_cfg3_full_size_tensor_core_equals_exact_engine(ctx):
     ctx.set_engine(binding.ENGINE_AUTO)
     assert len(m) == (planted >= 0).sum() and (planted[m["queryIdx"]] == m["trainIdx"]).all()
     assert (np.diff(m["queryIdx"]) > 0).all()
+    # the host-buffer call cuts the queries differently for pageable (above: 1/8 + 3/8 + 1/2) and pinned sources (5/32 + 27/32)
+    import torch
+    pq, pt = torch.from_numpy(q).pin_memory().numpy(), torch.from_numpy(t).pin_memory().numpy()
+    assert ctx.knn2_match(pq, pt, ratio=0.3).tobytes() == m.tobytes()
+    del pq, pt
     sub = np.arange(0, 100000, 64)
     oidx, odist, _ = O.knn2(q[sub], t)
     assert np.array_equal(idx[sub], oidx) and np.array_equal(dist[sub], odist)
