@@ -194,6 +194,34 @@ int upload_rows(erp_ctx* ctx, void* d_dst, const void* src, int rows, size_t row
     return ERP_OK;
 }
 
+// Match records of a host-buffer call back to the caller in ONE round trip: the count and the record array (capacity
+// `cap`) land in a pinned bounce buffer together, then the n records are copied out.  Waiting for the count first costs
+// a second synchronisation, and a pageable `out` the driver's staged copy on top.
+int download_matches(erp_ctx* ctx, const erp_dmatch* d_out, const int32_t* d_n, size_t cap, erp_dmatch* out, int* n_out)
+{
+    int32_t n = 0;
+    int st = ERP_OK;
+    const size_t cap_bytes = sizeof(erp_dmatch) * cap;
+    if (cap_bytes <= (size_t)(8u << 20)) {
+        uint8_t* h = ctx->host_scratch<uint8_t>(0, cap_bytes + 16, &st);
+        ERP_TRY(st);
+        ERP_CUDA(cudaMemcpyAsync(h, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cap_bytes) ERP_CUDA(cudaMemcpyAsync(h + 16, d_out, cap_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(&n, h, sizeof n);
+        if (n > 0) memcpy(out, h + 16, sizeof(erp_dmatch) * (size_t)n);
+    } else {
+        ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (n > 0) {
+            ERP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+            ERP_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    *n_out = n;
+    return ERP_OK;
+}
+
 } // namespace erp
 
 using namespace erp;
@@ -584,29 +612,7 @@ ERP_API int erp_knn2_match(erp_ctx* ctx, const float* q, int nq, size_t q_stride
         ERP_TRY(erp_nn1_reverse_dev(ctx, ctx->dev[S_Q].as<float>(), nq, ctx->dev[S_T].as<float>(), nt, dim, 0, rev, nullptr));
     }
     ERP_TRY(erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n));
-    int32_t n = 0;
-    const size_t cap_bytes = sizeof(erp_dmatch) * (size_t)nq;
-    if (cap_bytes <= (size_t)(8u << 20)) {
-        // one round trip: the count and the record array (capacity nq) land in a pinned bounce buffer together, then the
-        // n records are copied out.  Waiting for the count first costs a second synchronisation, and a pageable `out`
-        // the driver's staged copy on top.
-        uint8_t* h = ctx->host_scratch<uint8_t>(0, cap_bytes + 16, &st);
-        ERP_TRY(st);
-        ERP_CUDA(cudaMemcpyAsync(h, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-        ERP_CUDA(cudaMemcpyAsync(h + 16, d_out, cap_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-        memcpy(&n, h, sizeof n);
-        if (n > 0) memcpy(out, h + 16, sizeof(erp_dmatch) * (size_t)n);
-    } else {
-        ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (n > 0) {
-            ERP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-            ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-        }
-    }
-    *n_out = n;
-    return ERP_OK;
+    return download_matches(ctx, d_out, d_n, (size_t)nq, out, n_out);
 }
 
 ERP_API int erp_knn2_raw(erp_ctx* ctx, const float* q, int nq, size_t q_stride_bytes,

@@ -232,6 +232,7 @@ int pose_chain_tail(erp_ctx* ctx, const double* dl, const double* dr, const floa
 // touching the host again.  The first call with a key runs directly, the second is captured, the rest replay.
 int graph_run(erp_ctx* ctx, const void* key, size_t key_bytes, const std::function<int()>& body);
 void graph_release(erp_ctx* ctx);
+int download_matches(erp_ctx* ctx, const erp_dmatch* d_out, const int32_t* d_n, size_t cap, erp_dmatch* out, int* n_out);
 int upload_rows(erp_ctx* ctx, void* d_dst, const void* src, int rows, size_t row_bytes, size_t stride);
 void stage_release(erp_ctx* ctx);
 // multi-GPU (dist.cu)

@@ -587,15 +587,7 @@ ERP_API int erp_knn2_match_dist(erp_ctx* ctx, const float* q, int nq, size_t q_s
     float *dq, *dt;
     ERP_TRY(upload_sharded(ctx, q, lo, hi, q_stride_bytes, t, nt, t_stride_bytes, dim, &dq, &dt));
     ERP_TRY(match_shard_dev(ctx, dq, lo, hi, dt, nt, dim, ratio, cross_check, d_out, d_n));
-    int32_t n = 0;
-    ERP_CUDA(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-    ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n > 0) {
-        ERP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(erp_dmatch) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        ERP_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    *n_out = n;
-    return ERP_OK;
+    return download_matches(ctx, d_out, d_n, (size_t)(hi - lo), out, n_out);
 }
 
 ERP_API int erp_knn2_match_dist_dev(erp_ctx* ctx, const float* d_q_shard, int nq_total, const float* d_t, int nt, int dim,
