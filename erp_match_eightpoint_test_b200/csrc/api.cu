@@ -1009,6 +1009,28 @@ ERP_API int erp_ransac_pixels(erp_ctx* ctx, int width, int height, const void* l
     return ERP_OK;
 }
 
+// gather + bearings -> hypothesis search -> mask + refit on the device-resident match list of a pair (stage events 2, 3)
+static int pose_after_match(erp_ctx* ctx, const erp_dmatch* d_matches, int nq, const int32_t* d_n_matches,
+                            const void* d_left_xy, const void* d_right_xy, size_t kp_stride_bytes, int width, int height,
+                            uint64_t seed, int H, int S, int metric, float tau, uint8_t* d_mask, erp_ransac_result* d_result)
+{
+    PoseBuffers b;
+    ERP_TRY(pose_chain_buffers(ctx, nq, &b));
+    const bool tc = ransac_uses_tc(ctx, H, nq, metric);
+    ScoreTcBuffers sb = {};
+    if (tc) {
+        ERP_TRY(score_tc_buffers(ctx, H < RANSAC_CHUNK ? H : RANSAC_CHUNK, nq, &sb));
+        ERP_CUDA(cudaMemsetAsync(sb.w, 0, W_WORDS_BYTES, ctx->stream));
+    }
+    ERP_TRY(gather_bearings_chain(ctx, d_matches, nq, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes, 0, width, height,
+                                  b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[2]));
+    ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, nq, d_n_matches, seed, 0, H, S, metric, tau, tc, false,
+                            d_mask ? d_mask : b.mask, d_result));
+    ERP_CUDA(record_timing(ctx, ctx->ev_stage[3]));
+    return ERP_OK;
+}
+
 ERP_API int erp_pair_pose_dev(erp_ctx* ctx, const float* d_q, int nq, const float* d_t, int nt, int dim, float ratio, int cross_check,
                               const void* d_left_xy, const void* d_right_xy, size_t kp_stride_bytes, int width, int height,
                               uint64_t seed, int H, int S, int metric, float tau,
@@ -1025,21 +1047,8 @@ ERP_API int erp_pair_pose_dev(erp_ctx* ctx, const float* d_q, int nq, const floa
     ERP_CUDA(record_timing(ctx, ctx->ev_stage[0]));
     ERP_TRY(erp_knn2_match_dev(ctx, d_q, nq, d_t, nt, dim, ratio, cross_check, d_matches, d_n_matches));
     ERP_CUDA(record_timing(ctx, ctx->ev_stage[1]));
-    PoseBuffers b;
-    ERP_TRY(pose_chain_buffers(ctx, nq, &b));
-    const bool tc = ransac_uses_tc(ctx, H, nq, metric);
-    ScoreTcBuffers sb = {};
-    if (tc) {
-        ERP_TRY(score_tc_buffers(ctx, H < RANSAC_CHUNK ? H : RANSAC_CHUNK, nq, &sb));
-        ERP_CUDA(cudaMemsetAsync(sb.w, 0, W_WORDS_BYTES, ctx->stream));
-    }
-    ERP_TRY(gather_bearings_chain(ctx, d_matches, nq, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes, 0, width, height,
-                                  b.l3, b.r3, b.l4, b.r4, sb.Ks, sb.w));
-    ERP_CUDA(record_timing(ctx, ctx->ev_stage[2]));
-    ERP_TRY(pose_chain_tail(ctx, b.l3, b.r3, b.l4, b.r4, nq, d_n_matches, seed, 0, H, S, metric, tau, tc, false,
-                            d_mask ? d_mask : b.mask, d_result));
-    ERP_CUDA(record_timing(ctx, ctx->ev_stage[3]));
-    return ERP_OK;
+    return pose_after_match(ctx, d_matches, nq, d_n_matches, d_left_xy, d_right_xy, kp_stride_bytes, width, height, seed, H, S, metric, tau,
+                            d_mask, d_result);
     });
 }
 
@@ -1067,12 +1076,41 @@ ERP_API int erp_pair_pose(erp_ctx* ctx, const float* q, int nq, size_t q_stride_
     PoseBuffers b;
     ERP_TRY(pose_chain_buffers(ctx, nq, &b));
     ERP_TRY(st);
-    ERP_TRY(upload_rows(ctx, dt, t, nt, row, t_stride_bytes));
-    ERP_TRY(upload_rows(ctx, dq, q, nq, row, q_stride_bytes));
-    ERP_TRY(upload_rows(ctx, d_xy, left_xy, nq, 8, kp_stride_bytes));
-    ERP_TRY(upload_rows(ctx, d_xy + (size_t)nq * 2, right_xy, nt, 8, kp_stride_bytes));
-    ERP_TRY(erp_pair_pose_dev(ctx, dq, nq, dt, nt, dim, ratio, cross_check, d_xy, d_xy + (size_t)nq * 2, 8, width, height,
-                              seed, H, S, metric, tau, d_out, d_n, b.mask, b.res));
+    int bounds[9];
+    if (chunk_bounds(nq, nt, is_pageable(q), bounds) > 1) {
+        // large pair: the descriptors travel in chunks behind the search (knn2_host), the keypoints follow on the copy
+        // stream and are awaited by the gather; the chain is enqueued directly (launch cost hides behind the uploads)
+        int32_t* idx2 = ctx->scratch<int32_t>(S_IDX2, (size_t)nq * 2 + 2, &st);
+        float* dist2 = ctx->scratch<float>(S_DIST2, (size_t)nq * 2 + 2, &st);
+        ERP_TRY(st);
+        ERP_CUDA(record_timing(ctx, ctx->ev_stage[0]));
+        ERP_TRY(knn2_host(ctx, q, nq, q_stride_bytes, t, nt, t_stride_bytes, dim, idx2, dist2));
+        {
+            cudaStream_t main_stream = ctx->stream;
+            struct Swap { erp_ctx* c; cudaStream_t m; ~Swap() { c->stream = m; } } sw{ctx, main_stream};
+            ctx->stream = ctx->copy_stream;
+            ERP_TRY(upload_rows(ctx, d_xy, left_xy, nq, 8, kp_stride_bytes));
+            ERP_TRY(upload_rows(ctx, d_xy + (size_t)nq * 2, right_xy, nt, 8, kp_stride_bytes));
+            ERP_CUDA(cudaEventRecord(ctx->ev_copy[9], ctx->copy_stream));
+        }
+        int32_t* rev = nullptr;
+        if (cross_check) {
+            rev = ctx->scratch<int32_t>(S_REVQ, (size_t)nt, &st);
+            ERP_TRY(st);
+            ERP_TRY(erp_nn1_reverse_dev(ctx, dq, nq, dt, nt, dim, 0, rev, nullptr));
+        }
+        ERP_TRY(erp_match_filter_dev(ctx, idx2, dist2, nq, ratio, rev, 0, d_out, d_n));
+        ERP_CUDA(record_timing(ctx, ctx->ev_stage[1]));
+        ERP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[9], 0));
+        ERP_TRY(pose_after_match(ctx, d_out, nq, d_n, d_xy, d_xy + (size_t)nq * 2, 8, width, height, seed, H, S, metric, tau, b.mask, b.res));
+    } else {
+        ERP_TRY(upload_rows(ctx, dt, t, nt, row, t_stride_bytes));
+        ERP_TRY(upload_rows(ctx, dq, q, nq, row, q_stride_bytes));
+        ERP_TRY(upload_rows(ctx, d_xy, left_xy, nq, 8, kp_stride_bytes));
+        ERP_TRY(upload_rows(ctx, d_xy + (size_t)nq * 2, right_xy, nt, 8, kp_stride_bytes));
+        ERP_TRY(erp_pair_pose_dev(ctx, dq, nq, dt, nt, dim, ratio, cross_check, d_xy, d_xy + (size_t)nq * 2, 8, width, height,
+                                  seed, H, S, metric, tau, d_out, d_n, b.mask, b.res));
+    }
     // everything is enqueued: the host waits for the MATCH stage only (the pose chain keeps running), learns the match
     // count and brings the records back on the copy stream while the hypotheses are being scored
     int32_t n = 0;

@@ -72,7 +72,7 @@ struct erp_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;             // host-buffer calls upload query chunks here while the previous chunk computes
-    cudaEvent_t ev_copy[10] = {};                   // "chunk c is on the device" (0..6), fork events (7: chunked upload, 8: staged upload)
+    cudaEvent_t ev_copy[10] = {};                   // "chunk c is on the device" (0..6), fork events (7: chunked upload, 8: staged upload), 9: keypoints of a host pair call
     int tc_chunk = 0;                               // > 0: later query chunk of one host call: train operand and statistics carry over
     int engine = ERP_ENGINE_AUTO;
     uint64_t launches = 0;

@@ -280,6 +280,15 @@ def test_host_call_with_query_chunks_equals_single_call(tmp_path):
             np.save(sys.argv[1] + f"_idx{eng}.npy", idx); np.save(sys.argv[1] + f"_dist{eng}.npy", dist)
             np.save(sys.argv[1] + f"_m{eng}.npy", m)
             print(eng, st["rescanned"])
+        # the whole pair through one host-buffer call: with more than one chunk the descriptors travel behind the search
+        ctx.set_engine(binding.ENGINE_AUTO)
+        rng = np.random.default_rng(3)
+        left = (rng.uniform(0, 1, (3001, 2)) * [4096, 2047]).astype(np.float32)
+        right = (rng.uniform(0, 1, (2500, 2)) * [4096, 2047]).astype(np.float32)
+        for cross in (False, True):
+            pm, res = ctx.pair_pose(q, t, left, right, 4096, 2048, ratio=0.8, cross_check=cross, seed=3, H=3000)
+            np.save(sys.argv[1] + f"_pm{int(cross)}.npy", pm)
+            np.save(sys.argv[1] + f"_pres{int(cross)}.npy", np.frombuffer(np.array([res["packed"], res["count"]], np.uint64).tobytes() + res["mask"].tobytes() + res["E_refit"].tobytes(), np.uint8))
         ctx.close()
     """)
     import os
@@ -296,6 +305,11 @@ def test_host_call_with_query_chunks_equals_single_call(tmp_path):
             a = np.load(outs["1"] + f"_{what}{eng}.npy")
             for chunks in ("3", "7"):
                 assert a.tobytes() == np.load(outs[chunks] + f"_{what}{eng}.npy").tobytes(), (eng, what, chunks)
+    for what in ("pm0", "pm1", "pres0", "pres1"):
+        a = np.load(outs["1"] + f"_{what}.npy")
+        assert len(a) > 8
+        for chunks in ("3", "7"):
+            assert a.tobytes() == np.load(outs[chunks] + f"_{what}.npy").tobytes(), (what, chunks)
 
 
 @pytest.mark.parametrize("H,m,tau", [(5000, 3000, 0.002), (129, 257, 0.002), (20000, 777, 0.01), (3000, 3000, 1e-5),
