@@ -543,8 +543,9 @@ def run_pair(args, cfg, rig):
         cpu = {"value": s["evals_per_s"], "unit": "dist-evals/s", "cores": s["cores"], "kind": "port", "sample": s["sample"],
                "ransac_hyps_per_s": s["hyps_per_s"], "seconds": s["t_match"] + s["t_ransac"]}
         cpu_ctx = cv2_context(cfg, pair)
-    sharding = ("query rows + hypothesis ids per rank inside liberp_b200.so: ncclAllGather of the match slots, one 8-byte "
-                "ncclAllReduce(max) of the packed best model") if strong else \
+    sharding = ("query rows + hypothesis ids per rank inside liberp_b200.so: all-gather of the match slots, one 8-byte max all-reduce "
+                "of the packed best model -- both by the library's own kernels over NVLink peer-memory windows "
+                "(ERP_B200_PEER=0: ncclAllGather / ncclAllReduce)") if strong else \
                ("one GPU" if world == 1 else "one ERP pair per rank, no collective")
     return {
         "metric": "2nn_dist_evals_per_s", "value": value, "unit": "dist-evals/s", "n_gpus": world, "steps": args.steps,
