@@ -126,6 +126,27 @@ def test_tcgen05_engine_adversarial_inputs(ctx, tc_engine):
     assert np.array_equal(idx, oidx)
 
 
+@pytest.mark.parametrize("engine", [binding.ENGINE_EXACT_SIMT, binding.ENGINE_TCGEN05, binding.ENGINE_TCGEN05_1X])
+@pytest.mark.parametrize("shape", [(300, 400), (5000, 6000)])
+def test_nan_descriptors_never_match(ctx, engine, shape):
+    """A descriptor row holding a NaN compares false against everything (src/feature_matcher.cpp:52 on a NaN distance):
+    such a query has no neighbours (index -1) and emits no record, such a train row is never anyone's neighbour, with
+    and without cross-check, and every other row is unaffected.  Same as the oracle."""
+    nq, nt = shape
+    q, t, _ = synth.descriptor_pair(nq, nt, 64, seed=3)
+    q[5, 7] = np.nan; q[9, :] = np.nan; t[11, 3] = np.nan
+    oidx, _, _ = O.knn2(q, t)
+    assert (oidx[[5, 9]] == -1).all() and not (oidx == 11).any()
+    ctx.set_engine(engine)
+    try:
+        idx, _ = ctx.knn2_raw(q, t)
+        assert np.array_equal(idx, oidx)
+        for ratio, cross in ((0.8, False), (-1.0, True), (0.8, True)):
+            assert ctx.knn2_match(q, t, ratio, cross).tobytes() == O.match(q, t, ratio, cross).tobytes(), (ratio, cross)
+    finally:
+        ctx.set_engine(binding.ENGINE_AUTO)
+
+
 def test_match_edge_cases(ctx):
     q, t, _ = synth.descriptor_pair(10, 5, 64, seed=1)
     assert len(ctx.knn2_match(q[:0], t)) == 0                              # empty query set
