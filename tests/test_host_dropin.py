@@ -110,8 +110,33 @@ def test_reference_callers_compile_and_link_unchanged(tmp_path):
         assert name in syms, name
     usage = subprocess.run([str(exe)], capture_output=True, text=True)
     assert usage.returncode == 0 and "usage:" in usage.stdout
-    # the other mains and manual.cpp need highgui (windows, mouse callbacks): GUI, out of scope; their use of the replaced
-    # classes is the same member set (checked by the symbol list of test_host_classes_build...)
+    # manual.cpp and the GUI test mains (one_image_test, image_rotate_test, manual_*_test) need highgui windows,
+    # trackbars and mouse callbacks: out of scope; the two-image test mains follow below
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference checkout exists only in the build container")
+@pytest.mark.parametrize("main_dir", ["two_real_image_test", "two_synthesis_image_test"])
+def test_reference_test_mains_compile_and_link_unchanged(tmp_path, main_dir):
+    """The reference's own test programs for this path (two_real_image_test/main.cpp: do_all + three find() calls on a real
+    pair; two_synthesis_image_test/main.cpp: the same on a rotated copy) compile and link, unmodified, against the drop-in
+    classes -- copied to a scratch directory at test time together with the reference files that are NOT replaced."""
+    _build()
+    import shutil
+    ref_root = os.path.dirname(REFERENCE)
+    shutil.copy(os.path.join(ref_root, main_dir, "main.cpp"), tmp_path / "main.cpp")
+    for f in ("spherical_surf.cpp", "spherical_surf.hpp", "common_header.hpp", "INIReader.h", "pathkit.hpp"):
+        if os.path.exists(os.path.join(REFERENCE, f)):
+            shutil.copy(os.path.join(REFERENCE, f), tmp_path / f)
+    exe = tmp_path / "main.out"
+    cmd = ["g++", "-std=c++11", "-O1", "-fopenmp", "-w", f"-I{tmp_path}", f"-I{HOST}", f"-I{HOST}/compat", f"-I{ROOT}/include",
+           str(tmp_path / "main.cpp"), str(tmp_path / "spherical_surf.cpp"), os.path.join(HOST, "_build", "liberp_host.a"),
+           f"-L{ROOT}/erp_match_eightpoint_test_b200/lib", "-lerp_b200", f"-Wl,-rpath,{ROOT}/erp_match_eightpoint_test_b200/lib",
+           "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    syms = subprocess.run(["nm", "-C", str(exe)], capture_output=True, text=True).stdout
+    for name in ("feature_matcher::match_two_image", "eight_point::find", "spherical_surf::do_all"):
+        assert name in syms, name
 
 
 def test_rotate_pixel_loops_run_on_the_host(tmp_path):
